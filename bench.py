@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 gravitational force engine.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload direct|tree]
+
+Default workload = BASELINE.json configs[1]: DirectForceComputer, 2^20 particles,
+softened gravity (eps = 0.01), one force evaluation per step.  Metric: pairwise
+interactions/s (N_targets x N_sources per evaluation, self pair included -- it
+contributes exactly 0).  At N > 1 the SAME 2^20-particle problem is target-
+sharded over the ranks (strong scaling): each step all-gathers the source
+positions with NCCL and every rank evaluates its N/G targets against all sources.
+
+`value`  : device-resident throughput (CUDA events on the launching stream,
+           max over ranks, L2 flushed between timed steps).
+`e2e`    : the same metric through the host-pointer C-ABI call
+           (b200_direct_forces_host; pinned host buffers, H2D + D2H inside the
+           timed region).  This is the number to hold against --impl reference.
+`roofline`: dominant kernel (direct_kernel) against the FP32 FMA peak measured
+           in this run by an FFMA probe (MEASURED_PEAKS.json has no FP32 figure).
+`cpu_baseline` / --impl reference: the reference's own CPU direct sum
+           (oracle/_ref = /root/reference sources compiled in place; falls back
+           to the restated port) on all host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "lambda-cdm-raytracing_b200", "python"))
+
+FLOP_PER_INTERACTION = 20          # GPU-Gems-3 convention
+EPS = 0.01
+
+
+# --------------------------------------------------------------------------- inputs
+def make_particles(n, seed=42):
+    """Uniform in [-50,50)^3, unit masses (what every reference generator emits)."""
+    rng = np.random.default_rng(seed)
+    pos = rng.uniform(-50.0, 50.0, size=(n, 3)).astype(np.float32)
+    return pos, np.ones(n, np.float32)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons while the timed region runs."""
+
+    def __init__(self, index=0, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- CPU baseline
+def _ref_worker(args):
+    kind, n, seed, reps = args
+    sys.path.insert(0, ROOT)
+    from oracle.pyoracle import Oracle, Ref
+    pos, _ = make_particles(n, seed)
+    t0 = time.perf_counter()
+    if kind == "reference":
+        r = Ref()
+        for _ in range(reps):
+            r.direct(pos)                      # TreeForceComputer, one root leaf: the CPU direct sum
+    else:
+        os.environ["OMP_NUM_THREADS"] = "1"
+        o = Oracle()
+        for _ in range(reps):
+            o.direct_f32(pos, None, eps=EPS)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_batch(cores, n_sample, reps, pool, kind):
+    """One bounded batch: every core runs the reference's single-threaded CPU direct
+    sum on its own n_sample-particle subsample.  Returns (interactions, seconds)."""
+    t0 = time.perf_counter()
+    list(pool.map(_ref_worker, [(kind, n_sample, 1000 + c, reps) for c in range(cores)]))
+    dt = time.perf_counter() - t0
+    return cores * reps * float(n_sample) * float(n_sample), dt
+
+
+def cpu_kind():
+    from oracle.pyoracle import Ref
+    return "reference" if Ref.available() else "port"
+
+
+def run_cpu_baseline(target_seconds=12.0):
+    from concurrent.futures import ProcessPoolExecutor
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    kind = cpu_kind()
+    n_sample = 16384
+    with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("spawn")) as pool:
+        inter, dt = cpu_reference_batch(cores, 4096, 1, pool, kind)       # warm: page in, spawn
+        rate1 = inter / dt
+        reps = max(1, int(target_seconds * rate1 / (cores * float(n_sample) ** 2)))
+        inter, dt = cpu_reference_batch(cores, n_sample, reps, pool, kind)
+    return {"value": inter / dt, "unit": "interactions/s", "cores": cores, "kind": kind,
+            "sample": f"{cores} independent single-threaded instances of the reference CPU direct sum "
+                      f"(TreeForceComputer, leaf_capacity>N => leaf pair loop), {n_sample} particles each x {reps} "
+                      f"evaluations; {inter:.3e} interactions in {dt:.1f} s"}
+
+
+def bench_reference(args):
+    """--impl reference: the reference's own CPU path, all host cores, bounded steps."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from concurrent.futures import ProcessPoolExecutor
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    kind = cpu_kind()
+    n_sample, reps = 16384, 1
+    times, inter = [], 0.0
+    with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("spawn")) as pool:
+        cpu_reference_batch(cores, 2048, 1, pool, kind)
+        for _ in range(args.warmup):
+            cpu_reference_batch(cores, n_sample, reps, pool, kind)
+        for _ in range(args.steps):
+            inter, dt = cpu_reference_batch(cores, n_sample, reps, pool, kind)
+            times.append(dt)
+    total = sum(times)
+    value = inter * args.steps / total
+    sample = (f"each step = {cores} independent single-threaded instances of the reference CPU direct sum, "
+              f"{n_sample} particles each ({inter:.3e} interactions/step); rate is per-interaction so it "
+              f"transfers to the 2^20 workload")
+    line = {"impl": "reference", "metric": "pairwise_interactions_per_s", "value": value, "unit": "interactions/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    n = args.particles
+    if args.workload == "direct":
+        return {"workload": f"DirectForceComputer, {n} particles (BASELINE configs[1] when n = 2^20), "
+                            f"uniform [-50,50)^3, unit masses, eps = {EPS}, one force evaluation per step; "
+                            f"targets sharded over {args.gpus} GPU(s), sources all-gathered",
+                "particles": n, "eps": EPS, "l2": "flushed between timed steps (512 MB write)"}
+    return {"workload": f"TreeForceComputer Barnes-Hut theta=0.5 leaf=8 max_depth=20, {n} particles "
+                        f"(BASELINE configs[2] scale), uniform [-50,50)^3, build + walk per step",
+            "particles": n, "theta": 0.5, "leaf_capacity": 8, "l2": "flushed between timed steps (512 MB write)"}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def bench_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import b200grav
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = b200grav.Engine(local)
+
+    n = args.particles
+    pos, mass = make_particles(n)
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    nl = hi - lo
+    posm_host = np.ascontiguousarray(np.concatenate([pos, mass[:, None]], 1), np.float32)
+    posm = torch.from_numpy(posm_host).to(dev)             # full source set, resident in HBM
+    shard = posm[lo:hi].clone()                            # this rank's particles (all-gather input)
+    acc = torch.empty((nl, 3), dtype=torch.float32, device=dev)
+    flush = torch.empty(128 * 1024 * 1024, dtype=torch.float32, device=dev)   # 512 MB > 126 MB L2
+    equal_shards = (n % world == 0)
+
+    def gather_sources():
+        if world > 1:
+            if equal_shards:
+                dist.all_gather_into_tensor(posm.view(-1), shard.view(-1))
+            else:
+                outs = [posm[r * n // world:(r + 1) * n // world] for r in range(world)]
+                dist.all_gather(outs, shard)
+
+    def step():
+        gather_sources()
+        if args.workload == "direct":
+            eng.direct_forces_dev(posm, acc, lo, nl, eps=EPS)
+        else:
+            eng.tree_build_dev(posm, n, 100.0, 8, 20)
+            eng.tree_walk_dev(acc, lo, nl, theta=0.5)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # FP32 peak of this GPU, measured now (the roofline denominator)
+    peak_ffma, _ = eng.fp32_peak_probe(0, 4000)
+    peak_ffma2, _ = eng.fp32_peak_probe(1, 4000)
+    peak = max(peak_ffma, peak_ffma2)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    eng.set_timing(True)
+    launches0 = eng.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = []
+    for k in range(args.steps):
+        flush.zero_()                                      # evict L2 (untimed)
+        sync_all()
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+        torch.cuda.synchronize()
+        kernel_ms.append(eng.last_kernel_ms())
+    sync_all()
+    launches = eng.launches - launches0
+    eng.set_timing(False)
+    sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    kern_ms = torch.tensor([float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) * 1e-3
+    kern_s = float(kern_ms.item()) * 1e-3
+
+    # ---- end-to-end through the host-pointer C ABI (pinned host memory) ----
+    pin_pos = torch.from_numpy(pos).pin_memory()
+    pin_mass = torch.from_numpy(mass).pin_memory()
+    pin_out = torch.empty((n if world == 1 else nl, 3), dtype=torch.float32).pin_memory()
+    pin_shard = torch.from_numpy(posm_host[lo:hi].copy()).pin_memory()
+
+    def e2e_step():
+        if world == 1:
+            if args.workload == "direct":
+                eng.direct_forces_host(pin_pos.numpy(), pin_mass.numpy(), eps=EPS, out=pin_out.numpy())
+            else:
+                eng.tree_forces_host(pin_pos.numpy(), pin_mass.numpy(), 0.5, 8, 20, 100.0, out=pin_out.numpy())
+        else:   # each rank owns its shard on the host: H2D shard, all-gather, kernels, D2H shard result
+            shard.copy_(pin_shard, non_blocking=True)
+            step()
+            pin_out.copy_(acc, non_blocking=True)
+            torch.cuda.synchronize()
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    sync_all()
+    t_e2e = []
+    for _ in range(e2e_steps):
+        flush.zero_()
+        sync_all()
+        t0 = time.perf_counter()
+        e2e_step()
+        torch.cuda.synchronize()
+        t_e2e.append(time.perf_counter() - t0)
+    e2e_t = torch.tensor([sum(t_e2e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_t.item())
+
+    clocks = sampler.summary()
+
+    if args.workload == "direct":
+        per_step = float(n) * float(n)                      # whole job: all targets x all sources
+        per_launch = float(nl) * float(n)                   # this rank's main kernel
+    else:
+        eng.tree_set_counting(True)
+        eng.tree_walk_dev(acc, lo, nl, theta=0.5)
+        torch.cuda.synchronize()
+        cnt = eng.tree_counters()
+        eng.tree_set_counting(False)
+        c = torch.tensor([float(cnt[1] + cnt[2])], dtype=torch.float64, device=dev)
+        per_launch = float(c.item())
+        if world > 1:
+            dist.all_reduce(c)
+        per_step = float(c.item())
+
+    if rank == 0:
+        value = per_step * args.steps / total_s
+        e2e_value = per_step * e2e_steps / e2e_s
+        achieved = FLOP_PER_INTERACTION * per_launch / kern_s / 1e12
+        line = {
+            "metric": "pairwise_interactions_per_s", "value": value, "unit": "interactions/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "particle_steps_per_s": float(n) * args.steps / total_s,
+            "e2e": {"value": e2e_value, "unit": "interactions/s",
+                    "h2d_bytes_per_step": int(16 * n) if world == 1 else int(16 * nl) * world,
+                    "d2h_bytes_per_step": int(12 * n), "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                    "api": "b200_direct_forces_host (pinned host buffers)" if world == 1 else
+                           "per-rank pinned shard H2D + NCCL all-gather + b200_direct_forces_dev + D2H"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {
+                "bound": "fp32_fma", "kernel": "direct_kernel<4,false>" if args.workload == "direct" else "walk_kernel",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None,
+                "peak_source": "FFMA/FFMA2 register-chain probe run in this process (b200_fp32_peak_probe); "
+                               "MEASURED_PEAKS.json has no FP32 figure",
+                "peak_ffma": peak_ffma, "peak_ffma2": peak_ffma2,
+                "nominal_peak": 148 * 128 * 2 * (clocks.get("sm_max_mhz") or 1965) * 1e6 / 1e12,
+                "flop_per_interaction": FLOP_PER_INTERACTION,
+                "kernel_ms": 1e3 * kern_s,
+            },
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = run_cpu_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="direct", choices=["direct", "tree"])
+    ap.add_argument("--particles", type=int, default=1 << 20)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        bench_reference(args)
+    else:
+        bench_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,192 @@
+/*
+ * b200grav.h -- C ABI of libb200grav.so, the B200 (sm_100a) gravitational
+ * force engine that sits behind the reference's IForceComputer plugin API.
+ *
+ * Plain C: opaque handle, plain pointers and sizes, int status on every call
+ * (0 = ok, otherwise a b200_status / cudaError_t+1000 / ncclResult_t+2000 --
+ * see b200_error_string).  Nothing throws.  No torch, no TensorRT, no CPU
+ * fallback: every compute entry point fails with B200_ERR_NO_DEVICE when no
+ * sm_100 GPU is usable.
+ *
+ * "_host" entry points take HOST pointers in the reference's IForceComputer
+ * layout (positions float[3N] AoS xyz, masses float[N], forces float[3N];
+ * /root/reference include/core/interfaces.hpp:31-40) and do H2D, kernels, D2H.
+ * "_dev" entry points take DEVICE pointers and a cudaStream_t (as void*),
+ * in the reference's device layout (float4 x,y,z,m positions; 3 floats per
+ * particle for velocities and forces; src/physics/lambda_cdm_impl.cu:65-68).
+ *
+ * Each entry point cites the reference interface it replaces.
+ */
+#ifndef B200GRAV_H
+#define B200GRAV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200GRAV_ABI_VERSION 1
+
+typedef struct b200_ctx b200_ctx;
+
+enum b200_status {
+    B200_OK = 0,
+    B200_ERR_INVALID = 1,      /* bad argument (null pointer, eps <= 0, n > capacity ...) */
+    B200_ERR_NO_DEVICE = 2,    /* no CUDA device / not an sm_100 part */
+    B200_ERR_STATE = 3,        /* call out of order (walk before build ...) */
+    B200_ERR_NOMEM = 4,
+    B200_ERR_UNSUPPORTED = 5
+    /* 1000 + cudaError_t, 2000 + ncclResult_t */
+};
+
+const char* b200_error_string(int status);
+int b200_abi_version(void);
+
+/* ---- context -------------------------------------------------------------
+ * Replaces the per-object device state of the reference's computers:
+ * TreeForceComputer::initialize_gpu_resources / cleanup_gpu_resources
+ * (src/forces/tree_force_computer.cpp:349-408), BarnesHutTree ctor/dtor
+ * (src/forces/barnes_hut_tree.cu:343-381), LambdaCDMSimulationImpl ctor/dtor
+ * (src/physics/lambda_cdm_impl.cu:80-145).  device = ForceComputeParameters::
+ * cuda_device_id (include/forces/force_computer_factory.hpp:39).  Scratch
+ * grows on demand; max_particles is a sizing hint (0 = grow lazily). */
+int b200_ctx_create(int device, size_t max_particles, b200_ctx** out);
+int b200_ctx_destroy(b200_ctx* ctx);
+int b200_ctx_device(const b200_ctx* ctx);
+int b200_ctx_sm_count(const b200_ctx* ctx);
+/* Blocks until all work queued on stream (NULL = the context's own stream) is done. */
+int b200_ctx_sync(b200_ctx* ctx, void* stream);
+
+/* ---- direct sum (rows D1-D3) ---------------------------------------------
+ * acc_i = sum_j m_j d / (|d|^2 + eps^2)^{3/2}, d = x_j - x_i, G = 1; output is
+ * ACCELERATION (what TreeForceComputer writes), overwritten.
+ * box > 0 selects the periodic minimum-image variant of compute_forces_direct
+ * (src/physics/lambda_cdm_kernels.cu:14-56); box == 0 is the open-boundary sum
+ * of the CPU leaf loop (src/forces/tree_force_computer.cpp:312-347).
+ *
+ * _host replaces IForceComputer::compute_forces for "DirectForceComputer"
+ * (include/core/interfaces.hpp:33-35; name reserved at
+ * src/forces/force_computer_factory.cpp:40-43).  mass == NULL means unit mass. */
+int b200_direct_forces_host(b200_ctx* ctx, const float* pos3, const float* mass,
+                            float* acc3, size_t n, float eps, float box);
+/* _dev replaces launch_force_computation (src/physics/lambda_cdm_kernels.cu:
+ * 444-468) and launch_nbody_force_kernel (src/tensorrt/nbody_plugins.cu:175-191).
+ * posm4: float4[n_sources]; targets are posm4[i0 .. i0+n_targets); acc3:
+ * float[3*n_targets].  This is the target-sharded form used on >1 GPU. */
+int b200_direct_forces_dev(b200_ctx* ctx, const void* posm4, size_t n_sources,
+                           size_t i0, size_t n_targets, float eps, float box,
+                           void* acc3, void* stream);
+/* Tile-SoA source format of the direct-sum kernel: [tile][x|y|z|m][512] floats,
+ * 8 KB per 512 sources (slots past n hold zero-mass sources).  One TMA bulk copy
+ * per tile.  b200_tiles_bytes(n) bytes hold n particles. */
+size_t b200_tiles_bytes(size_t n);
+int b200_pack_tiles_dev(b200_ctx* ctx, const void* posm4, size_t n, void* tiles, void* stream);
+/* Direct sum with the sources supplied as `n_parts` (<= 16) tile-SoA buffers of
+ * part_len[p] particles each, concatenated in order.  Buffers may live on PEER
+ * GPUs (NVLink-mapped, see b200_ipc_*): the kernel pulls its source tiles
+ * straight over NVLink, so no all-gather precedes it.  Targets are local:
+ * targets4 float4[n_targets], acc3 float[3*n_targets]. */
+int b200_direct_forces_parts_dev(b200_ctx* ctx, const void* const* parts,
+                                 const size_t* part_len, int n_parts,
+                                 const void* targets4, size_t n_targets,
+                                 float eps, float box, void* acc3, void* stream);
+
+/* ---- Barnes-Hut (rows T1-T6) ----------------------------------------------
+ * Morton keys: replaces compute_morton_codes_kernel + morton3D
+ * (src/forces/barnes_hut_tree.cu:33-55, include/forces/barnes_hut_tree.hpp:11-27);
+ * IEEE divide, so device keys equal the host function bit for bit. */
+int b200_morton_keys_dev(b200_ctx* ctx, const void* posm4, size_t n, float box,
+                         void* keys_u32, void* stream);
+/* Stable ascending (key, index) sort: replaces thrust::sequence + sort_by_key
+ * (src/forces/barnes_hut_tree.cu:358,383-401).  keys_in is not modified. */
+int b200_sort_pairs_dev(b200_ctx* ctx, const void* keys_in_u32, size_t n,
+                        void* keys_out_u32, void* perm_out_i32, void* stream);
+/* Octree build + centre of mass: replaces TreeForceComputer::build_tree_cpu
+ * (src/forces/tree_force_computer.cpp:130-243) -- same tree, node for node:
+ * root cube centred on the origin with edge `box`, first leaf_cap arrivals stay
+ * in a node when it splits, strict > octant test, float centre recurrence. */
+int b200_tree_build_dev(b200_ctx* ctx, const void* posm4, size_t n, float box,
+                        int leaf_cap, int max_depth, void* stream);
+/* Walk: replaces compute_tree_forces / compute_force_on_particle
+ * (src/forces/tree_force_computer.cpp:245-347): accept iff size/|com-x| < theta,
+ * eps = 0.01f monopole and unit-mass leaf pairs.  Targets posm4[i0..i0+n_targets)
+ * of the array the tree was built from. acc3: float[3*n_targets]. */
+int b200_tree_walk_dev(b200_ctx* ctx, size_t i0, size_t n_targets, float theta,
+                       void* acc3, void* stream);
+/* IForceComputer::compute_forces for "TreeForceComputer" on host arrays. */
+int b200_tree_forces_host(b200_ctx* ctx, const float* pos3, const float* mass,
+                          float* acc3, size_t n, float theta, int leaf_cap,
+                          int max_depth, float box);
+
+/* Tree introspection (TreeForceComputer::get_node_count / get_leaf_count /
+ * get_tree_depth, src/forces/tree_force_computer.cpp:410-464) and a canonical
+ * breadth-first export for the bit-exact topology check.  Sizes first, then
+ * export into caller-allocated HOST arrays (any pointer may be NULL to skip):
+ *   level i32[n_nodes], center f32[3*n_nodes], size f32[n_nodes],
+ *   first_child i32[n_nodes] (-1 = leaf), arrivals i64[n_nodes],
+ *   part_off i64[n_nodes+1], part_idx i32[n_stored] (leaf members / orphans in
+ *   arrival order), mass f32[n_nodes], com f32[3*n_nodes]. */
+int b200_tree_stats(b200_ctx* ctx, size_t* n_nodes, size_t* n_leaves,
+                    size_t* depth, size_t* n_stored);
+int b200_tree_export(b200_ctx* ctx, int32_t* level, float* center, float* size,
+                     int32_t* first_child, int64_t* arrivals, int64_t* part_off,
+                     int32_t* part_idx, float* mass, float* com);
+/* Walk counters of the last b200_tree_walk_dev with counting enabled:
+ * [0] nodes visited, [1] monopole, [2] leaf pair interactions. */
+int b200_tree_set_counting(b200_ctx* ctx, int enabled);
+int b200_tree_counters(b200_ctx* ctx, uint64_t counters[3]);
+
+/* ---- leapfrog (rows L1-L3) -------------------------------------------------
+ * Replaces leapfrog_update / launch_leapfrog_update
+ * (src/physics/lambda_cdm_kernels.cu:290-335, 470-490) and the kick/drift
+ * sequencing of LambdaCDMSimulationImpl::step (src/physics/lambda_cdm_impl.cu:
+ * 167-213) with ONE pass over the particles:
+ *     n_kicks times: v += (acc*m) * (1/m) * dt_kick * (1/a^2)      (:307-318)
+ *     if dt_drift != 0: x += v*dt_drift; x = fmodf(x + box, box)   (:321-333)
+ * n_kicks = 2 fuses the closing half-kick of step s with the opening half-kick
+ * of step s+1 (same scale factor a in between) and the drift that follows.
+ * box <= 0 disables the wrap.  a is the scale factor (double, as :296). */
+int b200_leapfrog_dev(b200_ctx* ctx, void* posm4, void* vel3, const void* acc3,
+                      size_t n, int n_kicks, float dt_kick, double a,
+                      float dt_drift, float box, void* stream);
+/* CosmologyModel::hubble_parameter_a (include/physics/cosmology_model.hpp:49-61)
+ * and LambdaCDMSimulationImpl::update_scale_factor (lambda_cdm_impl.cu:261-269);
+ * host scalars, double precision. */
+double b200_hubble_a(double a, double omega_m, double omega_k, double omega_lambda, double h);
+double b200_scale_factor_step(double a, double dt, double omega_m, double omega_k,
+                              double omega_lambda, double h);
+
+/* ---- layout helpers --------------------------------------------------------
+ * pos3 + mass (device) -> float4 x,y,z,m (device); mass == NULL -> 1. */
+int b200_pack_posm_dev(b200_ctx* ctx, const void* pos3, const void* mass, size_t n,
+                       void* posm4, void* stream);
+
+/* ---- multi-GPU (row e) -----------------------------------------------------
+ * Target-sharded data parallelism: rank r owns targets [r*N/G, (r+1)*N/G);
+ * sources are all-gathered (semantic ancestor: ClusterCommunicator::
+ * gather_all_particles, src/mpi/cluster_comm.cpp:218-247) -- either by the
+ * caller's NCCL (torch.distributed) or pulled over NVLink by
+ * b200_direct_forces_parts_dev from peer buffers mapped with these calls.
+ * handle is a 64-byte cudaIpcMemHandle_t. */
+int b200_ipc_export(b200_ctx* ctx, void* dev_ptr, unsigned char handle[64]);
+int b200_ipc_open(b200_ctx* ctx, const unsigned char handle[64], void** dev_ptr);
+int b200_ipc_close(b200_ctx* ctx, void* dev_ptr);
+
+/* ---- measurement -----------------------------------------------------------
+ * FP32 pipe probe for the roofline denominator (MEASURED_PEAKS.json has no
+ * FP32 number): runs a register-resident FFMA chain on every SM and returns
+ * achieved TFLOP/s (2 flop per FMA lane).  mode 0 = FFMA, 1 = FFMA2 (f32x2). */
+int b200_fp32_peak_probe(b200_ctx* ctx, int mode, int iters, double* tflops, float* ms);
+/* Device time (ms) of the last direct / tree call's main kernel, measured with
+ * CUDA events on the stream it ran on; and the number of kernel launches this
+ * context has issued since creation. */
+int b200_last_kernel_ms(b200_ctx* ctx, float* ms);
+int b200_set_timing(b200_ctx* ctx, int enabled);
+uint64_t b200_launch_count(const b200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,326 @@
+// capi.cu -- the extern "C" surface of libb200grav.so (include/b200grav.h).
+#include <math.h>
+#include <new>
+#include <string.h>
+
+#include "common.cuh"
+#include "direct.cuh"
+#include "leapfrog.cuh"
+#include "probe.cuh"
+#include "sort.cuh"
+#include "tree.cuh"
+
+using namespace b200;
+
+static inline cudaStream_t pick_stream(b200_ctx* ctx, void* stream) {
+    return stream ? (cudaStream_t)stream : ctx->stream;
+}
+
+extern "C" {
+
+const char* b200_error_string(int status) {
+    switch (status) {
+        case B200_OK: return "ok";
+        case B200_ERR_INVALID: return "invalid argument";
+        case B200_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (there is no CPU fallback)";
+        case B200_ERR_STATE: return "call out of order";
+        case B200_ERR_NOMEM: return "device allocation failed";
+        case B200_ERR_UNSUPPORTED: return "unsupported configuration";
+        default: break;
+    }
+    if (status >= 1000 && status < 2000) return cudaGetErrorString((cudaError_t)(status - 1000));
+    return "unknown b200grav status";
+}
+
+int b200_abi_version(void) { return B200GRAV_ABI_VERSION; }
+
+int b200_ctx_create(int device, size_t max_particles, b200_ctx** out) {
+    if (!out) return B200_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return B200_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) return B200_ERR_INVALID;
+    cudaDeviceProp prop;
+    B200_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return B200_ERR_NO_DEVICE;     // sm_100a SASS only
+    B200_CUDA(cudaSetDevice(device));
+    b200_ctx* ctx = new (std::nothrow) b200_ctx();
+    if (!ctx) return B200_ERR_NOMEM;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    B200_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    B200_CUDA(cudaEventCreate(&ctx->ev0));
+    B200_CUDA(cudaEventCreate(&ctx->ev1));
+    if (max_particles) {
+        int s = ctx->src_tiles.reserve(direct_tiles_bytes(max_particles));
+        if (s != B200_OK) { b200_ctx_destroy(ctx); return s; }
+    }
+    *out = ctx;
+    return B200_OK;
+}
+
+int b200_ctx_destroy(b200_ctx* ctx) {
+    if (!ctx) return B200_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    tree_destroy(ctx);
+    ctx->src_tiles.release(); ctx->partials.release(); ctx->part_table.release();
+    ctx->h_pos3.release(); ctx->h_mass.release(); ctx->h_posm4.release(); ctx->h_acc3.release();
+    ctx->probe.release(); ctx->sort_scratch.release();
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return B200_OK;
+}
+
+int b200_ctx_device(const b200_ctx* ctx) { return ctx ? ctx->device : -1; }
+int b200_ctx_sm_count(const b200_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+int b200_ctx_sync(b200_ctx* ctx, void* stream) {
+    if (!ctx) return B200_ERR_INVALID;
+    B200_CUDA(cudaStreamSynchronize(pick_stream(ctx, stream)));
+    return B200_OK;
+}
+
+// ---- direct ---------------------------------------------------------------
+int b200_direct_forces_dev(b200_ctx* ctx, const void* posm4, size_t n_sources, size_t i0,
+                           size_t n_targets, float eps, float box, void* acc3, void* stream) {
+    if (!ctx) return B200_ERR_INVALID;
+    if (n_targets == 0) return B200_OK;
+    if (!posm4 || !acc3 || i0 + n_targets > n_sources) return B200_ERR_INVALID;
+    if (!(eps > 0.f) || box < 0.f) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick_stream(ctx, stream);
+    B200_TRY(ctx->src_tiles.reserve(direct_tiles_bytes(n_sources)));
+    B200_TRY(direct_pack_tiles(ctx, posm4, n_sources, ctx->src_tiles.as<float>(), st));
+    DirectSources src;
+    memset(&src, 0, sizeof src);
+    src.n_parts = 1;
+    src.tiles[0] = ctx->src_tiles.as<float>();
+    src.total_tiles = src.tile_end[0] = (int)((n_sources + DIRECT_TILE_J - 1) / DIRECT_TILE_J);
+    return direct_forces(ctx, src, (const float4*)posm4 + i0, n_targets, eps, box, acc3, st);
+}
+
+size_t b200_tiles_bytes(size_t n) { return direct_tiles_bytes(n); }
+
+int b200_pack_tiles_dev(b200_ctx* ctx, const void* posm4, size_t n, void* tiles, void* stream) {
+    if (!ctx || (n && (!posm4 || !tiles))) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return direct_pack_tiles(ctx, posm4, n, (float*)tiles, pick_stream(ctx, stream));
+}
+
+int b200_direct_forces_parts_dev(b200_ctx* ctx, const void* const* parts, const size_t* part_len,
+                                 int n_parts, const void* targets4, size_t n_targets, float eps,
+                                 float box, void* acc3, void* stream) {
+    if (!ctx) return B200_ERR_INVALID;
+    if (n_targets == 0) return B200_OK;
+    if (!parts || !part_len || n_parts < 1 || n_parts > DIRECT_MAX_PARTS || !targets4 || !acc3)
+        return B200_ERR_INVALID;
+    if (!(eps > 0.f) || box < 0.f) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    DirectSources src;
+    memset(&src, 0, sizeof src);
+    int total = 0, np = 0;
+    for (int p = 0; p < n_parts; ++p) {
+        int nt = (int)((part_len[p] + DIRECT_TILE_J - 1) / DIRECT_TILE_J);
+        if (nt == 0) continue;
+        if (!parts[p]) return B200_ERR_INVALID;
+        total += nt;
+        src.tiles[np] = (const float*)parts[p];
+        src.tile_end[np] = total;
+        ++np;
+    }
+    src.n_parts = np;
+    src.total_tiles = total;
+    return direct_forces(ctx, src, targets4, n_targets, eps, box, acc3, pick_stream(ctx, stream));
+}
+
+int b200_direct_forces_host(b200_ctx* ctx, const float* pos3, const float* mass, float* acc3,
+                            size_t n, float eps, float box) {
+    if (!ctx) return B200_ERR_INVALID;
+    if (n == 0) return B200_OK;            // tree_force_computer.cpp:83
+    if (!pos3 || !acc3) return B200_ERR_INVALID;
+    if (!(eps > 0.f) || box < 0.f) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    B200_TRY(ctx->h_pos3.reserve(n * 3 * sizeof(float)));
+    B200_TRY(ctx->h_posm4.reserve(n * 4 * sizeof(float)));
+    B200_TRY(ctx->h_acc3.reserve(n * 3 * sizeof(float)));
+    B200_CUDA(cudaMemcpyAsync(ctx->h_pos3.p, pos3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    const float* d_mass = nullptr;
+    if (mass) {
+        B200_TRY(ctx->h_mass.reserve(n * sizeof(float)));
+        B200_CUDA(cudaMemcpyAsync(ctx->h_mass.p, mass, n * sizeof(float), cudaMemcpyHostToDevice, st));
+        d_mass = ctx->h_mass.as<float>();
+    }
+    B200_TRY(pack_posm(ctx, ctx->h_pos3.p, d_mass, n, ctx->h_posm4.p, st));
+    B200_TRY(b200_direct_forces_dev(ctx, ctx->h_posm4.p, n, 0, n, eps, box, ctx->h_acc3.p, st));
+    B200_CUDA(cudaMemcpyAsync(acc3, ctx->h_acc3.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+
+// ---- Barnes-Hut -------------------------------------------------------------
+int b200_morton_keys_dev(b200_ctx* ctx, const void* posm4, size_t n, float box, void* keys_u32,
+                         void* stream) {
+    if (!ctx || (n && (!posm4 || !keys_u32))) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return morton_keys(ctx, posm4, n, box, (uint32_t*)keys_u32, pick_stream(ctx, stream));
+}
+
+int b200_sort_pairs_dev(b200_ctx* ctx, const void* keys_in_u32, size_t n, void* keys_out_u32,
+                        void* perm_out_i32, void* stream) {
+    if (!ctx || (n && (!keys_in_u32 || !keys_out_u32 || !perm_out_i32))) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    B200_TRY(ctx->sort_scratch.reserve(sort_scratch_bytes(n)));
+    return sort_pairs(ctx, (const uint32_t*)keys_in_u32, n, (uint32_t*)keys_out_u32,
+                      (int32_t*)perm_out_i32, 32, ctx->sort_scratch.p, pick_stream(ctx, stream));
+}
+
+int b200_tree_build_dev(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_cap,
+                        int max_depth, void* stream) {
+    if (!ctx) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return tree_build(ctx, posm4, n, box, leaf_cap, max_depth, pick_stream(ctx, stream));
+}
+
+int b200_tree_walk_dev(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* acc3,
+                       void* stream) {
+    if (!ctx) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return tree_walk(ctx, i0, n_targets, theta, acc3, pick_stream(ctx, stream));
+}
+
+int b200_tree_forces_host(b200_ctx* ctx, const float* pos3, const float* mass, float* acc3, size_t n,
+                          float theta, int leaf_cap, int max_depth, float box) {
+    if (!ctx) return B200_ERR_INVALID;
+    if (n == 0) return B200_OK;            // tree_force_computer.cpp:83
+    if (!pos3 || !mass || !acc3) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    B200_TRY(ctx->h_pos3.reserve(n * 3 * sizeof(float)));
+    B200_TRY(ctx->h_mass.reserve(n * sizeof(float)));
+    B200_TRY(ctx->h_posm4.reserve(n * 4 * sizeof(float)));
+    B200_TRY(ctx->h_acc3.reserve(n * 3 * sizeof(float)));
+    B200_CUDA(cudaMemcpyAsync(ctx->h_pos3.p, pos3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(ctx->h_mass.p, mass, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    B200_TRY(pack_posm(ctx, ctx->h_pos3.p, ctx->h_mass.p, n, ctx->h_posm4.p, st));
+    B200_TRY(tree_build(ctx, ctx->h_posm4.p, n, box, leaf_cap, max_depth, st));
+    B200_TRY(tree_walk(ctx, 0, n, theta, ctx->h_acc3.p, st));
+    B200_CUDA(cudaMemcpyAsync(acc3, ctx->h_acc3.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+int b200_tree_stats(b200_ctx* ctx, size_t* n_nodes, size_t* n_leaves, size_t* depth, size_t* n_stored) {
+    if (!ctx) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return tree_stats(ctx, n_nodes, n_leaves, depth, n_stored);
+}
+
+int b200_tree_export(b200_ctx* ctx, int32_t* level, float* center, float* size, int32_t* first_child,
+                     int64_t* arrivals, int64_t* part_off, int32_t* part_idx, float* mass, float* com) {
+    if (!ctx) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return tree_export(ctx, level, center, size, first_child, arrivals, part_off, part_idx, mass, com);
+}
+
+int b200_tree_set_counting(b200_ctx* ctx, int enabled) {
+    if (!ctx) return B200_ERR_INVALID;
+    return tree_set_counting(ctx, enabled);
+}
+
+int b200_tree_counters(b200_ctx* ctx, uint64_t counters[3]) {
+    if (!ctx || !counters) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return tree_counters(ctx, counters);
+}
+
+// ---- leapfrog ---------------------------------------------------------------
+int b200_leapfrog_dev(b200_ctx* ctx, void* posm4, void* vel3, const void* acc3, size_t n,
+                      int n_kicks, float dt_kick, double a, float dt_drift, float box, void* stream) {
+    if (!ctx) return B200_ERR_INVALID;
+    if (n == 0) return B200_OK;
+    if (!posm4 || !vel3 || !acc3) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return leapfrog(ctx, posm4, vel3, acc3, n, n_kicks, dt_kick, a, dt_drift, box,
+                    pick_stream(ctx, stream));
+}
+
+// include/physics/cosmology_model.hpp:49-61: H(z) with a = 1/(1+z), z = 1/a - 1.
+double b200_hubble_a(double a, double omega_m, double omega_k, double omega_lambda, double h) {
+    const double z = 1.0 / a - 1.0;
+    const double aa = 1.0 / (1.0 + z);
+    const double e2 = omega_m * pow(aa, -3) + omega_k * pow(aa, -2) + omega_lambda;
+    return 100.0 * h * sqrt(e2);
+}
+
+// src/physics/lambda_cdm_impl.cu:261-269: a += a * H(a) * dt (H in km/s/Mpc, as the reference).
+double b200_scale_factor_step(double a, double dt, double omega_m, double omega_k,
+                              double omega_lambda, double h) {
+    return a + a * b200_hubble_a(a, omega_m, omega_k, omega_lambda, h) * dt;
+}
+
+int b200_pack_posm_dev(b200_ctx* ctx, const void* pos3, const void* mass, size_t n, void* posm4,
+                       void* stream) {
+    if (!ctx || (n && (!pos3 || !posm4))) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return pack_posm(ctx, pos3, mass, n, posm4, pick_stream(ctx, stream));
+}
+
+// ---- multi-GPU peer mapping ------------------------------------------------
+int b200_ipc_export(b200_ctx* ctx, void* dev_ptr, unsigned char handle[64]) {
+    if (!ctx || !dev_ptr || !handle) return B200_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    B200_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    B200_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle, &h, 64);
+    return B200_OK;
+}
+
+int b200_ipc_open(b200_ctx* ctx, const unsigned char handle[64], void** dev_ptr) {
+    if (!ctx || !handle || !dev_ptr) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    B200_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return B200_OK;
+}
+
+int b200_ipc_close(b200_ctx* ctx, void* dev_ptr) {
+    if (!ctx || !dev_ptr) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    B200_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return B200_OK;
+}
+
+// ---- measurement -------------------------------------------------------------
+int b200_fp32_peak_probe(b200_ctx* ctx, int mode, int iters, double* tflops, float* ms) {
+    if (!ctx) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return fp32_peak_probe(ctx, mode, iters, tflops, ms);
+}
+
+int b200_set_timing(b200_ctx* ctx, int enabled) {
+    if (!ctx) return B200_ERR_INVALID;
+    ctx->timing = enabled != 0;
+    return B200_OK;
+}
+
+int b200_last_kernel_ms(b200_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return B200_ERR_INVALID;
+    if (!ctx->timing) return B200_ERR_STATE;
+    B200_CUDA(cudaEventSynchronize(ctx->ev1));
+    B200_CUDA(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return B200_OK;
+}
+
+uint64_t b200_launch_count(const b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// common.cuh -- context, error plumbing and small device helpers shared by the
+// sm_100a kernels of libb200grav.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "b200grav.h"
+
+#define B200_CUDA(call)                                   \
+    do {                                                  \
+        cudaError_t e__ = (call);                         \
+        if (e__ != cudaSuccess) return 1000 + (int)e__;   \
+    } while (0)
+
+#define B200_TRY(call)                  \
+    do {                                \
+        int s__ = (call);               \
+        if (s__ != B200_OK) return s__; \
+    } while (0)
+
+// A growable device buffer owned by the context.
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t need) {
+        if (need <= bytes) return B200_OK;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        size_t want = need + need / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { cudaGetLastError(); return B200_ERR_NOMEM; }
+        bytes = want;
+        return B200_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+namespace b200 { struct TreeState; }   // tree.cu
+
+struct b200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;        // the context's own stream (host entry points)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timing = false;
+    float last_ms = 0.f;
+    uint64_t launches = 0;
+
+    // direct sum scratch
+    DevBuf src_tiles;       // tile-SoA sources
+    DevBuf partials;        // per (CTA, target block) partial accelerations
+    DevBuf part_table;      // device copy of the source-part descriptor table
+    // host-entry staging
+    DevBuf h_pos3, h_mass, h_posm4, h_acc3;
+    // probe / standalone sort scratch
+    DevBuf probe, sort_scratch;
+
+    b200::TreeState* tree = nullptr;
+};
+
+static inline int ceil_div_i(long long a, long long b) { return (int)((a + b - 1) / b); }

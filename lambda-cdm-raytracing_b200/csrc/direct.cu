@@ -1,0 +1,370 @@
+// direct.cu -- softened direct-sum gravity for sm_100a (rows D1-D3 of SURVEY 8a).
+//
+// Replaces: the CPU leaf pair loop (reference src/forces/tree_force_computer.cpp:
+// 312-347), compute_forces_direct / compute_forces_tiled
+// (src/physics/lambda_cdm_kernels.cu:14-56, 144-221) and nbody_force_kernel_shared
+// (src/tensorrt/nbody_plugins.cu:53-129).  Not a translation of any of them:
+//
+//  * sources live in HBM as 8 KB tile-SoA blocks  [tile][x|y|z|m][512]  so one
+//    TMA bulk copy (cp.async.bulk + mbarrier, SASS UBLKCP) lands a tile in
+//    shared memory already split by component;
+//  * the inner loop is written in packed FP32 (fma/mul/add .f32x2 -> FFMA2 /
+//    FMUL2 / FADD2): one instruction handles the SAME target against TWO
+//    consecutive sources, whose x/y/z/m pairs are adjacent 64-bit words of the
+//    smem tile, so no register shuffling is needed; each LDS.128 broadcast
+//    feeds 4 sources x R register-blocked targets;
+//  * 12 FP32-pipe lane-ops + 1 MUFU.RSQ per interaction (3 sub, 3 fma for
+//    r^2+eps^2, rsqrt, 3 mul for m*rinv^3, 3 fma accumulate); no i==j branch
+//    (eps > 0 makes the self term exactly 0);
+//  * the (target block x source tile) work space is flattened and cut into
+//    gridDim.x equal contiguous spans, gridDim.x = SMs x resident CTAs, so
+//    there is no tail wave for any N; a span that crosses target-block
+//    boundaries writes one partial record per block, and a finalize pass adds
+//    the (few) records of a block in fixed order -> deterministic results;
+//  * per-tile FP32 partial sums are folded into FP64 running sums, so the
+//    round-off does not grow like sqrt(N_sources) (the sequential FP32 CPU
+//    loop is 8.6e-6 from FP64 truth at 64 K sources already).
+#include "common.cuh"
+#include "direct.cuh"
+
+namespace b200 {
+
+namespace {
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk(u64 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier.
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// -------------------------------------------------------------------------
+// float4 (x,y,z,m) -> tile-SoA.  Slots past n are zero-mass sources at the
+// origin: they contribute exactly 0 because eps > 0.
+__global__ void pack_tiles_kernel(const float4* __restrict__ posm, long long n, long long n_padded,
+                                  float* __restrict__ tiles) {
+    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_padded) return;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < n) p = posm[j];
+    long long t = j / DIRECT_TILE_J;
+    int o = (int)(j % DIRECT_TILE_J);
+    float* base = tiles + t * (4 * DIRECT_TILE_J) + o;
+    base[0 * DIRECT_TILE_J] = p.x;
+    base[1 * DIRECT_TILE_J] = p.y;
+    base[2 * DIRECT_TILE_J] = p.z;
+    base[3 * DIRECT_TILE_J] = p.w;
+}
+
+constexpr int STAGES = 4;
+constexpr int THREADS = DIRECT_THREADS;
+constexpr int TILE_J = DIRECT_TILE_J;
+constexpr int TILE_FLOATS = 4 * TILE_J;
+constexpr uint32_t TILE_BYTES = TILE_FLOATS * sizeof(float);
+
+__device__ __forceinline__ const float* tile_ptr(const DirectSources& src, int t) {
+    int p = 0, base = 0;
+#pragma unroll 1
+    while (p < src.n_parts - 1 && t >= src.tile_end[p]) { base = src.tile_end[p]; ++p; }
+    return src.tiles[p] + (size_t)(t - base) * TILE_FLOATS;
+}
+
+template <int R, bool PERIODIC>
+__global__ void __launch_bounds__(THREADS, (R <= 4 ? 2 : 1))
+direct_kernel(const DirectSources src, const float4* __restrict__ targets, long long n_targets,
+              float eps2, float box, double* __restrict__ partials, long long n_units, int n_tiles) {
+    constexpr int BLOCK_I = THREADS * R;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* stage_buf = reinterpret_cast<float*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * TILE_BYTES);
+
+    const int tid = threadIdx.x;
+    const long long G = gridDim.x, c = blockIdx.x;
+    const long long u0 = (c * n_units) / G, u1 = ((c + 1) * n_units) / G;
+    if (u0 >= u1) return;
+    const long long my_units = u1 - u0;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    long long b = u0 / n_tiles;          // current target block
+    int t = (int)(u0 % n_tiles);         // current source tile
+
+    if (tid == 0) {
+        int tt = t;
+        for (int k = 0; k < STAGES - 1 && k < my_units; ++k) {
+            mbar_expect_tx(&full[k], TILE_BYTES);
+            tma_load_1d(stage_buf + k * TILE_FLOATS, tile_ptr(src, tt), TILE_BYTES, &full[k]);
+            if (++tt == n_tiles) tt = 0;
+        }
+    }
+    int t_issue = (int)((u0 + (STAGES - 1)) % n_tiles);   // tile of unit k + STAGES-1
+
+    const u64 eps2_2 = pk(eps2, eps2);
+    u64 nxi[R], nyi[R], nzi[R];          // packed (-x_i, -x_i) per register-blocked target
+    double dax[R], day[R], daz[R];
+    auto load_targets = [&](long long blk) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            long long i = blk * BLOCK_I + r * THREADS + tid;
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n_targets) p = targets[i];
+            nxi[r] = pk(-p.x, -p.x);
+            nyi[r] = pk(-p.y, -p.y);
+            nzi[r] = pk(-p.z, -p.z);
+            dax[r] = day[r] = daz[r] = 0.0;
+        }
+    };
+    load_targets(b);
+
+    [[maybe_unused]] u64 inv_box2, magic2, nmagic2, nbox2;
+    if constexpr (PERIODIC) {
+        float ib = 1.0f / box;
+        inv_box2 = pk(ib, ib);
+        magic2 = pk(12582912.0f, 12582912.0f);      // 1.5 * 2^23: round-to-nearest-integer trick
+        nmagic2 = pk(-12582912.0f, -12582912.0f);
+        nbox2 = pk(-box, -box);
+    }
+
+    for (long long k = 0; k < my_units; ++k) {
+        const int s = (int)(k % STAGES);
+        if (tid == 0 && k + (STAGES - 1) < my_units) {
+            const int sn = (int)((k + STAGES - 1) % STAGES);
+            mbar_expect_tx(&full[sn], TILE_BYTES);
+            tma_load_1d(stage_buf + sn * TILE_FLOATS, tile_ptr(src, t_issue), TILE_BYTES, &full[sn]);
+        }
+        if (++t_issue == n_tiles) t_issue = 0;
+        mbar_wait(&full[s], (uint32_t)((k / STAGES) & 1));
+
+        const ulonglong2* sx = reinterpret_cast<const ulonglong2*>(stage_buf + s * TILE_FLOATS);
+        const ulonglong2* sy = sx + TILE_J / 4;
+        const ulonglong2* sz = sy + TILE_J / 4;
+        const ulonglong2* sm = sz + TILE_J / 4;
+
+        u64 ax[R], ay[R], az[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) ax[r] = ay[r] = az[r] = 0ull;
+
+        auto interact = [&](u64 X, u64 Y, u64 Z, u64 M) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                u64 dx = add2(X, nxi[r]);
+                u64 dy = add2(Y, nyi[r]);
+                u64 dz = add2(Z, nzi[r]);
+                if constexpr (PERIODIC) {
+                    u64 qx = add2(add2(mul2(dx, inv_box2), magic2), nmagic2);
+                    u64 qy = add2(add2(mul2(dy, inv_box2), magic2), nmagic2);
+                    u64 qz = add2(add2(mul2(dz, inv_box2), magic2), nmagic2);
+                    dx = fma2(qx, nbox2, dx);
+                    dy = fma2(qy, nbox2, dy);
+                    dz = fma2(qz, nbox2, dz);
+                }
+                u64 r2 = fma2(dx, dx, eps2_2);
+                r2 = fma2(dy, dy, r2);
+                r2 = fma2(dz, dz, r2);
+                float r2a, r2b;
+                unpk(r2, r2a, r2b);
+                u64 rinv = pk(rsqrt_approx(r2a), rsqrt_approx(r2b));
+                u64 rinv2 = mul2(rinv, rinv);
+                u64 mr = mul2(M, rinv);
+                u64 f = mul2(rinv2, mr);
+                ax[r] = fma2(f, dx, ax[r]);
+                ay[r] = fma2(f, dy, ay[r]);
+                az[r] = fma2(f, dz, az[r]);
+            }
+        };
+
+#pragma unroll 2
+        for (int j4 = 0; j4 < TILE_J / 4; ++j4) {
+            const ulonglong2 X = sx[j4], Y = sy[j4], Z = sz[j4], M = sm[j4];
+            interact(X.x, Y.x, Z.x, M.x);
+            interact(X.y, Y.y, Z.y, M.y);
+        }
+
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float lo, hi;
+            unpk(ax[r], lo, hi); dax[r] += (double)(lo + hi);
+            unpk(ay[r], lo, hi); day[r] += (double)(lo + hi);
+            unpk(az[r], lo, hi); daz[r] += (double)(lo + hi);
+        }
+        __syncthreads();      // every warp is done with stage s -> it may be refilled
+
+        ++t;
+        const bool last = (k == my_units - 1);
+        if (t == n_tiles || last) {
+            double* rec = partials + (size_t)(c + b) * 3 * BLOCK_I;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                rec[0 * BLOCK_I + r * THREADS + tid] = dax[r];
+                rec[1 * BLOCK_I + r * THREADS + tid] = day[r];
+                rec[2 * BLOCK_I + r * THREADS + tid] = daz[r];
+            }
+            if (t == n_tiles) {
+                t = 0;
+                ++b;
+                if (!last) load_targets(b);
+            }
+        }
+    }
+}
+
+// Adds the partial records of each target block in CTA order (fixed -> the
+// result does not depend on scheduling) and writes float acc3.
+__global__ void direct_finalize_kernel(const double* __restrict__ partials, float* __restrict__ acc3,
+                                       long long n_targets, int block_i, long long n_units,
+                                       int n_tiles, int G) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_targets) return;
+    long long b = i / block_i;
+    int o = (int)(i % block_i);
+    long long uf = b * n_tiles, ul = uf + n_tiles - 1;
+    long long cf = ((uf + 1) * G - 1) / n_units;
+    long long cl = ((ul + 1) * G - 1) / n_units;
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (long long c = cf; c <= cl; ++c) {
+        const double* rec = partials + (size_t)(c + b) * 3 * block_i;
+        sx += rec[o];
+        sy += rec[block_i + o];
+        sz += rec[2 * block_i + o];
+    }
+    acc3[3 * i + 0] = (float)sx;
+    acc3[3 * i + 1] = (float)sy;
+    acc3[3 * i + 2] = (float)sz;
+}
+
+template <int R, bool PERIODIC>
+int launch_direct(b200_ctx* ctx, const DirectSources& src, const float4* targets, size_t n_targets,
+                  float eps, float box, float* acc3, cudaStream_t st) {
+    constexpr int BLOCK_I = THREADS * R;
+    auto kern = direct_kernel<R, PERIODIC>;
+    const size_t smem = STAGES * TILE_BYTES + STAGES * sizeof(uint64_t);
+    static bool configured = false;     // per template instantiation
+    static int blocks_per_sm = 0;
+    if (!configured) {
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, THREADS, smem));
+        if (blocks_per_sm < 1) return B200_ERR_UNSUPPORTED;
+        configured = true;
+    }
+    const long long T = ((long long)n_targets + BLOCK_I - 1) / BLOCK_I;
+    const int NT = src.total_tiles;
+    const long long U = T * NT;
+    long long G = (long long)ctx->sm_count * blocks_per_sm;
+    if (G > U) G = U;
+    B200_TRY(ctx->partials.reserve((size_t)(G + T) * 3 * BLOCK_I * sizeof(double)));
+    if (ctx->timing) B200_CUDA(cudaEventRecord(ctx->ev0, st));
+    kern<<<(unsigned)G, THREADS, smem, st>>>(src, targets, (long long)n_targets, eps * eps, box,
+                                             ctx->partials.as<double>(), U, NT);
+    if (ctx->timing) B200_CUDA(cudaEventRecord(ctx->ev1, st));
+    B200_CUDA(cudaGetLastError());
+    const int fb = 256;
+    direct_finalize_kernel<<<(unsigned)((n_targets + fb - 1) / fb), fb, 0, st>>>(
+        ctx->partials.as<double>(), acc3, (long long)n_targets, BLOCK_I, U, NT, (int)G);
+    B200_CUDA(cudaGetLastError());
+    ctx->launches += 2;
+    return B200_OK;
+}
+
+}  // namespace
+
+size_t direct_tiles_bytes(size_t n) {
+    size_t nt = (n + DIRECT_TILE_J - 1) / DIRECT_TILE_J;
+    return nt * 4 * DIRECT_TILE_J * sizeof(float);
+}
+
+int direct_pack_tiles(b200_ctx* ctx, const void* posm4, size_t n, float* tiles, cudaStream_t st) {
+    size_t nt = (n + DIRECT_TILE_J - 1) / DIRECT_TILE_J;
+    long long n_padded = (long long)nt * DIRECT_TILE_J;
+    if (n_padded == 0) return B200_OK;
+    pack_tiles_kernel<<<(unsigned)((n_padded + 255) / 256), 256, 0, st>>>(
+        (const float4*)posm4, (long long)n, n_padded, tiles);
+    B200_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return B200_OK;
+}
+
+int direct_forces(b200_ctx* ctx, const DirectSources& src, const void* targets4, size_t n_targets,
+                  float eps, float box, void* acc3, cudaStream_t st) {
+    if (!(eps > 0.f) || box < 0.f) return B200_ERR_INVALID;
+    if (n_targets == 0) return B200_OK;
+    if (src.total_tiles <= 0) {
+        B200_CUDA(cudaMemsetAsync(acc3, 0, n_targets * 3 * sizeof(float), st));
+        return B200_OK;
+    }
+    const float4* tg = (const float4*)targets4;
+    float* out = (float*)acc3;
+    // Register blocking: 4 targets/thread once there is enough work to fill the
+    // chip; 2 below that so small problems still spread over all SMs.
+    const bool small = n_targets < (size_t)ctx->sm_count * 2 * THREADS * 4;
+    if (box > 0.f) {
+        return small ? launch_direct<2, true>(ctx, src, tg, n_targets, eps, box, out, st)
+                     : launch_direct<4, true>(ctx, src, tg, n_targets, eps, box, out, st);
+    }
+    return small ? launch_direct<2, false>(ctx, src, tg, n_targets, eps, box, out, st)
+                 : launch_direct<4, false>(ctx, src, tg, n_targets, eps, box, out, st);
+}
+
+}  // namespace b200

@@ -1,0 +1,84 @@
+// probe.cu -- FP32 pipe probe: the measured denominator of the direct-sum
+// roofline (MEASURED_PEAKS.json carries HBM and bf16 tensor numbers only).
+// Register-resident FMA chains, 16 independent accumulators per thread, every
+// SM filled with 2 x 1024 threads.  mode 0: fma.rn.f32 (FFMA); mode 1:
+// fma.rn.f32x2 (FFMA2, two FMAs per lane-instruction).
+#include "common.cuh"
+#include "probe.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr int CHAINS = 16;
+constexpr int INNER = 64;
+
+__global__ void __launch_bounds__(1024, 2)
+ffma_probe_kernel(float* out, int iters, float a, float b) {
+    float acc[CHAINS];
+#pragma unroll
+    for (int k = 0; k < CHAINS; ++k) acc[k] = (float)(threadIdx.x + k);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < INNER; ++u)
+#pragma unroll
+            for (int k = 0; k < CHAINS; ++k) acc[k] = fmaf(acc[k], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < CHAINS; ++k) s += acc[k];
+    if (s == 123.456f) out[0] = s;       // never true; keeps the chain alive
+}
+
+__global__ void __launch_bounds__(1024, 2)
+ffma2_probe_kernel(float* out, int iters, float a, float b) {
+    unsigned long long acc[CHAINS / 2], a2, b2;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(a2) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(b2) : "f"(b));
+#pragma unroll
+    for (int k = 0; k < CHAINS / 2; ++k) {
+        float x = (float)(threadIdx.x + k);
+        asm("mov.b64 %0, {%1, %1};" : "=l"(acc[k]) : "f"(x));
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < INNER; ++u)
+#pragma unroll
+            for (int k = 0; k < CHAINS / 2; ++k)
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[k]) : "l"(a2), "l"(b2));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < CHAINS / 2; ++k) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[k]));
+        s += lo + hi;
+    }
+    if (s == 123.456f) out[0] = s;
+}
+
+}  // namespace
+
+int fp32_peak_probe(b200_ctx* ctx, int mode, int iters, double* tflops, float* ms_out) {
+    if (iters <= 0 || (mode != 0 && mode != 1)) return B200_ERR_INVALID;
+    B200_TRY(ctx->probe.reserve(256));
+    cudaStream_t st = ctx->stream;
+    const int grid = ctx->sm_count * 2, block = 1024;
+    for (int rep = 0; rep < 2; ++rep) {      // rep 0 warms up, rep 1 is timed
+        B200_CUDA(cudaEventRecord(ctx->ev0, st));
+        if (mode == 0) ffma_probe_kernel<<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
+        else ffma2_probe_kernel<<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
+        B200_CUDA(cudaEventRecord(ctx->ev1, st));
+        B200_CUDA(cudaGetLastError());
+        B200_CUDA(cudaEventSynchronize(ctx->ev1));
+        ctx->launches += 1;
+    }
+    float ms = 0.f;
+    B200_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    // FMAs per thread: iters * INNER * CHAINS (mode 1: CHAINS/2 packed ops, 2 FMAs each)
+    double fmas = (double)grid * block * (double)iters * INNER * CHAINS;
+    if (tflops) *tflops = 2.0 * fmas / (ms * 1e-3) / 1e12;
+    if (ms_out) *ms_out = ms;
+    return B200_OK;
+}
+
+}  // namespace b200

@@ -1,0 +1,852 @@
+// tree.cu -- Barnes-Hut octree for sm_100a: build + centre of mass (rows T3/T4)
+// and the theta-criterion walk (rows T5/T6).
+//
+// Replaces TreeForceComputer::build_tree_cpu / insert_particle / subdivide_node /
+// get_octant / compute_center_of_mass (reference src/forces/tree_force_computer.cpp:
+// 130-243) and compute_tree_forces / compute_force_on_particle /
+// satisfies_opening_criterion / compute_node_particle_interaction (:245-347).
+//
+// The reference inserts particles one at a time into a pointer tree; the tree
+// it ends up with is nevertheless a pure function of (positions, index order,
+// leaf_capacity, max_depth, box):  a node reached by more than leaf_capacity
+// particles keeps the first leaf_capacity arrivals (they are never
+// redistributed) and routes the rest to its 8 children by a strict ">" test
+// against a float centre that follows  c + (+-(size*0.5f))*0.5f.  Since
+// arrival order is index order at the root and a STABLE split preserves it,
+// the whole build is, per level, one stable segmented 8-way partition:
+//
+//   classify nodes of the level (u64 scan: split rank | stored-particle offset)
+//   digit of every live entry + per-tile 8-bin histogram         (HBM pass 1)
+//   scan the tile histograms (8 channels)
+//   children of every split node from the prefix counts at its first entry
+//   scatter entries to their child segment, order preserved      (HBM pass 2)
+//
+// All counts live on the device; kernels are persistent grid-stride loops over
+// device-side extents, so a build is a fixed launch sequence with no host
+// synchronisation (max_depth+1 levels; empty levels cost a few microseconds).
+// Nodes are numbered breadth-first, children of a node contiguous -- the same
+// canonical numbering the CPU oracle exports, which is what makes the
+// bit-exact topology test a plain array compare.
+#include <vector>
+
+#include "common.cuh"
+#include "sort.cuh"
+#include "tree.cuh"
+
+namespace b200 {
+
+constexpr int MAX_LEVELS = 64;
+
+struct LevelInfo {
+    int node_begin, node_end;   // nodes of this level
+    int n_entries;              // live entries (particles that reached this level)
+    int n_split;                // nodes of this level that split
+    int stored_base;            // offset of this level's stored particles in part_idx
+    int pad[3];
+};
+
+struct TreeGlobals {
+    LevelInfo lv[MAX_LEVELS + 2];
+    unsigned int totals[8];     // digit totals of the level being processed
+    int error;                  // 1 = node table overflow
+    int stored_total;
+    unsigned long long counters[3];
+};
+
+struct TreeState {
+    size_t n = 0;
+    float box = 0.f;
+    int cap = 0, max_depth = 0;
+    const float4* posm = nullptr;
+    size_t max_nodes = 0, max_split = 0, max_tiles = 0, max_node_tiles = 0;
+    bool built = false;
+    bool counting = false;
+    DevBuf center, com, meta, nstart, ncount, nsplit_rank;
+    DevBuf ent_idx[2], ent_node[2], digit;
+    DevBuf part_idx, part_pos;
+    DevBuf globals;
+    DevBuf tile_hist, tile_warp_prefix, node_tile_sum;
+    DevBuf split_node, split_where, split_local, split_cstart;
+    DevBuf keys, keys_sorted, perm, sort_scratch, order;
+    size_t order_i0 = 0, order_n = 0;
+    bool order_valid = false;
+    void release() {
+        DevBuf* all[] = {&center, &com, &meta, &nstart, &ncount, &nsplit_rank, &ent_idx[0],
+                         &ent_idx[1], &ent_node[0], &ent_node[1], &digit, &part_idx, &part_pos,
+                         &globals, &tile_hist, &tile_warp_prefix, &node_tile_sum, &split_node,
+                         &split_where, &split_local, &split_cstart, &keys, &keys_sorted, &perm,
+                         &sort_scratch, &order};
+        for (DevBuf* b : all) b->release();
+    }
+};
+
+namespace {
+
+typedef unsigned long long u64;
+
+constexpr int ET_THREADS = 256;
+constexpr int ET_ITEMS = 8;
+constexpr int ET_WARPS = ET_THREADS / 32;
+constexpr int ENT_TILE = ET_THREADS * ET_ITEMS;       // 2048 entries per tile
+constexpr int NODE_TILE = 2048;                        // nodes per scan tile (256 x 8)
+constexpr unsigned FULL = 0xffffffffu;
+
+// ------------------------------------------------------------------ init ---
+__global__ void tree_init_kernel(TreeGlobals* g, float4* center, float4* com, int4* meta, int* nstart,
+                                 int* ncount, int* ent_idx, int* ent_node, int n, float box) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        for (int l = 0; l < MAX_LEVELS + 2; ++l) {
+            g->lv[l].node_begin = g->lv[l].node_end = 0;
+            g->lv[l].n_entries = g->lv[l].n_split = g->lv[l].stored_base = 0;
+        }
+        g->lv[0].node_begin = 0;
+        g->lv[0].node_end = 1;
+        g->lv[0].n_entries = n;
+        g->error = 0;
+        g->stored_total = 0;
+        g->counters[0] = g->counters[1] = g->counters[2] = 0;
+        center[0] = make_float4(0.f, 0.f, 0.f, box);     // tree_force_computer.cpp:132-133
+        com[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        meta[0] = make_int4(-1, -1, 0, 0);
+        nstart[0] = 0;
+        ncount[0] = n;
+    }
+    for (; i < n; i += gridDim.x * blockDim.x) {
+        ent_idx[i] = i;
+        ent_node[i] = 0;
+    }
+}
+
+// ----------------------------------------------------- K1: classify nodes ---
+// value per node: (split ? 1 : 0) << 40 | stored particles (leaf members or orphans)
+__device__ __forceinline__ u64 node_value(int count, int cap, bool may_split) {
+    const bool split = may_split && count > cap;
+    return split ? ((1ull << 40) | (u64)cap) : (u64)count;
+}
+
+__device__ __forceinline__ u64 block_reduce_u64(u64 v, u64* sh /* >= 8 */) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    u64 t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(256)
+node_reduce_kernel(const TreeGlobals* __restrict__ g, int level, int cap, int max_depth,
+                   const int* __restrict__ ncount, u64* __restrict__ tile_sum) {
+    __shared__ u64 sh[8];
+    const LevelInfo L = g->lv[level];
+    const int n_nodes = L.node_end - L.node_begin;
+    const int n_tiles = (n_nodes + NODE_TILE - 1) / NODE_TILE;
+    const bool may_split = level < max_depth;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        u64 v = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int k = tile * NODE_TILE + threadIdx.x * 8 + j;
+            if (k < n_nodes) v += node_value(ncount[L.node_begin + k], cap, may_split);
+        }
+        u64 t = block_reduce_u64(v, sh);
+        if (threadIdx.x == 0) tile_sum[tile] = t;
+    }
+}
+
+// single CTA: exclusive scan of the tile sums; publishes the extents of the next level
+__global__ void __launch_bounds__(1024)
+node_scan_kernel(TreeGlobals* __restrict__ g, int level, u64* __restrict__ tile_sum, int max_nodes) {
+    __shared__ u64 wsum[32];
+    __shared__ u64 carry_s, chunk_s;
+    const LevelInfo L = g->lv[level];
+    const int n_nodes = L.node_end - L.node_begin;
+    const int n_tiles = (n_nodes + NODE_TILE - 1) / NODE_TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const u64 v = (i < n_tiles) ? tile_sum[i] : 0ull;
+        u64 x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u64 y = __shfl_up_sync(FULL, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            const u64 w = wsum[lane];
+            u64 xs = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                u64 y = __shfl_up_sync(FULL, xs, o);
+                if (lane >= o) xs += y;
+            }
+            wsum[lane] = xs - w;
+            if (lane == 31) chunk_s = xs;
+        }
+        __syncthreads();
+        if (i < n_tiles) tile_sum[i] = carry_s + wsum[warp] + (x - v);
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += chunk_s;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const u64 tot = carry_s;
+        const int n_split = (int)(tot >> 40);
+        const int stored = (int)(tot & ((1ull << 40) - 1));
+        g->lv[level].n_split = n_split;
+        g->lv[level].stored_base = g->stored_total;
+        g->stored_total += stored;
+        long long next_end = (long long)L.node_end + 8ll * n_split;
+        if (next_end > max_nodes) { g->error = 1; next_end = L.node_end; g->lv[level].n_split = 0; }
+        g->lv[level + 1].node_begin = L.node_end;
+        g->lv[level + 1].node_end = (int)next_end;
+        g->lv[level + 1].n_entries = 0;         // filled by the histogram scan
+        for (int d = 0; d < 8; ++d) g->totals[d] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+node_apply_kernel(const TreeGlobals* __restrict__ g, int level, int cap, int max_depth,
+                  const int* __restrict__ ncount, const u64* __restrict__ tile_sum,
+                  int4* __restrict__ meta, int* __restrict__ nsplit_rank, int* __restrict__ split_node) {
+    __shared__ u64 wsum[8];
+    const LevelInfo L = g->lv[level];
+    if (L.n_split == 0 && g->error) return;
+    const int n_nodes = L.node_end - L.node_begin;
+    const int n_tiles = (n_nodes + NODE_TILE - 1) / NODE_TILE;
+    const bool may_split = level < max_depth;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        u64 v[8], tsum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int k = tile * NODE_TILE + threadIdx.x * 8 + j;
+            v[j] = (k < n_nodes) ? node_value(ncount[L.node_begin + k], cap, may_split) : 0ull;
+            tsum += v[j];
+        }
+        u64 x = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u64 y = __shfl_up_sync(FULL, x, o);
+            if (lane >= o) x += y;
+        }
+        __syncthreads();
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        u64 pre = tile_sum[tile] + (x - tsum);
+        for (int w = 0; w < warp; ++w) pre += wsum[w];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int k = tile * NODE_TILE + threadIdx.x * 8 + j;
+            if (k < n_nodes) {
+                const int node = L.node_begin + k;
+                const int rank = (int)(pre >> 40);
+                const int off = L.stored_base + (int)(pre & ((1ull << 40) - 1));
+                const bool split = (v[j] >> 40) != 0;
+                int4 m = meta[node];
+                m.x = split ? (L.node_end + 8 * rank) : -1;
+                m.z = off;
+                m.w = (int)(v[j] & ((1ull << 40) - 1));
+                meta[node] = m;
+                nsplit_rank[node] = split ? rank : -1;
+                if (split) split_node[rank] = node;
+            }
+            pre += v[j];
+        }
+    }
+}
+
+// ------------------------------------------- K2: digits + tile histograms ---
+// entry p of (tile, warp, row, lane) = tile*2048 + warp*256 + row*32 + lane
+__device__ __forceinline__ int entry_index(int tile, int warp, int row, int lane) {
+    return tile * ENT_TILE + warp * (32 * ET_ITEMS) + row * 32 + lane;
+}
+
+__device__ __forceinline__ unsigned digit_mask(unsigned bv, unsigned b0, unsigned b1, unsigned b2, int d) {
+    return bv & ((d & 1) ? b0 : ~b0) & ((d & 2) ? b1 : ~b1) & ((d & 4) ? b2 : ~b2);
+}
+
+__global__ void __launch_bounds__(ET_THREADS)
+entry_digit_kernel(const TreeGlobals* __restrict__ g, int level, int cap,
+                   const float4* __restrict__ posm, const float4* __restrict__ center,
+                   const int4* __restrict__ meta, const int* __restrict__ nstart,
+                   const int* __restrict__ nsplit_rank, const int* __restrict__ ent_idx,
+                   const int* __restrict__ ent_node, unsigned char* __restrict__ digit,
+                   int* __restrict__ part_idx, unsigned* __restrict__ tile_hist,
+                   unsigned* __restrict__ tile_warp_prefix, int* __restrict__ split_where,
+                   unsigned* __restrict__ split_local) {
+    __shared__ unsigned wtot[ET_WARPS][8];
+    const LevelInfo L = g->lv[level];
+    const int n_ent = L.n_entries;
+    const int n_tiles = (n_ent + ENT_TILE - 1) / ENT_TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        unsigned run = 0;             // lane l holds the warp's running count of digit (l & 7)
+#pragma unroll
+        for (int r = 0; r < ET_ITEMS; ++r) {
+            const int p = entry_index(tile, warp, r, lane);
+            int d = 8, sr = -1;
+            bool first_live = false;
+            if (p < n_ent) {
+                const int idx = ent_idx[p];
+                const int k = ent_node[p];
+                const int4 m = meta[k];
+                const int rel = p - nstart[k];
+                if (m.x < 0 || rel < cap) {
+                    part_idx[m.z + rel] = idx;          // leaf member, or orphan of a split node
+                } else {
+                    const float4 c = center[k];
+                    const float4 x = posm[idx];
+                    d = (x.x > c.x ? 1 : 0) | (x.y > c.y ? 2 : 0) | (x.z > c.z ? 4 : 0);   // :188-194
+                    if (rel == cap) { first_live = true; sr = nsplit_rank[k]; }
+                }
+                digit[p] = (unsigned char)d;
+            }
+            const unsigned bv = __ballot_sync(FULL, d < 8);
+            const unsigned b0 = __ballot_sync(FULL, d & 1);
+            const unsigned b1 = __ballot_sync(FULL, d & 2);
+            const unsigned b2 = __ballot_sync(FULL, d & 4);
+            if (__any_sync(FULL, first_live)) {
+                // prefix counts of all 8 digits at the first live entry of a split node
+#pragma unroll
+                for (int dd = 0; dd < 8; ++dd) {
+                    const unsigned before = __shfl_sync(FULL, run, dd);
+                    const unsigned c = before + __popc(digit_mask(bv, b0, b1, b2, dd) & lt);
+                    if (first_live) split_local[(size_t)sr * 8 + dd] = c;
+                }
+                if (first_live) split_where[sr] = tile * ET_WARPS + warp;
+            }
+            run += __popc(digit_mask(bv, b0, b1, b2, lane & 7));
+        }
+        __syncthreads();
+        if (lane < 8) wtot[warp][lane] = run;
+        __syncthreads();
+        if (threadIdx.x < 64) {      // thread (w, d): exclusive prefix over warps of digit d
+            const int w = threadIdx.x >> 3, d = threadIdx.x & 7;
+            unsigned pre = 0;
+            for (int ww = 0; ww < w; ++ww) pre += wtot[ww][d];
+            tile_warp_prefix[(size_t)tile * 64 + w * 8 + d] = pre;
+            if (w == ET_WARPS - 1) tile_hist[(size_t)tile * 8 + d] = pre + wtot[w][d];
+        }
+    }
+}
+
+// single CTA, warp d scans channel d over the tiles
+__global__ void __launch_bounds__(256)
+tile_scan_kernel(TreeGlobals* __restrict__ g, int level, unsigned* __restrict__ tile_hist) {
+    __shared__ unsigned tot[8];
+    const LevelInfo L = g->lv[level];
+    const int n_tiles = (L.n_entries + ENT_TILE - 1) / ENT_TILE;
+    const int lane = threadIdx.x & 31, d = threadIdx.x >> 5;
+    unsigned carry = 0;
+    for (int base = 0; base < n_tiles; base += 32) {
+        const int t = base + lane;
+        const unsigned v = (t < n_tiles) ? tile_hist[(size_t)t * 8 + d] : 0u;
+        unsigned x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned y = __shfl_up_sync(FULL, x, o);
+            if (lane >= o) x += y;
+        }
+        if (t < n_tiles) tile_hist[(size_t)t * 8 + d] = carry + x - v;
+        carry += __shfl_sync(FULL, x, 31);
+    }
+    if (lane == 0) { tot[d] = carry; g->totals[d] = carry; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned s = 0;
+        for (int k = 0; k < 8; ++k) s += tot[k];
+        g->lv[level + 1].n_entries = (int)s;
+    }
+}
+
+// ------------------------------------------------------ K4: make children ---
+__global__ void __launch_bounds__(256)
+make_children_kernel(const TreeGlobals* __restrict__ g, int level, const int* __restrict__ split_node,
+                     const int* __restrict__ split_where, const unsigned* __restrict__ split_local,
+                     const unsigned* __restrict__ tile_hist /* scanned */,
+                     const unsigned* __restrict__ tile_warp_prefix, unsigned* __restrict__ split_cstart,
+                     float4* __restrict__ center, float4* __restrict__ com, int4* __restrict__ meta,
+                     int* __restrict__ nstart, int* __restrict__ ncount) {
+    const LevelInfo L = g->lv[level];
+    const int n_split = L.n_split;
+    for (int sr = blockIdx.x * blockDim.x + threadIdx.x; sr < n_split; sr += gridDim.x * blockDim.x) {
+        unsigned cs[8], cn[8];
+        {
+            const int w = split_where[sr];
+            const int tile = w / ET_WARPS;
+#pragma unroll
+            for (int d = 0; d < 8; ++d)
+                cs[d] = tile_hist[(size_t)tile * 8 + d] + tile_warp_prefix[(size_t)w * 8 + d] +
+                        split_local[(size_t)sr * 8 + d];
+        }
+        if (sr + 1 < n_split) {
+            const int w = split_where[sr + 1];
+            const int tile = w / ET_WARPS;
+#pragma unroll
+            for (int d = 0; d < 8; ++d)
+                cn[d] = tile_hist[(size_t)tile * 8 + d] + tile_warp_prefix[(size_t)w * 8 + d] +
+                        split_local[(size_t)(sr + 1) * 8 + d];
+        } else {
+#pragma unroll
+            for (int d = 0; d < 8; ++d) cn[d] = g->totals[d];
+        }
+        unsigned base = 0;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) { split_cstart[(size_t)sr * 8 + d] = cs[d]; base += cs[d]; }
+        const int k = split_node[sr];
+        const float4 c = center[k];
+        const int4 mk = meta[k];
+        const int child0 = mk.x;
+        const float half_size = __fmul_rn(c.w, 0.5f);                    // :175
+        unsigned off = base;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+            const int id = child0 + d;
+            const float hx = (d & 1) ? half_size : -half_size;          // :180-182
+            const float hy = (d & 2) ? half_size : -half_size;
+            const float hz = (d & 4) ? half_size : -half_size;
+            center[id] = make_float4(__fadd_rn(c.x, __fmul_rn(hx, 0.5f)), __fadd_rn(c.y, __fmul_rn(hy, 0.5f)),
+                                     __fadd_rn(c.z, __fmul_rn(hz, 0.5f)), half_size);
+            com[id] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const unsigned cnt = cn[d] - cs[d];
+            nstart[id] = (int)off;
+            ncount[id] = (int)cnt;
+            meta[id] = make_int4(-1, (d < 7) ? id + 1 : mk.y, 0, 0);   // .y = skip pointer
+            off += cnt;
+        }
+    }
+}
+
+// ---------------------------------------------------------- K5: scatter ---
+__global__ void __launch_bounds__(ET_THREADS)
+entry_scatter_kernel(const TreeGlobals* __restrict__ g, int level, const int4* __restrict__ meta,
+                     const int* __restrict__ nstart, const int* __restrict__ nsplit_rank,
+                     const int* __restrict__ ent_idx, const int* __restrict__ ent_node,
+                     const unsigned char* __restrict__ digit, const unsigned* __restrict__ tile_hist,
+                     const unsigned* __restrict__ tile_warp_prefix,
+                     const unsigned* __restrict__ split_cstart, int* __restrict__ out_idx,
+                     int* __restrict__ out_node) {
+    const LevelInfo L = g->lv[level];
+    if (L.n_split == 0) return;
+    const int n_ent = L.n_entries;
+    const int n_tiles = (n_ent + ENT_TILE - 1) / ENT_TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // lane l: global prefix of digit (l & 7) at the start of this warp's rows
+        unsigned run = tile_hist[(size_t)tile * 8 + (lane & 7)] +
+                       tile_warp_prefix[(size_t)tile * 64 + warp * 8 + (lane & 7)];
+#pragma unroll
+        for (int r = 0; r < ET_ITEMS; ++r) {
+            const int p = entry_index(tile, warp, r, lane);
+            const int d = (p < n_ent) ? (int)digit[p] : 8;
+            const unsigned bv = __ballot_sync(FULL, d < 8);
+            const unsigned b0 = __ballot_sync(FULL, d & 1);
+            const unsigned b1 = __ballot_sync(FULL, d & 2);
+            const unsigned b2 = __ballot_sync(FULL, d & 4);
+            const unsigned before = __shfl_sync(FULL, run, d & 7);
+            if (d < 8) {
+                const unsigned cpos = before + __popc(digit_mask(bv, b0, b1, b2, d) & lt);
+                const int k = ent_node[p];
+                const int child = meta[k].x + d;
+                const int dst = nstart[child] + (int)(cpos - split_cstart[(size_t)nsplit_rank[k] * 8 + d]);
+                out_idx[dst] = ent_idx[p];
+                out_node[dst] = child;
+            }
+            run += __popc(digit_mask(bv, b0, b1, b2, lane & 7));
+        }
+    }
+}
+
+// ------------------------------------------------------- centre of mass ---
+__global__ void part_pos_kernel(const int* __restrict__ part_idx, const float4* __restrict__ posm, int n,
+                                float4* __restrict__ part_pos) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int idx = part_idx[q];
+    float4 p = posm[idx];
+    p.w = __int_as_float(idx);
+    part_pos[q] = p;
+}
+
+// compute_center_of_mass (:196-243): one rounding per operation, reference order
+__global__ void __launch_bounds__(256)
+com_kernel(const TreeGlobals* __restrict__ g, int level, const int4* __restrict__ meta,
+           const int* __restrict__ part_idx, const float4* __restrict__ posm, float4* __restrict__ com) {
+    const LevelInfo L = g->lv[level];
+    const int n_nodes = L.node_end - L.node_begin;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += gridDim.x * blockDim.x) {
+        const int k = L.node_begin + i;
+        const int4 m = meta[k];
+        float total = 0.f, wx = 0.f, wy = 0.f, wz = 0.f;
+        if (m.x < 0) {
+            for (int q = m.z; q < m.z + m.w; ++q) {
+                const float4 p = posm[part_idx[q]];
+                total = __fadd_rn(total, p.w);
+                wx = __fadd_rn(wx, __fmul_rn(p.x, p.w));
+                wy = __fadd_rn(wy, __fmul_rn(p.y, p.w));
+                wz = __fadd_rn(wz, __fmul_rn(p.z, p.w));
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                const float4 c = com[m.x + d];
+                if (c.w > 0.f) {
+                    total = __fadd_rn(total, c.w);
+                    wx = __fadd_rn(wx, __fmul_rn(c.x, c.w));
+                    wy = __fadd_rn(wy, __fmul_rn(c.y, c.w));
+                    wz = __fadd_rn(wz, __fmul_rn(c.z, c.w));
+                }
+            }
+        }
+        float4 o = make_float4(0.f, 0.f, 0.f, total);
+        if (total > 0.f) {
+            o.x = __fdiv_rn(wx, total);
+            o.y = __fdiv_rn(wy, total);
+            o.z = __fdiv_rn(wz, total);
+        }
+        com[k] = o;
+    }
+}
+
+// ------------------------------------------------------------------ walk ---
+// One thread per target, targets taken in Morton order so the 32 lanes of a
+// warp walk nearly the same nodes.  Stackless: every node carries the id of the
+// node that follows its subtree in depth-first order (meta.y), so "skip" is one
+// load and "open" is meta.x.  Accept test: IEEE sqrt/divide, no contraction, so
+// every lane takes exactly the decision the CPU code takes (:302-310).
+template <bool COUNT>
+__global__ void __launch_bounds__(128)
+walk_kernel(const float4* __restrict__ posm, const int* __restrict__ order, int i0, int n_targets,
+            const float4* __restrict__ com, const float4* __restrict__ center,
+            const int4* __restrict__ meta, const float4* __restrict__ part_pos, float theta,
+            float* __restrict__ acc3, TreeGlobals* __restrict__ g) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long c_vis = 0, c_pc = 0, c_pp = 0;
+    if (t < n_targets) {
+        const int i = order ? order[t] : (i0 + t);
+        const float4 p = posm[i];
+        float ax = 0.f, ay = 0.f, az = 0.f;
+        const float eps2 = __fmul_rn(0.01f, 0.01f);                      // :281-282, :334-335
+        int k = 0;
+        while (k >= 0) {
+            const float4 c = com[k];
+            const int4 m = meta[k];
+            if (COUNT) ++c_vis;
+            if (c.w == 0.0f) { k = m.y; continue; }                      // :260
+            if (m.x < 0) {                                               // leaf :268-270
+                for (int q = m.z; q < m.z + m.w; ++q) {
+                    const float4 s = part_pos[q];
+                    if (__float_as_int(s.w) == i) continue;              // :321
+                    const float dx = s.x - p.x, dy = s.y - p.y, dz = s.z - p.z;
+                    const float r2 = dx * dx + dy * dy + dz * dz + eps2;
+                    const float rinv = rsqrtf(r2);
+                    const float f = rinv * rinv * rinv;                  // unit mass (:253, :340)
+                    ax += f * dx; ay += f * dy; az += f * dz;
+                    if (COUNT) ++c_pp;
+                }
+                k = m.y;
+                continue;
+            }
+            const float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            const float r = __fsqrt_rn(d2);
+            if (__fdiv_rn(center[k].w, r) < theta) {                     // :309
+                const float r2 = d2 + eps2;
+                const float rinv = rsqrtf(r2);
+                const float f = c.w * rinv * rinv * rinv;                // :280-290
+                ax += f * dx; ay += f * dy; az += f * dz;
+                if (COUNT) ++c_pc;
+                k = m.y;
+            } else {
+                k = m.x;                                                 // :293-297
+            }
+        }
+        const size_t o = (size_t)(i - i0) * 3;
+        acc3[o + 0] = ax; acc3[o + 1] = ay; acc3[o + 2] = az;
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            c_vis += __shfl_down_sync(FULL, c_vis, s);
+            c_pc += __shfl_down_sync(FULL, c_pc, s);
+            c_pp += __shfl_down_sync(FULL, c_pp, s);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&g->counters[0], c_vis);
+            atomicAdd(&g->counters[1], c_pc);
+            atomicAdd(&g->counters[2], c_pp);
+        }
+    }
+}
+
+// keep only the targets of [i0, i0+n): order[] = sorted perm filtered (stable)
+__global__ void range_keys_kernel(const uint32_t* __restrict__ keys, int i0, int n, uint32_t* __restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[t] = keys[i0 + t];
+}
+__global__ void add_offset_kernel(int* __restrict__ v, int n, int off) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) v[t] += off;
+}
+__global__ void zero_counters_kernel(TreeGlobals* g) {
+    g->counters[0] = g->counters[1] = g->counters[2] = 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- host side ---
+static TreeState* state(b200_ctx* ctx) {
+    if (!ctx->tree) ctx->tree = new TreeState();
+    return ctx->tree;
+}
+
+void tree_destroy(b200_ctx* ctx) {
+    if (ctx->tree) {
+        ctx->tree->release();
+        delete ctx->tree;
+        ctx->tree = nullptr;
+    }
+}
+
+int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_cap, int max_depth,
+               cudaStream_t st) {
+    if (!posm4 || n == 0 || !(box > 0.f)) return B200_ERR_INVALID;
+    if (leaf_cap < 1 || max_depth < 0 || max_depth > MAX_LEVELS - 2) return B200_ERR_UNSUPPORTED;
+    if (n >= (1ull << 30)) return B200_ERR_UNSUPPORTED;
+    TreeState* T = state(ctx);
+    T->built = false;
+    T->order_valid = false;
+    T->n = n; T->box = box; T->cap = leaf_cap; T->max_depth = max_depth;
+    T->posm = (const float4*)posm4;
+    // every internal node keeps exactly leaf_cap particles => at most n/leaf_cap internal nodes
+    T->max_split = n / (size_t)leaf_cap + 1;
+    T->max_nodes = 8 * T->max_split + 1;
+    T->max_tiles = (n + ENT_TILE - 1) / ENT_TILE + 1;
+    T->max_node_tiles = (T->max_nodes + NODE_TILE - 1) / NODE_TILE + 1;
+    B200_TRY(T->center.reserve(T->max_nodes * sizeof(float4)));
+    B200_TRY(T->com.reserve(T->max_nodes * sizeof(float4)));
+    B200_TRY(T->meta.reserve(T->max_nodes * sizeof(int4)));
+    B200_TRY(T->nstart.reserve(T->max_nodes * sizeof(int)));
+    B200_TRY(T->ncount.reserve(T->max_nodes * sizeof(int)));
+    B200_TRY(T->nsplit_rank.reserve(T->max_nodes * sizeof(int)));
+    for (int b = 0; b < 2; ++b) {
+        B200_TRY(T->ent_idx[b].reserve(n * sizeof(int)));
+        B200_TRY(T->ent_node[b].reserve(n * sizeof(int)));
+    }
+    B200_TRY(T->digit.reserve(n));
+    B200_TRY(T->part_idx.reserve(n * sizeof(int)));
+    B200_TRY(T->part_pos.reserve(n * sizeof(float4)));
+    B200_TRY(T->globals.reserve(sizeof(TreeGlobals)));
+    B200_TRY(T->tile_hist.reserve(T->max_tiles * 8 * sizeof(unsigned)));
+    B200_TRY(T->tile_warp_prefix.reserve(T->max_tiles * 64 * sizeof(unsigned)));
+    B200_TRY(T->node_tile_sum.reserve(T->max_node_tiles * sizeof(u64)));
+    B200_TRY(T->split_node.reserve(T->max_split * sizeof(int)));
+    B200_TRY(T->split_where.reserve(T->max_split * sizeof(int)));
+    B200_TRY(T->split_local.reserve(T->max_split * 8 * sizeof(unsigned)));
+    B200_TRY(T->split_cstart.reserve(T->max_split * 8 * sizeof(unsigned)));
+
+    TreeGlobals* g = T->globals.as<TreeGlobals>();
+    float4* center = T->center.as<float4>();
+    float4* com = T->com.as<float4>();
+    int4* meta = T->meta.as<int4>();
+    int* nstart = T->nstart.as<int>();
+    int* ncount = T->ncount.as<int>();
+    int* nsr = T->nsplit_rank.as<int>();
+    const int pgrid = ctx->sm_count * 8;      // persistent grids: 8 x 256-thread CTAs per SM
+
+    tree_init_kernel<<<pgrid, 256, 0, st>>>(g, center, com, meta, nstart, ncount, T->ent_idx[0].as<int>(),
+                                            T->ent_node[0].as<int>(), (int)n, box);
+    ctx->launches += 1;
+    for (int L = 0; L <= max_depth; ++L) {
+        const int cur = L & 1, nxt = cur ^ 1;
+        // a level cannot hold more nodes / entries than these bounds: trim the grids
+        const double lvl_nodes = (L < 10) ? (double)(1ull << (3 * L)) : 1e30;
+        const size_t nb = (size_t)((lvl_nodes < (double)T->max_nodes) ? lvl_nodes : (double)T->max_nodes);
+        const int ngrid = (int)((nb + NODE_TILE - 1) / NODE_TILE < (size_t)pgrid ? (nb + NODE_TILE - 1) / NODE_TILE : (size_t)pgrid);
+        const int egrid = (int)(T->max_tiles < (size_t)pgrid ? T->max_tiles : (size_t)pgrid);
+        const int sgrid = (int)((nb + 255) / 256 < (size_t)pgrid ? (nb + 255) / 256 : (size_t)pgrid);
+        node_reduce_kernel<<<ngrid, 256, 0, st>>>(g, L, leaf_cap, max_depth, ncount, T->node_tile_sum.as<u64>());
+        node_scan_kernel<<<1, 1024, 0, st>>>(g, L, T->node_tile_sum.as<u64>(), (int)T->max_nodes);
+        node_apply_kernel<<<ngrid, 256, 0, st>>>(g, L, leaf_cap, max_depth, ncount, T->node_tile_sum.as<u64>(),
+                                                 meta, nsr, T->split_node.as<int>());
+        entry_digit_kernel<<<egrid, ET_THREADS, 0, st>>>(
+            g, L, leaf_cap, T->posm, center, meta, nstart, nsr, T->ent_idx[cur].as<int>(),
+            T->ent_node[cur].as<int>(), T->digit.as<unsigned char>(), T->part_idx.as<int>(),
+            T->tile_hist.as<unsigned>(), T->tile_warp_prefix.as<unsigned>(), T->split_where.as<int>(),
+            T->split_local.as<unsigned>());
+        tile_scan_kernel<<<1, 256, 0, st>>>(g, L, T->tile_hist.as<unsigned>());
+        make_children_kernel<<<sgrid, 256, 0, st>>>(g, L, T->split_node.as<int>(), T->split_where.as<int>(),
+                                                    T->split_local.as<unsigned>(), T->tile_hist.as<unsigned>(),
+                                                    T->tile_warp_prefix.as<unsigned>(),
+                                                    T->split_cstart.as<unsigned>(), center, com, meta, nstart, ncount);
+        entry_scatter_kernel<<<egrid, ET_THREADS, 0, st>>>(
+            g, L, meta, nstart, nsr, T->ent_idx[cur].as<int>(), T->ent_node[cur].as<int>(),
+            T->digit.as<unsigned char>(), T->tile_hist.as<unsigned>(), T->tile_warp_prefix.as<unsigned>(),
+            T->split_cstart.as<unsigned>(), T->ent_idx[nxt].as<int>(), T->ent_node[nxt].as<int>());
+        B200_CUDA(cudaGetLastError());
+        ctx->launches += 7;
+    }
+    part_pos_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(T->part_idx.as<int>(), T->posm, (int)n,
+                                                                 T->part_pos.as<float4>());
+    ctx->launches += 1;
+    for (int L = max_depth; L >= 0; --L) {
+        const double lvl_nodes = (L < 10) ? (double)(1ull << (3 * L)) : 1e30;
+        const size_t nb = (size_t)((lvl_nodes < (double)T->max_nodes) ? lvl_nodes : (double)T->max_nodes);
+        const int cgrid = (int)((nb + 255) / 256 < (size_t)pgrid ? (nb + 255) / 256 : (size_t)pgrid);
+        com_kernel<<<cgrid, 256, 0, st>>>(g, L, meta, T->part_idx.as<int>(), T->posm, com);
+        ctx->launches += 1;
+    }
+    B200_CUDA(cudaGetLastError());
+    T->built = true;
+    return B200_OK;
+}
+
+// Morton order of the targets [i0, i0+n): stable sort of their 30-bit keys.
+static int tree_target_order(b200_ctx* ctx, TreeState* T, size_t i0, size_t n_targets, cudaStream_t st) {
+    if (T->order_valid && T->order_i0 == i0 && T->order_n == n_targets) return B200_OK;
+    B200_TRY(T->keys.reserve(n_targets * sizeof(uint32_t)));
+    B200_TRY(T->keys_sorted.reserve(n_targets * sizeof(uint32_t)));
+    B200_TRY(T->order.reserve(n_targets * sizeof(int)));
+    B200_TRY(T->sort_scratch.reserve(sort_scratch_bytes(n_targets)));
+    B200_TRY(morton_keys(ctx, T->posm + i0, n_targets, T->box, T->keys.as<uint32_t>(), st));
+    B200_TRY(sort_pairs(ctx, T->keys.as<uint32_t>(), n_targets, T->keys_sorted.as<uint32_t>(),
+                        T->order.as<int>(), 30, T->sort_scratch.p, st));
+    if (i0) {
+        add_offset_kernel<<<(unsigned)((n_targets + 255) / 256), 256, 0, st>>>(T->order.as<int>(),
+                                                                               (int)n_targets, (int)i0);
+        ctx->launches += 1;
+    }
+    B200_CUDA(cudaGetLastError());
+    T->order_valid = true; T->order_i0 = i0; T->order_n = n_targets;
+    return B200_OK;
+}
+
+int tree_walk(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* acc3, cudaStream_t st) {
+    TreeState* T = ctx->tree;
+    if (!T || !T->built) return B200_ERR_STATE;
+    if (n_targets == 0) return B200_OK;
+    if (!acc3 || i0 + n_targets > T->n) return B200_ERR_INVALID;
+    B200_TRY(tree_target_order(ctx, T, i0, n_targets, st));
+    TreeGlobals* g = T->globals.as<TreeGlobals>();
+    const unsigned grid = (unsigned)((n_targets + 127) / 128);
+    if (T->counting) {
+        zero_counters_kernel<<<1, 1, 0, st>>>(g);
+        ctx->launches += 1;
+    }
+    if (ctx->timing) B200_CUDA(cudaEventRecord(ctx->ev0, st));
+    if (T->counting)
+        walk_kernel<true><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
+                                                T->com.as<float4>(), T->center.as<float4>(), T->meta.as<int4>(),
+                                                T->part_pos.as<float4>(), theta, (float*)acc3, g);
+    else
+        walk_kernel<false><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
+                                                 T->com.as<float4>(), T->center.as<float4>(), T->meta.as<int4>(),
+                                                 T->part_pos.as<float4>(), theta, (float*)acc3, g);
+    if (ctx->timing) B200_CUDA(cudaEventRecord(ctx->ev1, st));
+    B200_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return B200_OK;
+}
+
+int tree_set_counting(b200_ctx* ctx, int enabled) {
+    state(ctx)->counting = enabled != 0;
+    return B200_OK;
+}
+
+static int fetch_globals(b200_ctx* ctx, TreeState* T, TreeGlobals* h) {
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    B200_CUDA(cudaDeviceSynchronize());
+    B200_CUDA(cudaMemcpy(h, T->globals.p, sizeof(TreeGlobals), cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+int tree_counters(b200_ctx* ctx, uint64_t counters[3]) {
+    TreeState* T = ctx->tree;
+    if (!T || !T->built) return B200_ERR_STATE;
+    TreeGlobals h;
+    B200_TRY(fetch_globals(ctx, T, &h));
+    for (int k = 0; k < 3; ++k) counters[k] = h.counters[k];
+    return B200_OK;
+}
+
+int tree_stats(b200_ctx* ctx, size_t* n_nodes, size_t* n_leaves, size_t* depth, size_t* n_stored) {
+    TreeState* T = ctx->tree;
+    if (!T || !T->built) return B200_ERR_STATE;
+    TreeGlobals h;
+    B200_TRY(fetch_globals(ctx, T, &h));
+    if (h.error) return B200_ERR_NOMEM;
+    size_t nn = 0, dep = 0;
+    for (int L = 0; L <= T->max_depth; ++L)
+        if (h.lv[L].node_end > h.lv[L].node_begin) { nn = (size_t)h.lv[L].node_end; dep = (size_t)L + 1; }
+    if (n_nodes) *n_nodes = nn;
+    if (depth) *depth = dep;
+    if (n_stored) *n_stored = (size_t)h.stored_total;
+    if (n_leaves) {
+        std::vector<int4> m(nn);
+        B200_CUDA(cudaMemcpy(m.data(), T->meta.p, nn * sizeof(int4), cudaMemcpyDeviceToHost));
+        size_t c = 0;
+        for (size_t k = 0; k < nn; ++k) c += (m[k].x < 0);
+        *n_leaves = c;
+    }
+    return B200_OK;
+}
+
+int tree_export(b200_ctx* ctx, int32_t* level, float* center, float* size, int32_t* first_child,
+                int64_t* arrivals, int64_t* part_off, int32_t* part_idx, float* mass, float* com) {
+    TreeState* T = ctx->tree;
+    if (!T || !T->built) return B200_ERR_STATE;
+    TreeGlobals h;
+    B200_TRY(fetch_globals(ctx, T, &h));
+    if (h.error) return B200_ERR_NOMEM;
+    size_t nn = 0;
+    for (int L = 0; L <= T->max_depth; ++L)
+        if (h.lv[L].node_end > h.lv[L].node_begin) nn = (size_t)h.lv[L].node_end;
+    if (level)
+        for (int L = 0; L <= T->max_depth; ++L)
+            for (int k = h.lv[L].node_begin; k < h.lv[L].node_end; ++k) level[k] = L;
+    if (center || size) {
+        std::vector<float4> c(nn);
+        B200_CUDA(cudaMemcpy(c.data(), T->center.p, nn * sizeof(float4), cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < nn; ++k) {
+            if (center) { center[3 * k] = c[k].x; center[3 * k + 1] = c[k].y; center[3 * k + 2] = c[k].z; }
+            if (size) size[k] = c[k].w;
+        }
+    }
+    if (first_child || part_off) {
+        std::vector<int4> m(nn);
+        B200_CUDA(cudaMemcpy(m.data(), T->meta.p, nn * sizeof(int4), cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < nn; ++k) {
+            if (first_child) first_child[k] = m[k].x;
+            if (part_off) part_off[k] = m[k].z;
+        }
+        if (part_off) part_off[nn] = h.stored_total;
+    }
+    if (arrivals) {
+        std::vector<int> a(nn);
+        B200_CUDA(cudaMemcpy(a.data(), T->ncount.p, nn * sizeof(int), cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < nn; ++k) arrivals[k] = a[k];
+    }
+    if (part_idx)
+        B200_CUDA(cudaMemcpy(part_idx, T->part_idx.p, (size_t)h.stored_total * sizeof(int), cudaMemcpyDeviceToHost));
+    if (mass || com) {
+        std::vector<float4> c(nn);
+        B200_CUDA(cudaMemcpy(c.data(), T->com.p, nn * sizeof(float4), cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < nn; ++k) {
+            if (com) { com[3 * k] = c[k].x; com[3 * k + 1] = c[k].y; com[3 * k + 2] = c[k].z; }
+            if (mass) mass[k] = c[k].w;
+        }
+    }
+    return B200_OK;
+}
+
+}  // namespace b200

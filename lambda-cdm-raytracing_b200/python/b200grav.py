@@ -1,0 +1,330 @@
+"""ctypes binding of libb200grav.so (include/b200grav.h) for the test and
+benchmark harness.
+
+The product is the C-ABI library; this module only marshals pointers.  Device
+buffers are torch CUDA tensors (torch is plumbing: memory, streams,
+torch.distributed) or raw integer device pointers.  There is no CPU fallback:
+a missing library or a missing sm_100 GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb200grav.so")
+
+EXPORTS = [
+    "b200_error_string", "b200_abi_version", "b200_ctx_create", "b200_ctx_destroy",
+    "b200_ctx_device", "b200_ctx_sm_count", "b200_ctx_sync",
+    "b200_direct_forces_host", "b200_direct_forces_dev", "b200_tiles_bytes",
+    "b200_pack_tiles_dev", "b200_direct_forces_parts_dev",
+    "b200_morton_keys_dev", "b200_sort_pairs_dev", "b200_tree_build_dev",
+    "b200_tree_walk_dev", "b200_tree_forces_host", "b200_tree_stats", "b200_tree_export",
+    "b200_tree_set_counting", "b200_tree_counters",
+    "b200_leapfrog_dev", "b200_hubble_a", "b200_scale_factor_step", "b200_pack_posm_dev",
+    "b200_ipc_export", "b200_ipc_open", "b200_ipc_close",
+    "b200_fp32_peak_probe", "b200_last_kernel_ms", "b200_set_timing", "b200_launch_count",
+]
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise B200Error(
+            f"{path} is missing: build it with `make -C lambda-cdm-raytracing_b200/csrc` "
+            "(__graft_entry__.build()). There is no CPU fallback.")
+    L = C.CDLL(path)
+    sz, vp, f32, i32, f64 = C.c_size_t, C.c_void_p, C.c_float, C.c_int, C.c_double
+    L.b200_error_string.restype = C.c_char_p
+    L.b200_error_string.argtypes = [i32]
+    L.b200_ctx_create.argtypes = [i32, sz, C.POINTER(vp)]
+    L.b200_ctx_destroy.argtypes = [vp]
+    L.b200_ctx_device.argtypes = [vp]
+    L.b200_ctx_sm_count.argtypes = [vp]
+    L.b200_ctx_sync.argtypes = [vp, vp]
+    L.b200_direct_forces_host.argtypes = [vp, vp, vp, vp, sz, f32, f32]
+    L.b200_direct_forces_dev.argtypes = [vp, vp, sz, sz, sz, f32, f32, vp, vp]
+    L.b200_tiles_bytes.argtypes = [sz]
+    L.b200_tiles_bytes.restype = sz
+    L.b200_pack_tiles_dev.argtypes = [vp, vp, sz, vp, vp]
+    L.b200_direct_forces_parts_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), i32, vp, sz, f32, f32, vp, vp]
+    L.b200_morton_keys_dev.argtypes = [vp, vp, sz, f32, vp, vp]
+    L.b200_sort_pairs_dev.argtypes = [vp, vp, sz, vp, vp, vp]
+    L.b200_tree_build_dev.argtypes = [vp, vp, sz, f32, i32, i32, vp]
+    L.b200_tree_walk_dev.argtypes = [vp, sz, sz, f32, vp, vp]
+    L.b200_tree_forces_host.argtypes = [vp, vp, vp, vp, sz, f32, i32, i32, f32]
+    L.b200_tree_stats.argtypes = [vp] + [C.POINTER(sz)] * 4
+    L.b200_tree_export.argtypes = [vp] + [vp] * 9
+    L.b200_tree_set_counting.argtypes = [vp, i32]
+    L.b200_tree_counters.argtypes = [vp, vp]
+    L.b200_leapfrog_dev.argtypes = [vp, vp, vp, vp, sz, i32, f32, f64, f32, f32, vp]
+    L.b200_hubble_a.argtypes = [f64] * 5
+    L.b200_hubble_a.restype = f64
+    L.b200_scale_factor_step.argtypes = [f64] * 6
+    L.b200_scale_factor_step.restype = f64
+    L.b200_pack_posm_dev.argtypes = [vp, vp, vp, sz, vp, vp]
+    L.b200_ipc_export.argtypes = [vp, vp, vp]
+    L.b200_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
+    L.b200_ipc_close.argtypes = [vp, vp]
+    L.b200_fp32_peak_probe.argtypes = [vp, i32, i32, C.POINTER(f64), C.POINTER(f32)]
+    L.b200_last_kernel_ms.argtypes = [vp, C.POINTER(f32)]
+    L.b200_set_timing.argtypes = [vp, i32]
+    L.b200_launch_count.argtypes = [vp]
+    L.b200_launch_count.restype = C.c_uint64
+    return L
+
+
+def _ptr(x):
+    """Device/host pointer of a torch tensor, numpy array, int or None."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    raise TypeError(type(x))
+
+
+def _stream(stream):
+    if stream is None:
+        import torch
+        return torch.cuda.current_stream().cuda_stream
+    if isinstance(stream, int):
+        return stream
+    return stream.cuda_stream
+
+
+class Engine:
+    """One b200_ctx: the device-side state behind a force computer."""
+
+    def __init__(self, device=0, max_particles=0, lib=None):
+        self.L = lib or load_library()
+        h = C.c_void_p()
+        self._h = None
+        self._check(self.L.b200_ctx_create(device, max_particles, C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B200Error(f"b200grav status {rc}: {self.L.b200_error_string(rc).decode()}")
+
+    def close(self):
+        if self._h is not None:
+            self.L.b200_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def sm_count(self):
+        return self.L.b200_ctx_sm_count(self._h)
+
+    @property
+    def launches(self):
+        return int(self.L.b200_launch_count(self._h))
+
+    def sync(self, stream=0):
+        self._check(self.L.b200_ctx_sync(self._h, stream or None))
+
+    # -- direct --------------------------------------------------------------
+    def direct_forces_host(self, pos, mass=None, eps=0.01, box=0.0, out=None):
+        pos = np.ascontiguousarray(pos, np.float32)
+        n = pos.shape[0]
+        m = None if mass is None else np.ascontiguousarray(mass, np.float32)
+        if out is None:
+            out = np.empty((n, 3), np.float32)
+        self._check(self.L.b200_direct_forces_host(self._h, _ptr(pos), _ptr(m), _ptr(out), n, eps, box))
+        return out
+
+    def direct_forces_dev(self, posm, acc, i0=0, n_targets=None, eps=0.01, box=0.0, stream=None):
+        n = posm.shape[0]
+        nt = n - i0 if n_targets is None else n_targets
+        self._check(self.L.b200_direct_forces_dev(self._h, _ptr(posm), n, i0, nt, eps, box, _ptr(acc),
+                                                  _stream(stream)))
+        return acc
+
+    def tiles_bytes(self, n):
+        return int(self.L.b200_tiles_bytes(n))
+
+    def pack_tiles_dev(self, posm, n, tiles, stream=None):
+        self._check(self.L.b200_pack_tiles_dev(self._h, _ptr(posm), n, _ptr(tiles), _stream(stream)))
+
+    def direct_forces_parts_dev(self, parts, part_len, targets, n_targets, acc, eps=0.01, box=0.0, stream=None):
+        k = len(parts)
+        arr_p = (C.c_void_p * k)(*[_ptr(p) for p in parts])
+        arr_n = (C.c_size_t * k)(*part_len)
+        self._check(self.L.b200_direct_forces_parts_dev(self._h, arr_p, arr_n, k, _ptr(targets), n_targets,
+                                                        eps, box, _ptr(acc), _stream(stream)))
+        return acc
+
+    # -- tree ----------------------------------------------------------------
+    def morton_keys_dev(self, posm, n, box, keys, stream=None):
+        self._check(self.L.b200_morton_keys_dev(self._h, _ptr(posm), n, box, _ptr(keys), _stream(stream)))
+
+    def sort_pairs_dev(self, keys_in, n, keys_out, perm_out, stream=None):
+        self._check(self.L.b200_sort_pairs_dev(self._h, _ptr(keys_in), n, _ptr(keys_out), _ptr(perm_out),
+                                               _stream(stream)))
+
+    def tree_build_dev(self, posm, n, box=100.0, leaf_cap=8, max_depth=20, stream=None):
+        self._check(self.L.b200_tree_build_dev(self._h, _ptr(posm), n, box, leaf_cap, max_depth, _stream(stream)))
+
+    def tree_walk_dev(self, acc, i0, n_targets, theta=0.5, stream=None):
+        self._check(self.L.b200_tree_walk_dev(self._h, i0, n_targets, theta, _ptr(acc), _stream(stream)))
+        return acc
+
+    def tree_forces_host(self, pos, mass, theta=0.5, leaf_cap=8, max_depth=20, box=100.0, out=None):
+        pos = np.ascontiguousarray(pos, np.float32)
+        mass = np.ascontiguousarray(mass, np.float32)
+        n = pos.shape[0]
+        if out is None:
+            out = np.empty((n, 3), np.float32)
+        self._check(self.L.b200_tree_forces_host(self._h, _ptr(pos), _ptr(mass), _ptr(out), n, theta,
+                                                 leaf_cap, max_depth, box))
+        return out
+
+    def tree_stats(self):
+        v = [C.c_size_t() for _ in range(4)]
+        self._check(self.L.b200_tree_stats(self._h, *[C.byref(x) for x in v]))
+        return dict(n_nodes=v[0].value, n_leaves=v[1].value, depth=v[2].value, n_stored=v[3].value)
+
+    def tree_export(self):
+        st = self.tree_stats()
+        nn, ns = st["n_nodes"], st["n_stored"]
+        d = dict(level=np.empty(nn, np.int32), center=np.empty((nn, 3), np.float32),
+                 size=np.empty(nn, np.float32), first_child=np.empty(nn, np.int32),
+                 arrivals=np.empty(nn, np.int64), part_off=np.empty(nn + 1, np.int64),
+                 part_idx=np.empty(max(ns, 1), np.int32), mass=np.empty(nn, np.float32),
+                 com=np.empty((nn, 3), np.float32))
+        self._check(self.L.b200_tree_export(self._h, *[_ptr(d[k]) for k in (
+            "level", "center", "size", "first_child", "arrivals", "part_off", "part_idx", "mass", "com")]))
+        d["part_idx"] = d["part_idx"][:ns]
+        return d
+
+    def tree_set_counting(self, on):
+        self._check(self.L.b200_tree_set_counting(self._h, int(on)))
+
+    def tree_counters(self):
+        c = np.zeros(3, np.uint64)
+        self._check(self.L.b200_tree_counters(self._h, _ptr(c)))
+        return c
+
+    # -- leapfrog ------------------------------------------------------------
+    def leapfrog_dev(self, posm, vel, acc, n, n_kicks, dt_kick, a, dt_drift, box, stream=None):
+        self._check(self.L.b200_leapfrog_dev(self._h, _ptr(posm), _ptr(vel), _ptr(acc), n, n_kicks, dt_kick,
+                                             a, dt_drift, box, _stream(stream)))
+
+    def hubble_a(self, a, om=0.31, ok=0.0, ol=0.69, h=0.67):
+        return float(self.L.b200_hubble_a(a, om, ok, ol, h))
+
+    def scale_factor_step(self, a, dt, om=0.31, ok=0.0, ol=0.69, h=0.67):
+        return float(self.L.b200_scale_factor_step(a, dt, om, ok, ol, h))
+
+    def pack_posm_dev(self, pos3, mass, n, posm, stream=None):
+        self._check(self.L.b200_pack_posm_dev(self._h, _ptr(pos3), _ptr(mass), n, _ptr(posm), _stream(stream)))
+
+    # -- multi-GPU -----------------------------------------------------------
+    def ipc_export(self, tensor_or_ptr):
+        h = (C.c_ubyte * 64)()
+        self._check(self.L.b200_ipc_export(self._h, _ptr(tensor_or_ptr), C.addressof(h)))
+        return bytes(h)
+
+    def ipc_open(self, handle):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        self._check(self.L.b200_ipc_open(self._h, C.addressof(buf), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        self._check(self.L.b200_ipc_close(self._h, ptr))
+
+    # -- measurement ---------------------------------------------------------
+    def fp32_peak_probe(self, mode=0, iters=2000):
+        t, ms = C.c_double(), C.c_float()
+        self._check(self.L.b200_fp32_peak_probe(self._h, mode, iters, C.byref(t), C.byref(ms)))
+        return t.value, ms.value
+
+    def set_timing(self, on):
+        self._check(self.L.b200_set_timing(self._h, int(on)))
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        self._check(self.L.b200_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+
+class LambdaCDMSimulation:
+    """Device-resident KDK leapfrog driver with the call shape of the reference's
+    physics::LambdaCDMSimulation (include/physics/lambda_cdm.hpp:22-75;
+    step order src/physics/lambda_cdm_impl.cu:167-213), driving the C ABI.
+
+    force: "direct" or "tree".  The first half-kick of the first step uses the
+    forces at the initial positions (the reference reads uninitialised memory
+    there)."""
+
+    def __init__(self, engine, pos, vel, mass, box=100.0, force="direct", eps=0.01, theta=0.5,
+                 leaf_cap=8, max_depth=20, wrap=True, a0=1.0, cosmo=(0.31, 0.0, 0.69, 0.67),
+                 i0=0, n_local=None, gather=None):
+        import torch
+        self.torch = torch
+        self.e = engine
+        dev = torch.device("cuda", engine.device)
+        n = pos.shape[0]
+        self.n = n
+        self.i0 = i0
+        self.nl = n - i0 if n_local is None else n_local
+        self.box, self.force, self.eps, self.theta = float(box), force, float(eps), float(theta)
+        self.leaf_cap, self.max_depth, self.wrap = leaf_cap, max_depth, wrap
+        self.a = float(a0)
+        self.cosmo = cosmo
+        self.gather = gather              # callable(posm_full) -> refreshes non-local rows (multi-GPU)
+        pm = np.concatenate([np.asarray(pos, np.float32), np.asarray(mass, np.float32)[:, None]], axis=1)
+        self.posm = torch.from_numpy(np.ascontiguousarray(pm)).to(dev)
+        self.vel = torch.from_numpy(np.ascontiguousarray(vel, np.float32)[i0:i0 + self.nl].copy()).to(dev)
+        self.acc = torch.zeros((self.nl, 3), dtype=torch.float32, device=dev)
+        self.steps = 0
+        self.have_forces = False
+
+    def compute_forces(self):
+        if self.force == "direct":
+            self.e.direct_forces_dev(self.posm, self.acc, self.i0, self.nl, self.eps, 0.0)
+        else:
+            self.e.tree_build_dev(self.posm, self.n, self.box, self.leaf_cap, self.max_depth)
+            self.e.tree_walk_dev(self.acc, self.i0, self.nl, self.theta)
+        self.have_forces = True
+
+    def step(self, dt):
+        e = self.e
+        if not self.have_forces:
+            self.compute_forces()
+        local = self.posm[self.i0:self.i0 + self.nl]
+        wrap_box = self.box if self.wrap else 0.0
+        # opening half-kick + drift (fused)
+        e.leapfrog_dev(local, self.vel, self.acc, self.nl, 1, np.float32(dt * 0.5), self.a, np.float32(dt), wrap_box)
+        self.a = e.scale_factor_step(self.a, dt, *self.cosmo)
+        if self.gather is not None:
+            self.gather(self.posm)
+        self.compute_forces()
+        # closing half-kick with the new scale factor
+        e.leapfrog_dev(local, self.vel, self.acc, self.nl, 1, np.float32(dt * 0.5), self.a, 0.0, wrap_box)
+        self.steps += 1
+
+    def get_scale_factor(self):
+        return self.a
+
+    def positions(self):
+        return self.posm[:, :3].cpu().numpy()
+
+    def velocities(self):
+        return self.vel.cpu().numpy()

@@ -1,0 +1,65 @@
+"""CPU suite, part 2: the C-ABI library loads, exports every symbol that
+include/b200grav.h declares, and fails loudly (no CPU fallback) without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "b200grav.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported():
+    import b200grav
+    lib = b200grav.load_library()
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/b200grav.h but not exported"
+    assert sorted(b200grav.EXPORTS) == names
+    assert lib.b200_abi_version() == 1
+
+
+def test_host_scalars_match_oracle(oracle):
+    import b200grav
+    lib = b200grav.load_library()
+    for a in (0.02, 0.3, 1.0, 1.9):
+        assert lib.b200_hubble_a(a, 0.31, 0.0, 0.69, 0.67) == oracle.hubble_a(a)
+        assert lib.b200_scale_factor_step(a, 1e-3, 0.31, 0.0, 0.69, 0.67) == oracle.scale_factor_step(a, 1e-3)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import b200grav
+    with pytest.raises(b200grav.B200Error, match="no usable sm_100"):
+        b200grav.Engine(0)
+    lib = b200grav.load_library()
+    pos = np.zeros((4, 3), np.float32)
+    out = np.zeros((4, 3), np.float32)
+    assert lib.b200_direct_forces_host(None, pos.ctypes.data, None, out.ctypes.data, 4, 0.01, 0.0) == 1
+
+
+def test_missing_library_raises(tmp_path):
+    import b200grav
+    with pytest.raises(b200grav.B200Error, match="no CPU fallback"):
+        b200grav.load_library(str(tmp_path / "nope.so"))
+
+
+def test_product_never_imports_oracle():
+    """The product tree must not reference oracle/ (parity would be void)."""
+    pkg = os.path.join(ROOT, "lambda-cdm-raytracing_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", "Makefile")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                for tok in ("pyoracle", "liboracle", "oracle/", "oracle.h", "orc_", "lcdm_ref"):
+                    assert tok not in txt, (os.path.join(dp, f), tok)

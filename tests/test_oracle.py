@@ -1,0 +1,141 @@
+"""CPU suite, part 1: the restated oracle against the reference's golden
+vectors (tests/golden/*.npz, generated from the reference's own compiled CPU
+sources) and against the known answers of SURVEY 8c."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from inputs import masses_np, rel_l2, uniform_mt, uniform_np
+
+TREE_KEYS = ("level", "center", "size", "first_child", "part_off", "part_idx", "mass", "com")
+
+
+def test_two_body_kat(oracle):
+    # CONTRIBUTING.md:118-131 (doc says 1.0; softening 0.01 makes it 0.99985)
+    pos = np.array([[0, 0, 0], [1, 0, 0]], np.float32)
+    a = oracle.direct_f32(pos, None)
+    g = golden("scalars.npz")
+    assert np.array_equal(a, g["two_body"])
+    assert abs(a[0, 0] - 0.999850035) < 1e-7 and a[1, 0] == -a[0, 0]
+    # NewtonianGravityKernel has the opposite sign (documented quirk, row D4)
+    assert g["newtonian_pair"][0, 0] < 0 < g["newtonian_pair"][1, 0]
+
+
+def test_morton_kat(oracle):
+    g = golden("scalars.npz")
+    want = [0x38000000, 0x24924920, 0x12492490, 0x09249248, 0x16200000, 0x3FFFFFFF]
+    for xyz, k, w in zip(g["morton_xyz"], g["morton"], want):
+        assert oracle.morton3d(*map(float, xyz)) == int(k) == w
+    assert oracle.expand_bits(0x3FF) == int(g["expand_3ff"]) == 0x09249249
+
+
+def test_hubble_golden(oracle):
+    g = golden("scalars.npz")
+    for a, h in zip(g["a"], g["hubble"]):
+        assert oracle.hubble_a(float(a)) == h
+        assert abs(h - 67.0 * np.sqrt(0.31 * a ** -3 + 0.69)) < 1e-9 * h
+
+
+def test_direct_golden(oracle):
+    g = golden("direct_768.npz")
+    assert np.array_equal(g["pos"], uniform_mt(768, seed=42))      # numpy == libstdc++ generator
+    assert np.array_equal(oracle.direct_f32(g["pos"], None), g["acc"])
+
+
+@pytest.mark.parametrize("name", ["tree_centred_4096.npz", "tree_box_3000.npz", "tree_clustered_2500.npz"])
+def test_tree_golden(oracle, name):
+    g = golden(name)
+    kw = dict(box=float(g["box"]), leaf_cap=int(g["leaf_cap"]), max_depth=int(g["max_depth"]))
+    for method in ("levels", "insert"):
+        t = oracle.tree_build(g["pos"], g["mass"], method=method, **kw)
+        for k in TREE_KEYS:
+            assert np.array_equal(getattr(t, k), g["t_" + k]), (method, k)
+        assert (t.n_nodes, t.n_leaves, t.depth) == tuple(int(x) for x in g["stats"])
+        acc = oracle.tree_forces(t, g["pos"], float(g["theta"]))
+        assert np.array_equal(acc, g["acc"]), method
+
+
+def test_tree_stats_kat(oracle):
+    # mt19937(42) uniform(-50,50): 4793 nodes / 4194 leaves / depth 6 / 4792 orphans
+    p = uniform_mt(16384)
+    t = oracle.tree_build(p, np.ones(16384, np.float32))
+    assert (t.n_nodes, t.n_leaves, t.depth) == (4793, 4194, 6)
+    assert tuple(int(x) for x in golden("scalars.npz")["stats_uniform_mt_16384"]) == (4793, 4194, 6)
+    internal = t.first_child >= 0
+    orphans = int((t.part_off[1:] - t.part_off[:-1])[internal].sum())
+    assert orphans == 4792
+
+
+def test_zeldovich_golden(oracle):
+    g = golden("zeldovich_4096.npz")
+    # examples/zeldovich_test.cpp known answers
+    sc = golden("scalars.npz")
+    assert np.allclose(sc["zeldovich_10000_head"][1], [0.78125, 0.78125, 72.4096], atol=1e-4)
+    assert np.allclose(sc["zeldovich_10000_head"][3], [0.78125, 1.8346, 15.5282], atol=1e-4)
+    assert np.allclose(sc["zeldovich_10000_com"], [49.3107, 49.5227, 48.3185], atol=1e-3)
+    assert np.array_equal(oracle.morton_keys(g["pos_box"], 100.0), g["keys"])
+    t = oracle.tree_build(g["pos"], g["mass"])
+    assert np.array_equal(oracle.tree_forces(t, g["pos"]), g["acc"])
+    r = golden("random_2048.npz")
+    assert np.array_equal(oracle.morton_keys(r["pos"], 100.0), r["keys"])
+
+
+def test_builders_agree_on_edge_cases(oracle):
+    rng = np.random.default_rng(5)
+    p = uniform_np(6000, seed=12)
+    p[100:130] = p[0:30]                         # exact duplicates
+    p[200:230, 0] = 0.0                          # on cell boundaries
+    p[230:260] = np.array([12.5, -25.0, 6.25], np.float32)
+    p[300:340] *= 1.3                            # outside the root cube
+    m = masses_np(6000, seed=13)
+    for cap, depth in ((8, 20), (1, 20), (3, 4), (8, 0), (64, 20)):
+        a = oracle.tree_build(p, m, leaf_cap=cap, max_depth=depth, method="insert")
+        b = oracle.tree_build(p, m, leaf_cap=cap, max_depth=depth, method="levels")
+        assert oracle.tree_equal(a, b), (cap, depth)
+        assert int(a.part_off[-1]) == 6000
+    del rng
+
+
+def test_sort_is_stable(oracle):
+    rng = np.random.default_rng(3)
+    keys = rng.integers(0, 50, size=5000).astype(np.uint32)
+    sk, perm = oracle.sort_pairs(keys)
+    order = np.argsort(keys, kind="stable").astype(np.int32)
+    assert np.array_equal(perm, order) and np.array_equal(sk, keys[order])
+
+
+def test_direct_f32_vs_f64(oracle):
+    p = uniform_mt(2048)
+    m = masses_np(2048)
+    assert rel_l2(oracle.direct_f32(p, m), oracle.direct_f64(p, m)) < 2e-6
+    # targets subset == rows of the full result
+    full = oracle.direct_f32(p, m)
+    assert np.array_equal(oracle.direct_f32(p, m, i0=100, n_targets=50), full[100:150])
+
+
+def test_kdk_matches_manual(oracle):
+    p = uniform_mt(256)
+    v = np.zeros_like(p)
+    m = np.ones(256, np.float32)
+    pos, vel, a = oracle.kdk_run(p, v, m, lambda x: oracle.direct_f32(x, m), steps=3, dt=1e-3, box=0.0)
+    assert a > 1.0 and np.isfinite(pos).all() and np.isfinite(vel).all()
+    assert abs(a - (1.0 + 67.0 * 1e-3) * 1.0) < 0.3        # a grows ~6.7 %/step
+
+
+def test_oracle_vs_reference_live(oracle, ref):
+    """Where the reference tree is present: the restatement against the
+    reference's own compiled code on fresh inputs (skipped on the GPU box)."""
+    p = uniform_np(5000, seed=21)
+    m = masses_np(5000, seed=22)
+    for pp in (p, p + np.float32(50.0)):
+        d = ref.tree_dump(pp, m)
+        t = oracle.tree_build(pp, m)
+        for k in TREE_KEYS:
+            assert np.array_equal(getattr(t, k), d[k]), k
+        assert np.array_equal(oracle.tree_forces(t, pp), ref.tree_forces(pp, m))
+    q = uniform_mt(1500)
+    assert np.array_equal(oracle.direct_f32(q, None), ref.direct(q))
+    assert np.array_equal(ref.factory_tree_forces(p, m), ref.tree_forces(p, m))
+    assert np.array_equal(oracle.morton_keys(p + 50, 100.0), ref.morton_keys(p + 50, 100.0))
+    for a in (0.1, 0.5, 1.0, 1.7):
+        assert oracle.hubble_a(a) == ref.hubble_a(a)
