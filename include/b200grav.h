@@ -11,7 +11,8 @@
  * "_host" entry points take HOST pointers in the reference's IForceComputer
  * layout (positions float[3N] AoS xyz, masses float[N], forces float[3N];
  * /root/reference include/core/interfaces.hpp:31-40) and do H2D, kernels, D2H.
- * "_dev" entry points take DEVICE pointers and a cudaStream_t (as void*),
+ * "_dev" entry points take DEVICE pointers and a cudaStream_t (as void*; NULL is
+ * the legacy default stream, as in a kernel launch) and only enqueue work,
  * in the reference's device layout (float4 x,y,z,m positions; 3 floats per
  * particle for velocities and forces; src/physics/lambda_cdm_impl.cu:65-68).
  *

