@@ -152,6 +152,11 @@ int b200_tree_counters(b200_ctx* ctx, uint64_t counters[3]);
 int b200_leapfrog_dev(b200_ctx* ctx, void* posm4, void* vel3, const void* acc3,
                       size_t n, int n_kicks, float dt_kick, double a,
                       float dt_drift, float box, void* stream);
+/* Host-array form (core::IIntegrator::step, include/core/interfaces.hpp:42-49):
+ * pos3/vel3 float[3n] updated in place, acc3 float[3n], mass float[n] or NULL (= 1). */
+int b200_leapfrog_host(b200_ctx* ctx, float* pos3, float* vel3, const float* acc3,
+                       const float* mass, size_t n, int n_kicks, float dt_kick, double a,
+                       float dt_drift, float box);
 /* CosmologyModel::hubble_parameter_a (include/physics/cosmology_model.hpp:49-61)
  * and LambdaCDMSimulationImpl::update_scale_factor (lambda_cdm_impl.cu:261-269);
  * host scalars, double precision. */

@@ -68,7 +68,7 @@ int b200_ctx_destroy(b200_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     tree_destroy(ctx);
     ctx->src_tiles.release(); ctx->partials.release(); ctx->part_table.release(); ctx->mass_flag.release();
-    ctx->h_pos3.release(); ctx->h_mass.release(); ctx->h_posm4.release(); ctx->h_acc3.release();
+    ctx->h_pos3.release(); ctx->h_vel3.release(); ctx->h_mass.release(); ctx->h_posm4.release(); ctx->h_acc3.release();
     ctx->probe.release(); ctx->sort_scratch.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -252,6 +252,36 @@ int b200_leapfrog_dev(b200_ctx* ctx, void* posm4, void* vel3, const void* acc3, 
     B200_CUDA(cudaSetDevice(ctx->device));
     return leapfrog(ctx, posm4, vel3, acc3, n, n_kicks, dt_kick, a, dt_drift, box,
                     pick_stream(ctx, stream));
+}
+
+int b200_leapfrog_host(b200_ctx* ctx, float* pos3, float* vel3, const float* acc3, const float* mass,
+                       size_t n, int n_kicks, float dt_kick, double a, float dt_drift, float box) {
+    if (!ctx) return B200_ERR_INVALID;
+    if (n == 0) return B200_OK;
+    if (!pos3 || !vel3 || !acc3) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t b3 = n * 3 * sizeof(float);
+    B200_TRY(ctx->h_pos3.reserve(b3));
+    B200_TRY(ctx->h_posm4.reserve(n * 4 * sizeof(float)));
+    B200_TRY(ctx->h_acc3.reserve(b3 + 16));
+    B200_TRY(ctx->h_vel3.reserve(b3 + 16));
+    B200_CUDA(cudaMemcpyAsync(ctx->h_pos3.p, pos3, b3, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(ctx->h_vel3.p, vel3, b3, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(ctx->h_acc3.p, acc3, b3, cudaMemcpyHostToDevice, st));
+    const float* d_mass = nullptr;
+    if (mass) {
+        B200_TRY(ctx->h_mass.reserve(n * sizeof(float)));
+        B200_CUDA(cudaMemcpyAsync(ctx->h_mass.p, mass, n * sizeof(float), cudaMemcpyHostToDevice, st));
+        d_mass = ctx->h_mass.as<float>();
+    }
+    B200_TRY(pack_posm(ctx, ctx->h_pos3.p, d_mass, n, ctx->h_posm4.p, st));
+    B200_TRY(leapfrog(ctx, ctx->h_posm4.p, ctx->h_vel3.p, ctx->h_acc3.p, n, n_kicks, dt_kick, a, dt_drift, box, st));
+    B200_TRY(unpack_pos3(ctx, ctx->h_posm4.p, n, ctx->h_pos3.p, st));
+    B200_CUDA(cudaMemcpyAsync(pos3, ctx->h_pos3.p, b3, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(vel3, ctx->h_vel3.p, b3, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
 }
 
 // include/physics/cosmology_model.hpp:49-61: H(z) with a = 1/(1+z), z = 1/a - 1.

@@ -55,7 +55,7 @@ struct b200_ctx {
     DevBuf part_table;      // device copy of the source-part descriptor table
     DevBuf mass_flag;       // int: number of sources whose mass differs from the first
     // host-entry staging
-    DevBuf h_pos3, h_mass, h_posm4, h_acc3;
+    DevBuf h_pos3, h_vel3, h_mass, h_posm4, h_acc3;
     // probe / standalone sort scratch
     DevBuf probe, sort_scratch;
 

@@ -100,7 +100,22 @@ __global__ void pack_posm_kernel(const float* __restrict__ pos3, const float* __
     posm[i] = make_float4(pos3[3 * i], pos3[3 * i + 1], pos3[3 * i + 2], mass ? mass[i] : 1.0f);
 }
 
+__global__ void unpack_pos3_kernel(const float4* __restrict__ posm, long long n, float* __restrict__ pos3) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = posm[i];
+    pos3[3 * i] = p.x; pos3[3 * i + 1] = p.y; pos3[3 * i + 2] = p.z;
+}
+
 }  // namespace
+
+int unpack_pos3(b200_ctx* ctx, const void* posm4, size_t n, void* pos3, cudaStream_t st) {
+    if (n == 0) return B200_OK;
+    unpack_pos3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float4*)posm4, (long long)n, (float*)pos3);
+    B200_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return B200_OK;
+}
 
 int leapfrog(b200_ctx* ctx, void* posm4, void* vel3, const void* acc3, size_t n, int n_kicks,
              float dt_kick, double a, float dt_drift, float box, cudaStream_t st) {

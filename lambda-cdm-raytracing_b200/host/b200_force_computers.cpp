@@ -1,0 +1,152 @@
+// b200_force_computers.cpp -- see the header.  Host C++ only; every numerical
+// call goes through the C ABI (include/b200grav.h).
+#include "b200_force_computers.hpp"
+
+#include <iostream>
+#include <stdexcept>
+
+#include "b200grav.h"
+#include "core/simulation_context.hpp"
+
+namespace {
+
+[[noreturn]] void fail(const char* where, int status) {
+    throw std::runtime_error(std::string(where) + ": " + b200_error_string(status));
+}
+
+// A caller may hand a ForceComputeParameters through compute_forces' std::any
+// (the factory accepts one and ignores it: force_computer_factory.cpp:14-28).
+const forces::ForceComputeParameters* params_of(const std::any& a) {
+    return std::any_cast<forces::ForceComputeParameters>(&a);
+}
+
+}  // namespace
+
+namespace forces {
+
+B200ComputerBase::~B200ComputerBase() {
+    if (ctx_) b200_ctx_destroy(ctx_);
+    ctx_ = nullptr;
+}
+
+bool B200ComputerBase::initialize(const core::SimulationContext& context) {
+    if (ctx_) return true;
+    const int ctx_dev = context.get_cuda_device_id();
+    if (ctx_dev > 0) device_ = ctx_dev;
+    const int rc = b200_ctx_create(device_, 0, &ctx_);
+    if (rc != B200_OK) {
+        // the reference prints and downgrades to its CPU path here
+        // (tree_force_computer.cpp:54-62); this plugin has none.
+        std::cerr << get_type() << " initialization failed: " << b200_error_string(rc) << std::endl;
+        ctx_ = nullptr;
+        return false;
+    }
+    std::cout << get_type() << " initialized: " << name_ << " (B200 device " << device_ << ")" << std::endl;
+    return true;
+}
+
+void B200ComputerBase::finalize() {
+    if (ctx_) {
+        b200_ctx_destroy(ctx_);
+        ctx_ = nullptr;
+        std::cout << get_type() << " finalized: " << name_ << std::endl;
+    }
+}
+
+void B200ComputerBase::require_ctx() const {
+    if (!ctx_) throw std::runtime_error(get_type() + ": not initialized (no B200 context; there is no CPU fallback)");
+}
+
+void DirectForceComputer::compute_forces(const float* positions, const float* masses, float* forces,
+                                         size_t num_particles, const std::any& params) {
+    if (num_particles == 0) return;                    // tree_force_computer.cpp:83
+    require_ctx();
+    float eps = softening_;
+    if (const ForceComputeParameters* p = params_of(params)) eps = p->softening_length;
+    const int rc = b200_direct_forces_host(ctx_, positions, masses, forces, num_particles, eps, box_size_);
+    if (rc != B200_OK) {
+        std::cerr << "DirectForceComputer::compute_forces failed: " << b200_error_string(rc) << std::endl;
+        fail("DirectForceComputer::compute_forces", rc);
+    }
+    force_evaluations_ += num_particles;
+}
+
+void B200TreeForceComputer::compute_forces(const float* positions, const float* masses, float* forces,
+                                           size_t num_particles, const std::any& params) {
+    if (num_particles == 0) return;
+    require_ctx();
+    float theta = theta_;
+    size_t cap = leaf_capacity_;
+    int depth = max_depth_;
+    if (const ForceComputeParameters* p = params_of(params)) {
+        theta = p->theta; cap = p->leaf_capacity; depth = p->tree_max_depth;
+    }
+    const int rc = b200_tree_forces_host(ctx_, positions, masses, forces, num_particles, theta, (int)cap,
+                                         depth, box_size_);
+    if (rc != B200_OK) {
+        std::cerr << "TreeForceComputer::compute_forces failed: " << b200_error_string(rc) << std::endl;
+        fail("TreeForceComputer::compute_forces", rc);
+    }
+    force_evaluations_ += num_particles;
+}
+
+size_t B200TreeForceComputer::get_node_count() const {
+    size_t n = 0;
+    return (ctx_ && b200_tree_stats(ctx_, &n, nullptr, nullptr, nullptr) == B200_OK) ? n : 0;
+}
+size_t B200TreeForceComputer::get_leaf_count() const {
+    size_t n = 0;
+    return (ctx_ && b200_tree_stats(ctx_, nullptr, &n, nullptr, nullptr) == B200_OK) ? n : 0;
+}
+size_t B200TreeForceComputer::get_tree_depth() const {
+    size_t n = 0;
+    return (ctx_ && b200_tree_stats(ctx_, nullptr, nullptr, &n, nullptr) == B200_OK) ? n : 0;
+}
+
+void register_b200_force_computers(bool replace_cpu_tree) {
+    ForceComputerFactory::register_force_computer<DirectForceComputer>("DirectForceComputer");
+    ForceComputerFactory::register_force_computer<DirectForceComputer>("B200DirectForceComputer");
+    ForceComputerFactory::register_force_computer<B200TreeForceComputer>("B200TreeForceComputer");
+    if (replace_cpu_tree)
+        ForceComputerFactory::register_force_computer<B200TreeForceComputer>("TreeForceComputer");
+}
+
+}  // namespace forces
+
+namespace physics {
+
+B200LeapfrogIntegrator::~B200LeapfrogIntegrator() {
+    if (ctx_) b200_ctx_destroy(ctx_);
+    ctx_ = nullptr;
+}
+
+bool B200LeapfrogIntegrator::initialize(const core::SimulationContext& context) {
+    if (ctx_) return true;
+    if (context.get_cuda_device_id() > 0) device_ = context.get_cuda_device_id();
+    const int rc = b200_ctx_create(device_, 0, &ctx_);
+    if (rc != B200_OK) {
+        std::cerr << "LeapfrogIntegrator initialization failed: " << b200_error_string(rc) << std::endl;
+        ctx_ = nullptr;
+        return false;
+    }
+    return true;
+}
+
+void B200LeapfrogIntegrator::finalize() {
+    if (ctx_) b200_ctx_destroy(ctx_);
+    ctx_ = nullptr;
+}
+
+void B200LeapfrogIntegrator::step(float* positions, float* velocities, const float* forces,
+                                  size_t num_particles, double dt, const std::any& params) {
+    if (num_particles == 0) return;
+    if (!ctx_) throw std::runtime_error("LeapfrogIntegrator: not initialized (no B200 context)");
+    LeapfrogStepParams p;
+    if (const LeapfrogStepParams* q = std::any_cast<LeapfrogStepParams>(&params)) p = *q;
+    // lambda_cdm_impl.cu:170-189: kick by dt*0.5 (double, narrowed to the kernel's float dt), drift by dt
+    const int rc = b200_leapfrog_host(ctx_, positions, velocities, forces, p.masses, num_particles, p.n_kicks,
+                                      (float)(dt * 0.5), p.scale_factor, p.drift ? (float)dt : 0.0f, p.box_size);
+    if (rc != B200_OK) fail("LeapfrogIntegrator::step", rc);
+}
+
+}  // namespace physics

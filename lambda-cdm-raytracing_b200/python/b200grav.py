@@ -22,7 +22,7 @@ EXPORTS = [
     "b200_morton_keys_dev", "b200_sort_pairs_dev", "b200_tree_build_dev",
     "b200_tree_walk_dev", "b200_tree_forces_host", "b200_tree_stats", "b200_tree_export",
     "b200_tree_set_counting", "b200_tree_counters",
-    "b200_leapfrog_dev", "b200_hubble_a", "b200_scale_factor_step", "b200_pack_posm_dev",
+    "b200_leapfrog_dev", "b200_leapfrog_host", "b200_hubble_a", "b200_scale_factor_step", "b200_pack_posm_dev",
     "b200_ipc_export", "b200_ipc_open", "b200_ipc_close",
     "b200_fp32_peak_probe", "b200_last_kernel_ms", "b200_set_timing", "b200_launch_count",
 ]
@@ -63,6 +63,7 @@ def load_library(path=None):
     L.b200_tree_set_counting.argtypes = [vp, i32]
     L.b200_tree_counters.argtypes = [vp, vp]
     L.b200_leapfrog_dev.argtypes = [vp, vp, vp, vp, sz, i32, f32, f64, f32, f32, vp]
+    L.b200_leapfrog_host.argtypes = [vp, vp, vp, vp, vp, sz, i32, f32, f64, f32, f32]
     L.b200_hubble_a.argtypes = [f64] * 5
     L.b200_hubble_a.restype = f64
     L.b200_scale_factor_step.argtypes = [f64] * 6
@@ -225,6 +226,12 @@ class Engine:
         self._check(self.L.b200_leapfrog_dev(self._h, _ptr(posm), _ptr(vel), _ptr(acc), n, n_kicks, dt_kick,
                                              a, dt_drift, box, _stream(stream)))
 
+    def leapfrog_host(self, pos, vel, acc, mass, n_kicks, dt_kick, a, dt_drift, box):
+        n = pos.shape[0]
+        m = None if mass is None else np.ascontiguousarray(mass, np.float32)
+        self._check(self.L.b200_leapfrog_host(self._h, _ptr(pos), _ptr(vel), _ptr(np.ascontiguousarray(acc, np.float32)),
+                                              _ptr(m), n, n_kicks, dt_kick, a, dt_drift, box))
+
     def hubble_a(self, a, om=0.31, ok=0.0, ol=0.69, h=0.67):
         return float(self.L.b200_hubble_a(a, om, ok, ol, h))
 
@@ -328,3 +335,43 @@ class LambdaCDMSimulation:
 
     def velocities(self):
         return self.vel.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------
+# Target-sharded data parallelism: rank r owns the contiguous
+# original-index range [r*N/G, (r+1)*N/G) of the targets; sources are all-gathered.
+def shard_range(n, rank, world):
+    return rank * n // world, (rank + 1) * n // world
+
+
+class SourceGather:
+    """All-gathers each rank's float4 shard into the replicated posm array with
+    torch.distributed (NCCL on GPUs, gloo in the CPU tests).  Semantic ancestor:
+    ClusterCommunicator::gather_all_particles (reference src/mpi/cluster_comm.cpp:218-247)."""
+
+    def __init__(self, n, rank, world, group=None):
+        self.n, self.rank, self.world, self.group = n, rank, world, group
+        self.lo, self.hi = shard_range(n, rank, world)
+        self.equal = (n % world == 0)
+
+    def __call__(self, posm):
+        import torch.distributed as dist
+        if self.world == 1:
+            return posm
+        mine = posm[self.lo:self.hi].clone()
+        if self.equal:
+            dist.all_gather_into_tensor(posm.view(-1), mine.view(-1), group=self.group)
+        else:
+            outs = [posm[slice(*shard_range(self.n, r, self.world))] for r in range(self.world)]
+            if posm.is_cuda:
+                dist.all_gather(outs, mine, group=self.group)
+            else:   # gloo needs equal-sized outputs: pad
+                width = max(o.shape[0] for o in outs)
+                import torch
+                pad = torch.zeros((width, posm.shape[1]), dtype=posm.dtype)
+                pad[: mine.shape[0]] = mine
+                bufs = [torch.empty_like(pad) for _ in range(self.world)]
+                dist.all_gather(bufs, pad, group=self.group)
+                for o, b in zip(outs, bufs):
+                    o.copy_(b[: o.shape[0]])
+        return posm

@@ -1,0 +1,133 @@
+// host_parity_test.cpp -- the plugin seen from the reference's side, written the
+// way the reference's own (never compiled) test reads (CONTRIBUTING.md:106-131):
+// build computers through forces::ForceComputerFactory, call
+// IForceComputer::compute_forces on host arrays, compare with the reference's
+// own CPU TreeForceComputer on identical inputs.
+//
+// TEST INFRASTRUCTURE: links the reference's CPU sources (compiled from where
+// they lie by tests/host/Makefile) as the checker.  Run on the GPU box by
+// tests/test_gpu_host_plugin.py.
+#include <cmath>
+#include <cstdio>
+#include <iostream>
+#include <random>
+#include <sstream>
+#include <vector>
+
+#include "b200_force_computers.hpp"
+#include "core/simulation_context.hpp"
+#include "forces/tree_force_computer.hpp"
+
+static int failures = 0;
+#define CHECK(cond, ...)                                               \
+    do {                                                               \
+        if (cond) { std::printf("PASS  "); } else { std::printf("FAIL  "); ++failures; } \
+        std::printf(__VA_ARGS__); std::printf("\n");                   \
+    } while (0)
+
+static double rel_l2(const std::vector<float>& a, const std::vector<float>& b) {
+    double num = 0, den = 0;
+    for (size_t i = 0; i < a.size(); ++i) { double d = (double)a[i] - b[i]; num += d * d; den += (double)b[i] * b[i]; }
+    return std::sqrt(num / (den > 0 ? den : 1));
+}
+
+int main() {
+    using namespace forces;
+    std::ostringstream quiet;
+    auto* old = std::cout.rdbuf(quiet.rdbuf());            // the reference is chatty on stdout
+    core::SimulationContext ctx;
+    ForceComputerFactory::register_all_builtin_computers();                       // basic_simulation.cpp:12-13
+    auto cpu_tree = ForceComputerFactory::create_force_computer("TreeForceComputer", "cpu_tree");
+    cpu_tree->initialize(ctx);                                                     // downgrades itself to CPU
+    TreeForceComputer cpu_direct("cpu_direct", 0.5f, /*leaf_capacity=*/size_t(1) << 40, 20);   // one root leaf
+    cpu_direct.initialize(ctx);
+
+    register_b200_force_computers();                                               // the plugin
+    auto direct = ForceComputerFactory::create_direct_computer("direct");
+    auto tree = ForceComputerFactory::create_tree_computer("tree");
+    std::cout.rdbuf(old);
+    CHECK(direct && direct->get_type() == "DirectForceComputer", "factory creates DirectForceComputer");
+    CHECK(tree && tree->get_type() == "TreeForceComputer" && tree->supports_gpu(), "factory creates the B200 TreeForceComputer");
+    std::cout.rdbuf(quiet.rdbuf());
+    const bool ok_d = direct->initialize(ctx), ok_t = tree->initialize(ctx);
+    std::cout.rdbuf(old);
+    CHECK(ok_d && ok_t, "initialize() on a B200 (no CPU fallback exists)");
+    if (!ok_d || !ok_t) return 2;
+
+    {   // CONTRIBUTING.md:118-131
+        std::vector<float> pos = {0, 0, 0, 1, 0, 0}, m = {1, 1}, f(6), g(6);
+        direct->compute_forces(pos.data(), m.data(), f.data(), 2);
+        cpu_direct.compute_forces(pos.data(), m.data(), g.data(), 2);
+        CHECK(std::fabs(f[0] - 0.999850035f) < 2e-6f && std::fabs(f[3] + 0.999850035f) < 2e-6f && std::fabs(f[0] - g[0]) < 2e-6f,
+              "two-body KAT: a0.x = %.9f (reference CPU %.9f)", f[0], g[0]);
+        direct->compute_forces(pos.data(), m.data(), f.data(), 0);               // num_particles == 0 -> return
+    }
+
+    const size_t n = 20000;
+    std::mt19937 gen(42);
+    std::uniform_real_distribution<float> u(-50.0f, 50.0f);
+    std::vector<float> pos(3 * n), mass(n, 1.0f), a_gpu(3 * n), a_cpu(3 * n);
+    for (size_t i = 0; i < 3 * n; ++i) pos[i] = u(gen);
+
+    direct->compute_forces(pos.data(), mass.data(), a_gpu.data(), n);
+    cpu_direct.compute_forces(pos.data(), mass.data(), a_cpu.data(), n);
+    double e = rel_l2(a_gpu, a_cpu);
+    CHECK(e < 1e-5, "direct sum vs reference CPU leaf loop, N=%zu: rel-L2 %.2e (gate 1e-5)", n, e);
+
+    tree->compute_forces(pos.data(), mass.data(), a_gpu.data(), n);
+    cpu_tree->compute_forces(pos.data(), mass.data(), a_cpu.data(), n);
+    e = rel_l2(a_gpu, a_cpu);
+    CHECK(e < 1e-3, "Barnes-Hut theta=0.5 leaf=8 vs reference CPU tree: rel-L2 %.2e (gate 1e-3)", e);
+    auto* bt = dynamic_cast<B200TreeForceComputer*>(tree.get());
+    auto* ct = dynamic_cast<TreeForceComputer*>(cpu_tree.get());
+    CHECK(bt && ct && bt->get_node_count() == ct->get_node_count() && bt->get_leaf_count() == ct->get_leaf_count() &&
+              bt->get_tree_depth() == ct->get_tree_depth(),
+          "tree statistics equal: %zu nodes, %zu leaves, depth %zu", bt->get_node_count(), bt->get_leaf_count(), bt->get_tree_depth());
+
+    {   // ForceComputeParameters through std::any
+        ForceComputeParameters p;
+        p.softening_length = 0.5f;
+        std::vector<float> b(3 * n);
+        direct->compute_forces(pos.data(), mass.data(), b.data(), n, p);
+        CHECK(rel_l2(b, a_cpu) > 1e-3, "softening_length from ForceComputeParameters is honoured");
+    }
+
+    {   // KDK: IIntegrator + IForceComputer + ICosmologyModel, 5 steps, against the same loop on the CPU tree
+        physics::B200LeapfrogIntegrator integ("leapfrog");
+        physics::LambdaCDMModel cosmo("lcdm");
+        integ.initialize(ctx);
+        const size_t m_n = 4096;
+        std::vector<float> x(pos.begin(), pos.begin() + 3 * m_n), v(3 * m_n, 0.0f), f(3 * m_n), ms(m_n, 1.0f);
+        std::vector<float> xc = x, vc = v, fc(3 * m_n);
+        double a = 1.0, ac = 1.0;
+        const double dt = 1e-3;
+        tree->compute_forces(x.data(), ms.data(), f.data(), m_n);
+        cpu_tree->compute_forces(xc.data(), ms.data(), fc.data(), m_n);
+        for (int s = 0; s < 5; ++s) {
+            physics::LeapfrogStepParams p; p.scale_factor = a; p.n_kicks = 1; p.drift = true;
+            integ.step(x.data(), v.data(), f.data(), m_n, dt, p);
+            cosmo.update_scale_factor(a, dt);
+            tree->compute_forces(x.data(), ms.data(), f.data(), m_n);
+            p.scale_factor = a; p.drift = false;
+            integ.step(x.data(), v.data(), f.data(), m_n, dt, p);
+            // CPU restatement of lambda_cdm_kernels.cu:307-333 on the reference tree's forces
+            const float hdt = (float)(dt * 0.5), fdt = (float)dt;
+            float a2 = (float)(1.0f / (ac * ac));
+            for (size_t i = 0; i < 3 * m_n; ++i) { vc[i] += fc[i] * 1.0f * hdt * a2; xc[i] += vc[i] * fdt; }
+            ac += ac * cosmo.hubble_function(ac) * dt;
+            cpu_tree->compute_forces(xc.data(), ms.data(), fc.data(), m_n);
+            a2 = (float)(1.0f / (ac * ac));
+            for (size_t i = 0; i < 3 * m_n; ++i) vc[i] += fc[i] * 1.0f * hdt * a2;
+        }
+        double mx = 0;
+        for (size_t i = 0; i < 3 * m_n; ++i) mx = std::fmax(mx, std::fabs((double)x[i] - xc[i]));
+        CHECK(a == ac && mx < 1e-4 * 100.0, "5 KDK steps through IIntegrator/ICosmologyModel: a = %.6f, max |dx| = %.2e (gate 1e-2)", a, mx);
+    }
+
+    std::cout.rdbuf(quiet.rdbuf());
+    direct->finalize(); direct->finalize();                                        // idempotent
+    tree->finalize(); cpu_tree->finalize();
+    std::cout.rdbuf(old);
+    std::printf("%s (%d failure%s)\n", failures ? "HOST PARITY FAILED" : "HOST PARITY OK", failures, failures == 1 ? "" : "s");
+    return failures ? 1 : 0;
+}

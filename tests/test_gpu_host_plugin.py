@@ -1,0 +1,21 @@
+"""-m gpu: the C++ plugin layer (IForceComputer / IIntegrator / ICosmologyModel
+adapters + ForceComputerFactory registration) exercised from a C++ program that
+also links the reference's CPU TreeForceComputer as the checker."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def test_host_plugin_parity():
+    exe = os.path.join(ROOT, "tests", "host", "_bin", "host_parity_test")
+    if not os.path.exists(exe):
+        pytest.skip("tests/host/_bin/host_parity_test not built (needs the reference headers at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-4000:], r.stderr[-2000:])
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "HOST PARITY OK" in r.stdout and "FAIL" not in r.stdout
