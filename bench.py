@@ -138,9 +138,9 @@ def run_cpu_baseline(target_seconds=12.0):
     kind = cpu_kind()
     n_sample = 16384
     with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("spawn")) as pool:
-        inter, dt = cpu_reference_batch(cores, 4096, 1, pool, kind)       # warm: page in, spawn
-        rate1 = inter / dt
-        reps = max(1, int(target_seconds * rate1 / (cores * float(n_sample) ** 2)))
+        cpu_reference_batch(cores, 2048, 1, pool, kind)                   # warm: spawn workers, page in
+        inter, dt = cpu_reference_batch(cores, n_sample, 1, pool, kind)   # calibrate on the real sample size
+        reps = max(1, int(round(target_seconds / dt)))
         inter, dt = cpu_reference_batch(cores, n_sample, reps, pool, kind)
     return {"value": inter / dt, "unit": "interactions/s", "cores": cores, "kind": kind,
             "sample": f"{cores} independent single-threaded instances of the reference CPU direct sum "
@@ -349,7 +349,8 @@ def bench_gpu(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
-                "bound": "fp32_fma", "kernel": "direct_kernel<4,false>" if args.workload == "direct" else "walk_kernel",
+                "bound": "fp32_fma", "kernel": ("direct_kernel<R=6,THREADS=256,1 CTA/SM,open,equal-mass> (11 FP32 lane-ops + 1 MUFU per interaction; "
+                           "unequal masses run the 12-op instance)") if args.workload == "direct" else "walk_kernel",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": None,
                 "peak_source": "FFMA/FFMA2 register-chain probe run in this process (b200_fp32_peak_probe); "

@@ -160,6 +160,9 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage_buf = reinterpret_cast<float*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * TILE_BYTES);
+    // FP64 running sums live in shared memory (touched once per tile): 3R doubles per
+    // thread would otherwise cost 6R registers that the inner loop needs for ILP.
+    double* dsum = reinterpret_cast<double*>(smem_raw + STAGES * TILE_BYTES + 64);
 
     const int tid = threadIdx.x;
     const long long G = gridDim.x, c = blockIdx.x;
@@ -189,7 +192,6 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
 
     const u64 eps2_2 = pk(eps2, eps2);
     u64 nxi[R], nyi[R], nzi[R];          // packed (-x_i, -x_i) per register-blocked target
-    double dax[R], day[R], daz[R];
     auto load_targets = [&](long long blk) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -199,7 +201,9 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
             nxi[r] = pk(-p.x, -p.x);
             nyi[r] = pk(-p.y, -p.y);
             nzi[r] = pk(-p.z, -p.z);
-            dax[r] = day[r] = daz[r] = 0.0;
+            dsum[(0 * R + r) * THREADS + tid] = 0.0;
+            dsum[(1 * R + r) * THREADS + tid] = 0.0;
+            dsum[(2 * R + r) * THREADS + tid] = 0.0;
         }
     };
     load_targets(b);
@@ -273,9 +277,9 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             float lo, hi;
-            unpk(ax[r], lo, hi); dax[r] += (double)(lo + hi);
-            unpk(ay[r], lo, hi); day[r] += (double)(lo + hi);
-            unpk(az[r], lo, hi); daz[r] += (double)(lo + hi);
+            unpk(ax[r], lo, hi); dsum[(0 * R + r) * THREADS + tid] += (double)(lo + hi);
+            unpk(ay[r], lo, hi); dsum[(1 * R + r) * THREADS + tid] += (double)(lo + hi);
+            unpk(az[r], lo, hi); dsum[(2 * R + r) * THREADS + tid] += (double)(lo + hi);
         }
         __syncthreads();      // every warp is done with stage s -> it may be refilled
 
@@ -285,9 +289,9 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
             double* rec = partials + (size_t)(c + b) * 3 * BLOCK_I;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                rec[0 * BLOCK_I + r * THREADS + tid] = dax[r];
-                rec[1 * BLOCK_I + r * THREADS + tid] = day[r];
-                rec[2 * BLOCK_I + r * THREADS + tid] = daz[r];
+                rec[0 * BLOCK_I + r * THREADS + tid] = dsum[(0 * R + r) * THREADS + tid];
+                rec[1 * BLOCK_I + r * THREADS + tid] = dsum[(1 * R + r) * THREADS + tid];
+                rec[2 * BLOCK_I + r * THREADS + tid] = dsum[(2 * R + r) * THREADS + tid];
             }
             if (t == n_tiles) {
                 t = 0;
@@ -334,7 +338,7 @@ int launch_direct(b200_ctx* ctx, const DirectSources& src, const float4* targets
     constexpr int BLOCK_I = THREADS * R;
     auto kern_g = direct_kernel<R, THREADS, MINB, PERIODIC, false>;
     auto kern_u = direct_kernel<R, THREADS, MINB, PERIODIC, true>;
-    const size_t smem = STAGES * TILE_BYTES + STAGES * sizeof(uint64_t);
+    const size_t smem = STAGES * TILE_BYTES + 64 + (size_t)3 * R * THREADS * sizeof(double);
     static bool configured = false;     // per template instantiation
     static int blocks_per_sm = 0;
     if (!configured) {
@@ -415,6 +419,8 @@ int direct_forces(b200_ctx* ctx, const DirectSources& src, const void* targets4,
             B200_VARIANT(2, 256, 2) B200_VARIANT(4, 256, 1) B200_VARIANT(4, 256, 2) B200_VARIANT(5, 256, 1)
             B200_VARIANT(6, 256, 1) B200_VARIANT(8, 256, 1) B200_VARIANT(4, 384, 1) B200_VARIANT(4, 512, 1)
             B200_VARIANT(3, 512, 1) B200_VARIANT(6, 128, 2) B200_VARIANT(8, 128, 2) B200_VARIANT(7, 256, 1)
+            B200_VARIANT(6, 384, 1) B200_VARIANT(5, 384, 1) B200_VARIANT(8, 192, 1) B200_VARIANT(6, 320, 1)
+            B200_VARIANT(10, 256, 1) B200_VARIANT(5, 128, 3) B200_VARIANT(4, 128, 4)
 #undef B200_VARIANT
             return B200_ERR_UNSUPPORTED;
         }

@@ -56,17 +56,66 @@ ffma2_probe_kernel(float* out, int iters, float a, float b) {
     if (s == 123.456f) out[0] = s;
 }
 
+// modes 2..5: what else the inner loop issues -- FADD2, FMUL2, and FFMA2 with one
+// MUFU.RSQ per 6 / per 3 packed ops (the direct-sum mix is 2 MUFU per 11-12 packed).
+template <int MODE>
+__global__ void __launch_bounds__(1024, 2)
+mix_probe_kernel(float* out, int iters, float a, float b) {
+    unsigned long long acc[CHAINS / 2], a2, b2;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(a2) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(b2) : "f"(b));
+    float mu[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mu[k] = 1.0f + threadIdx.x + k;
+#pragma unroll
+    for (int k = 0; k < CHAINS / 2; ++k) {
+        float x = (float)(threadIdx.x + k);
+        asm("mov.b64 %0, {%1, %1};" : "=l"(acc[k]) : "f"(x));
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < INNER; ++u) {
+#pragma unroll
+            for (int k = 0; k < CHAINS / 2; ++k) {
+                if (MODE == 2) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(acc[k]) : "l"(b2));
+                else if (MODE == 3) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(acc[k]) : "l"(a2));
+                else asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[k]) : "l"(a2), "l"(b2));
+            }
+            if (MODE == 4) {
+                asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(mu[u & 3]));
+                if ((u & 3) == 3) asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(mu[0]));   // ~1.25 per 8 packed
+            }
+            if (MODE == 5) {
+                asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(mu[u & 3]));
+                asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(mu[(u + 1) & 3]));          // 2 per 8 packed
+            }
+        }
+    }
+    float s = mu[0] + mu[1] + mu[2] + mu[3];
+#pragma unroll
+    for (int k = 0; k < CHAINS / 2; ++k) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[k]));
+        s += lo + hi;
+    }
+    if (s == 123.456f) out[0] = s;
+}
+
 }  // namespace
 
 int fp32_peak_probe(b200_ctx* ctx, int mode, int iters, double* tflops, float* ms_out) {
-    if (iters <= 0 || (mode != 0 && mode != 1)) return B200_ERR_INVALID;
+    if (iters <= 0 || mode < 0 || mode > 5) return B200_ERR_INVALID;
     B200_TRY(ctx->probe.reserve(256));
     cudaStream_t st = ctx->stream;
     const int grid = ctx->sm_count * 2, block = 1024;
     for (int rep = 0; rep < 2; ++rep) {      // rep 0 warms up, rep 1 is timed
         B200_CUDA(cudaEventRecord(ctx->ev0, st));
         if (mode == 0) ffma_probe_kernel<<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
-        else ffma2_probe_kernel<<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
+        else if (mode == 1) ffma2_probe_kernel<<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
+        else if (mode == 2) mix_probe_kernel<2><<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
+        else if (mode == 3) mix_probe_kernel<3><<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
+        else if (mode == 4) mix_probe_kernel<4><<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
+        else mix_probe_kernel<5><<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
         B200_CUDA(cudaEventRecord(ctx->ev1, st));
         B200_CUDA(cudaGetLastError());
         B200_CUDA(cudaEventSynchronize(ctx->ev1));
