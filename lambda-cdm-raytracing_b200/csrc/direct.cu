@@ -406,10 +406,11 @@ int direct_forces(b200_ctx* ctx, const DirectSources& src, const void* targets4,
     }
     const float4* tg = (const float4*)targets4;
     float* out = (float*)acc3;
-    // Register blocking: 6 targets/thread (one 256-thread CTA per SM, ~240 registers)
-    // once there is enough work to fill the chip; 2 targets/thread, 2 CTAs per SM
-    // below that so small problems still spread over all SMs.
-    const bool small = n_targets < (size_t)ctx->sm_count * 256 * 6;
+    // Register blocking: 6 targets/thread (one 256-thread CTA per SM, 228 registers) whenever
+    // the flattened (target block x source tile) space gives every CTA several units of work
+    // and the last, partly filled target block wastes little; 2 targets/thread below that.
+    const long long units6 = (((long long)n_targets + 1535) / 1536) * (long long)src.total_tiles;
+    const bool small = n_targets < 4 * 1536 || units6 < 4ll * ctx->sm_count;
     if (const char* v = getenv("B200_DIRECT_VARIANT")) {      // tuning hook: "R,THREADS,MINB"
         int r = 0, th = 0, mb = 0;
         if (sscanf(v, "%d,%d,%d", &r, &th, &mb) == 3 && box == 0.f) {

@@ -101,10 +101,46 @@ mix_probe_kernel(float* out, int iters, float a, float b) {
     if (s == 123.456f) out[0] = s;
 }
 
+// modes 6/7: FP64 pipe alone (DFMA chains) and FFMA2 + DFMA interleaved 1:1 -- are the
+// FP32 and FP64 pipes independent, i.e. does the mix take max(t32, t64) or t32 + t64?
+template <bool WITH_F32>
+__global__ void __launch_bounds__(1024, 2)
+dual_probe_kernel(float* out, int iters, float a, float b) {
+    unsigned long long acc[CHAINS / 2], a2, b2;
+    double dacc[CHAINS / 2];
+    const double da = (double)a, db = (double)b;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(a2) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(b2) : "f"(b));
+#pragma unroll
+    for (int k = 0; k < CHAINS / 2; ++k) {
+        float x = (float)(threadIdx.x + k);
+        asm("mov.b64 %0, {%1, %1};" : "=l"(acc[k]) : "f"(x));
+        dacc[k] = (double)x;
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < INNER; ++u) {
+#pragma unroll
+            for (int k = 0; k < CHAINS / 2; ++k) {
+                if (WITH_F32) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[k]) : "l"(a2), "l"(b2));
+                asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dacc[k]) : "d"(da), "d"(db));
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < CHAINS / 2; ++k) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[k]));
+        s += lo + hi + (float)dacc[k];
+    }
+    if (s == 123.456f) out[0] = s;
+}
+
 }  // namespace
 
 int fp32_peak_probe(b200_ctx* ctx, int mode, int iters, double* tflops, float* ms_out) {
-    if (iters <= 0 || mode < 0 || mode > 5) return B200_ERR_INVALID;
+    if (iters <= 0 || mode < 0 || mode > 7) return B200_ERR_INVALID;
     B200_TRY(ctx->probe.reserve(256));
     cudaStream_t st = ctx->stream;
     const int grid = ctx->sm_count * 2, block = 1024;
@@ -115,7 +151,9 @@ int fp32_peak_probe(b200_ctx* ctx, int mode, int iters, double* tflops, float* m
         else if (mode == 2) mix_probe_kernel<2><<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
         else if (mode == 3) mix_probe_kernel<3><<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
         else if (mode == 4) mix_probe_kernel<4><<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
-        else mix_probe_kernel<5><<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
+        else if (mode == 5) mix_probe_kernel<5><<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
+        else if (mode == 6) dual_probe_kernel<false><<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
+        else dual_probe_kernel<true><<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
         B200_CUDA(cudaEventRecord(ctx->ev1, st));
         B200_CUDA(cudaGetLastError());
         B200_CUDA(cudaEventSynchronize(ctx->ev1));

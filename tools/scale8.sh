@@ -1,0 +1,16 @@
+#!/bin/bash
+# 8-GPU validation of the sharded paths (run under: gpurun --gpus 8 -- bash tools/scale8.sh)
+run() { # name, nproc, args...
+  name=$1; np=$2; shift 2
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $np --master-addr 127.0.0.1 --master-port $((29600 + RANDOM % 300)) \
+     bench.py --gpus $np "$@" > gpurun_out/$name.json 2> gpurun_out/$name.err
+  echo "$name rc=$?" >> gpurun_out/scale8.log
+}
+: > gpurun_out/scale8.log
+run direct_1m_8gpu 8 --steps 5 --warmup 3
+run direct_1m_4gpu 4 --steps 5 --warmup 3
+run direct_8m_8gpu 8 --steps 2 --warmup 3 --particles 8388608
+run tree_16m_kdk_8gpu 8 --steps 5 --warmup 3 --workload tree --particles 16777216 --kdk
+run tree_16m_kdk_4gpu 4 --steps 3 --warmup 3 --workload tree --particles 16777216 --kdk
+run tree_16m_kdk_2gpu 2 --steps 3 --warmup 3 --workload tree --particles 16777216 --kdk
+nvidia-smi topo -m > gpurun_out/topo8.log 2>&1
