@@ -194,7 +194,8 @@ def _workload_config(args):
         return {"workload": f"DirectForceComputer, {n} particles (BASELINE configs[1] when n = 2^20), "
                             f"uniform [-50,50)^3, unit masses, eps = {EPS}, one force evaluation per step; "
                             f"targets sharded over {args.gpus} GPU(s), sources all-gathered",
-                "particles": n, "eps": EPS, "l2": "flushed between timed steps (512 MB write)"}
+                "particles": n, "eps": EPS, "l2": "flushed between timed steps (512 MB write)",
+                "sources": getattr(args, "sources", "allgather")}
     return {"workload": f"TreeForceComputer Barnes-Hut theta=0.5 leaf=8 max_depth=20, {n} particles "
                         f"(BASELINE configs[2] scale), uniform [-50,50)^3, build + walk per step",
             "particles": n, "theta": 0.5, "leaf_capacity": 8, "l2": "flushed between timed steps (512 MB write)"}
@@ -240,7 +241,24 @@ def bench_gpu(args):
                 outs = [posm[r * n // world:(r + 1) * n // world] for r in range(world)]
                 dist.all_gather(outs, shard)
 
+    masses_equal = bool((mass == mass[0]).all())    # every rank holds the same (replicated) initial masses
+    peers = None
+    if world > 1 and args.sources == "peer" and args.workload == "direct":
+        def _exchange(mine):
+            out = [None] * world
+            dist.all_gather_object(out, mine)
+            return out
+        _tok = torch.zeros(1, device=dev)
+        peers = b200grav.PeerSources(eng, n, rank, world, lambda: dist.all_reduce(_tok), _exchange)
+
     def step():
+        if peers is not None:       # fused: no all-gather, source tiles are pulled from peer HBM over NVLink
+            if args.kdk:
+                eng.leapfrog_dev(shard, vel, acc, nl, 2, np.float32(kdk["dt"] * 0.5), kdk["a"], np.float32(kdk["dt"]), 0.0)
+                kdk["a"] = eng.scale_factor_step(kdk["a"], kdk["dt"])
+            parts = peers.publish(shard)
+            eng.direct_forces_parts_dev(parts, peers.lens, shard, nl, acc, eps=EPS, all_masses_equal=masses_equal)
+            return
         if args.kdk:    # closing half-kick of the previous step + opening half-kick + drift, one pass
             eng.leapfrog_dev(shard, vel, acc, nl, 2, np.float32(kdk["dt"] * 0.5), kdk["a"], np.float32(kdk["dt"]), 0.0)
             kdk["a"] = eng.scale_factor_step(kdk["a"], kdk["dt"])
@@ -406,6 +424,8 @@ def bench_gpu(args):
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        if peers is not None:
+            peers.close()
         dist.destroy_process_group()
     eng.close()
 
@@ -419,6 +439,9 @@ def main():
     ap.add_argument("--workload", default="direct", choices=["direct", "tree"])
     ap.add_argument("--particles", type=int, default=1 << 20)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sources", default="allgather", choices=["allgather", "peer"],
+                    help="N>1 direct sum: NCCL all-gather of the shards (default) or peer-mapped source tiles "
+                         "pulled over NVLink by the force kernel itself")
     ap.add_argument("--kdk", action="store_true",
                     help="each step is a full Lambda-CDM KDK leapfrog step (fused kick-kick-drift pass, scale-factor "
                          "update, source all-gather, force evaluation) instead of a bare force evaluation")

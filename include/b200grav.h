@@ -88,11 +88,15 @@ int b200_pack_tiles_dev(b200_ctx* ctx, const void* posm4, size_t n, void* tiles,
  * part_len[p] particles each, concatenated in order.  Buffers may live on PEER
  * GPUs (NVLink-mapped, see b200_ipc_*): the kernel pulls its source tiles
  * straight over NVLink, so no all-gather precedes it.  Targets are local:
- * targets4 float4[n_targets], acc3 float[3*n_targets]. */
+ * targets4 float4[n_targets], acc3 float[3*n_targets].  all_masses_equal != 0 is
+ * the caller's promise that every source in every part has the same mass (the
+ * ranks agree on it once, masses do not change during a run): the 11-op
+ * equal-mass instance runs.  0 = general masses. */
 int b200_direct_forces_parts_dev(b200_ctx* ctx, const void* const* parts,
                                  const size_t* part_len, int n_parts,
                                  const void* targets4, size_t n_targets,
-                                 float eps, float box, void* acc3, void* stream);
+                                 float eps, float box, int all_masses_equal,
+                                 void* acc3, void* stream);
 
 /* ---- Barnes-Hut (rows T1-T6) ----------------------------------------------
  * Morton keys: replaces compute_morton_codes_kernel + morton3D
@@ -176,6 +180,8 @@ int b200_pack_posm_dev(b200_ctx* ctx, const void* pos3, const void* mass, size_t
  * caller's NCCL (torch.distributed) or pulled over NVLink by
  * b200_direct_forces_parts_dev from peer buffers mapped with these calls.
  * handle is a 64-byte cudaIpcMemHandle_t. */
+int b200_device_alloc(b200_ctx* ctx, size_t bytes, void** dev_ptr);   /* cudaMalloc: exportable */
+int b200_device_free(b200_ctx* ctx, void* dev_ptr);
 int b200_ipc_export(b200_ctx* ctx, void* dev_ptr, unsigned char handle[64]);
 int b200_ipc_open(b200_ctx* ctx, const unsigned char handle[64], void** dev_ptr);
 int b200_ipc_close(b200_ctx* ctx, void* dev_ptr);

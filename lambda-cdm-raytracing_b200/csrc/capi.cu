@@ -67,7 +67,7 @@ int b200_ctx_destroy(b200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     tree_destroy(ctx);
-    ctx->src_tiles.release(); ctx->partials.release(); ctx->part_table.release(); ctx->mass_flag.release();
+    ctx->src_tiles.release(); ctx->partials.release(); ctx->part_table.release(); ctx->mass_flag.release(); ctx->zero_flag.release();
     ctx->h_pos3.release(); ctx->h_vel3.release(); ctx->h_mass.release(); ctx->h_posm4.release(); ctx->h_acc3.release();
     ctx->probe.release(); ctx->sort_scratch.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -117,7 +117,7 @@ int b200_pack_tiles_dev(b200_ctx* ctx, const void* posm4, size_t n, void* tiles,
 
 int b200_direct_forces_parts_dev(b200_ctx* ctx, const void* const* parts, const size_t* part_len,
                                  int n_parts, const void* targets4, size_t n_targets, float eps,
-                                 float box, void* acc3, void* stream) {
+                                 float box, int all_masses_equal, void* acc3, void* stream) {
     if (!ctx) return B200_ERR_INVALID;
     if (n_targets == 0) return B200_OK;
     if (!parts || !part_len || n_parts < 1 || n_parts > DIRECT_MAX_PARTS || !targets4 || !acc3)
@@ -138,7 +138,13 @@ int b200_direct_forces_parts_dev(b200_ctx* ctx, const void* const* parts, const 
     }
     src.n_parts = np;
     src.total_tiles = total;
-    return direct_forces(ctx, src, targets4, n_targets, eps, box, acc3, nullptr, pick_stream(ctx, stream));
+    const int* flag = nullptr;
+    if (all_masses_equal) {         // a device int that reads 0 = "no source differs from the first"
+        B200_TRY(ctx->zero_flag.reserve(sizeof(int)));
+        B200_CUDA(cudaMemsetAsync(ctx->zero_flag.p, 0, sizeof(int), pick_stream(ctx, stream)));
+        flag = ctx->zero_flag.as<int>();
+    }
+    return direct_forces(ctx, src, targets4, n_targets, eps, box, acc3, flag, pick_stream(ctx, stream));
 }
 
 int b200_direct_forces_host(b200_ctx* ctx, const float* pos3, const float* mass, float* acc3,
@@ -306,6 +312,20 @@ int b200_pack_posm_dev(b200_ctx* ctx, const void* pos3, const void* mass, size_t
 }
 
 // ---- multi-GPU peer mapping ------------------------------------------------
+int b200_device_alloc(b200_ctx* ctx, size_t bytes, void** dev_ptr) {
+    if (!ctx || !dev_ptr || bytes == 0) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    if (cudaMalloc(dev_ptr, bytes) != cudaSuccess) { cudaGetLastError(); return B200_ERR_NOMEM; }
+    return B200_OK;
+}
+
+int b200_device_free(b200_ctx* ctx, void* dev_ptr) {
+    if (!ctx) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    if (dev_ptr) B200_CUDA(cudaFree(dev_ptr));
+    return B200_OK;
+}
+
 int b200_ipc_export(b200_ctx* ctx, void* dev_ptr, unsigned char handle[64]) {
     if (!ctx || !dev_ptr || !handle) return B200_ERR_INVALID;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");

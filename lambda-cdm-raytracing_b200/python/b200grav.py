@@ -23,7 +23,7 @@ EXPORTS = [
     "b200_tree_walk_dev", "b200_tree_forces_host", "b200_tree_stats", "b200_tree_export",
     "b200_tree_set_counting", "b200_tree_counters",
     "b200_leapfrog_dev", "b200_leapfrog_host", "b200_hubble_a", "b200_scale_factor_step", "b200_pack_posm_dev",
-    "b200_ipc_export", "b200_ipc_open", "b200_ipc_close",
+    "b200_device_alloc", "b200_device_free", "b200_ipc_export", "b200_ipc_open", "b200_ipc_close",
     "b200_fp32_peak_probe", "b200_last_kernel_ms", "b200_set_timing", "b200_launch_count",
 ]
 
@@ -52,7 +52,7 @@ def load_library(path=None):
     L.b200_tiles_bytes.argtypes = [sz]
     L.b200_tiles_bytes.restype = sz
     L.b200_pack_tiles_dev.argtypes = [vp, vp, sz, vp, vp]
-    L.b200_direct_forces_parts_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), i32, vp, sz, f32, f32, vp, vp]
+    L.b200_direct_forces_parts_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), i32, vp, sz, f32, f32, i32, vp, vp]
     L.b200_morton_keys_dev.argtypes = [vp, vp, sz, f32, vp, vp]
     L.b200_sort_pairs_dev.argtypes = [vp, vp, sz, vp, vp, vp]
     L.b200_tree_build_dev.argtypes = [vp, vp, sz, f32, i32, i32, vp]
@@ -69,6 +69,8 @@ def load_library(path=None):
     L.b200_scale_factor_step.argtypes = [f64] * 6
     L.b200_scale_factor_step.restype = f64
     L.b200_pack_posm_dev.argtypes = [vp, vp, vp, sz, vp, vp]
+    L.b200_device_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+    L.b200_device_free.argtypes = [vp, vp]
     L.b200_ipc_export.argtypes = [vp, vp, vp]
     L.b200_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
     L.b200_ipc_close.argtypes = [vp, vp]
@@ -162,12 +164,13 @@ class Engine:
     def pack_tiles_dev(self, posm, n, tiles, stream=None):
         self._check(self.L.b200_pack_tiles_dev(self._h, _ptr(posm), n, _ptr(tiles), _stream(stream)))
 
-    def direct_forces_parts_dev(self, parts, part_len, targets, n_targets, acc, eps=0.01, box=0.0, stream=None):
+    def direct_forces_parts_dev(self, parts, part_len, targets, n_targets, acc, eps=0.01, box=0.0, stream=None,
+                                all_masses_equal=False):
         k = len(parts)
         arr_p = (C.c_void_p * k)(*[_ptr(p) for p in parts])
         arr_n = (C.c_size_t * k)(*part_len)
         self._check(self.L.b200_direct_forces_parts_dev(self._h, arr_p, arr_n, k, _ptr(targets), n_targets,
-                                                        eps, box, _ptr(acc), _stream(stream)))
+                                                        eps, box, int(all_masses_equal), _ptr(acc), _stream(stream)))
         return acc
 
     # -- tree ----------------------------------------------------------------
@@ -242,6 +245,14 @@ class Engine:
         self._check(self.L.b200_pack_posm_dev(self._h, _ptr(pos3), _ptr(mass), n, _ptr(posm), _stream(stream)))
 
     # -- multi-GPU -----------------------------------------------------------
+    def device_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(self.L.b200_device_alloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def device_free(self, ptr):
+        self._check(self.L.b200_device_free(self._h, ptr))
+
     def ipc_export(self, tensor_or_ptr):
         h = (C.c_ubyte * 64)()
         self._check(self.L.b200_ipc_export(self._h, _ptr(tensor_or_ptr), C.addressof(h)))
@@ -375,3 +386,36 @@ class SourceGather:
                 for o, b in zip(outs, bufs):
                     o.copy_(b[: o.shape[0]])
         return posm
+
+
+class PeerSources:
+    """The fused alternative to SourceGather for the direct sum: every rank packs its
+    shard into a tile-SoA buffer it owns and exports (CUDA IPC); peers map it, and
+    b200_direct_forces_parts_dev pulls source tiles straight out of peer HBM over
+    NVLink with TMA bulk copies -- no all-gather, one barrier per step.
+    Two buffers alternate so that a rank may repack while slower peers still read."""
+
+    def __init__(self, engine, n, rank, world, barrier, exchange):
+        self.e, self.n, self.rank, self.world, self.barrier = engine, n, rank, world, barrier
+        self.lens = [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
+        nbytes = max(engine.tiles_bytes(max(self.lens)), 8192)
+        self.mine = [engine.device_alloc(nbytes) for _ in range(2)]
+        handles = exchange([engine.ipc_export(p) for p in self.mine])       # list over ranks of [h0, h1]
+        self.parts = [[self.mine[b] if r == rank else engine.ipc_open(handles[r][b]) for r in range(world)]
+                      for b in range(2)]
+        self.step = 0
+
+    def publish(self, shard_posm, stream=None):
+        """Pack this rank's float4 shard into the current buffer, then barrier."""
+        b = self.step & 1
+        self.e.pack_tiles_dev(shard_posm, self.lens[self.rank], self.mine[b], stream)
+        self.barrier()
+        self.step += 1
+        return self.parts[b]
+
+    def close(self):
+        for b in range(2):
+            for r in range(self.world):
+                if r != self.rank:
+                    self.e.ipc_close(self.parts[b][r])
+            self.e.device_free(self.mine[b])

@@ -89,6 +89,17 @@ def test_direct_parts_equals_whole(engine):
     engine.direct_forces_parts_dev(parts, lens, posm, n, out, eps=0.01)
     torch.cuda.synchronize()
     assert rel_l2(out.cpu().numpy(), whole.cpu().numpy()) < 2e-6
+    # the equal-mass promise: same sources with m = 2.5 everywhere
+    posm[:, 3] = 2.5
+    engine.direct_forces_dev(posm, whole, 0, n, eps=0.01)
+    parts = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        t = torch.empty(max(engine.tiles_bytes(b - a), 16) // 4, dtype=torch.float32, device="cuda")
+        engine.pack_tiles_dev(posm[a:b], b - a, t)
+        parts.append(t)
+    engine.direct_forces_parts_dev(parts, lens, posm, n, out, eps=0.01, all_masses_equal=True)
+    torch.cuda.synchronize()
+    assert rel_l2(out.cpu().numpy(), whole.cpu().numpy()) < 2e-6
 
 
 def test_direct_periodic_vs_oracle(engine, oracle):

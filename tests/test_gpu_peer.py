@@ -1,0 +1,78 @@
+"""-m gpu: the peer-memory direct sum.  Two processes share GPU 0; each packs half of
+the sources into a tile buffer it exports over CUDA IPC, maps the other's, and runs
+b200_direct_forces_parts_dev over [own part, peer part].  (Host-side gloo barrier;
+no kernel waits on another process.)"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, n, q):
+    for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "lambda-cdm-raytracing_b200", "python")):
+        sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    import b200grav
+    from inputs import masses_np, uniform_mt
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    torch.cuda.set_device(0)
+    eng = b200grav.Engine(0)
+    pos = uniform_mt(n, seed=5)
+    mass = masses_np(n, seed=6)
+    full = np.concatenate([pos, mass[:, None]], 1).astype(np.float32)
+    lo, hi = b200grav.shard_range(n, rank, world)
+    shard = torch.from_numpy(full[lo:hi].copy()).cuda()
+
+    def exchange(mine):
+        out = [None] * world
+        dist.all_gather_object(out, mine)
+        return out
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    peers = b200grav.PeerSources(eng, n, rank, world, barrier, exchange)
+    acc = torch.empty((hi - lo, 3), dtype=torch.float32, device="cuda")
+    res = None
+    for step in range(3):                       # exercises both buffers
+        parts = peers.publish(shard)
+        eng.direct_forces_parts_dev(parts, peers.lens, shard, hi - lo, acc, eps=0.01)
+        torch.cuda.synchronize()
+        res = acc.cpu().numpy()
+    out = [None] * world
+    dist.all_gather_object(out, (lo, hi, res))
+    dist.barrier()
+    peers.close()
+    eng.close()
+    if rank == 0:
+        r = np.empty((n, 3), np.float32)
+        for a, b, part in out:
+            r[a:b] = part
+        q.put(r)
+    dist.destroy_process_group()
+
+
+def test_peer_mapped_sources_two_processes(oracle):
+    import torch.multiprocessing as mp
+    from inputs import masses_np, rel_l2, uniform_mt
+    n = 6000
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    want = oracle.direct_f32(uniform_mt(n, seed=5), masses_np(n, seed=6), eps=0.01)
+    assert rel_l2(res, want) < 1e-5
