@@ -367,6 +367,14 @@ def bench_gpu(args):
         tree_bytes = 32.0 * float(cnt[0]) + 16.0 * float(cnt[2]) + 28.0 * nl
         tree_counts = [int(x) for x in cnt]
 
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if world == 1:
+            traffic = tr.get(args.workload, {}).get(str(n))
+    except Exception:
+        pass
+
     if rank == 0:
         value = per_step * args.steps / total_s
         e2e_value = per_step * e2e_steps / e2e_s
@@ -393,7 +401,7 @@ def bench_gpu(args):
                 "kernel": ("direct_kernel<R=6,THREADS=256,1 CTA/SM,open,equal-mass> (11 FP32 lane-ops + 1 MUFU per "
                            "interaction; unequal masses run the 12-op instance)"),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None,
+                "traffic": traffic,
                 "peak_source": "FFMA/FFMA2 register-chain probe run in this process (b200_fp32_peak_probe); "
                                "MEASURED_PEAKS.json has no FP32 figure",
                 "peak_ffma": peak_ffma, "peak_ffma2": peak_ffma2,
@@ -411,7 +419,7 @@ def bench_gpu(args):
             gbs = tree_bytes / kern_s / 1e9
             line["roofline"] = {
                 "bound": "hbm", "kernel": "walk_kernel (stackless theta walk, one thread per Morton-ordered target)",
-                "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": None,
+                "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": traffic,
                 "peak_source": src,
                 "note": "algorithmic bytes = 32 B x nodes visited + 16 B x leaf-pair sources + 28 B x targets; most of it "
                         "is served by L1/L2 (a warp's 32 Morton-adjacent targets visit nearly the same nodes), so this is "

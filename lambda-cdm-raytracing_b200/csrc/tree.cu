@@ -27,6 +27,8 @@
 // Nodes are numbered breadth-first, children of a node contiguous -- the same
 // canonical numbering the CPU oracle exports, which is what makes the
 // bit-exact topology test a plain array compare.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -478,43 +480,77 @@ __global__ void part_pos_kernel(const int* __restrict__ part_idx, const float4* 
     part_pos[q] = p;
 }
 
-// compute_center_of_mass (:196-243): one rounding per operation, reference order
+// compute_center_of_mass (:196-243): one rounding per operation, reference order.
+// One thread per node.  Leaves holding more than 64 particles (the max-depth
+// overflow leaves that inputs outside the root cube produce can hold 10^5) are
+// summed by the whole warp instead: coalesced gathers, then every lane replays the
+// SAME sequential sum from shuffled values, so the result keeps the reference's
+// summation order bit for bit while the memory latency is paid once per 32 particles.
 __global__ void __launch_bounds__(256)
 com_kernel(const TreeGlobals* __restrict__ g, int level, const int4* __restrict__ meta,
            const int* __restrict__ part_idx, const float4* __restrict__ posm, float4* __restrict__ com) {
     const LevelInfo L = g->lv[level];
     const int n_nodes = L.node_end - L.node_begin;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += gridDim.x * blockDim.x) {
-        const int k = L.node_begin + i;
-        const int4 m = meta[k];
+    const int lane = threadIdx.x & 31;
+    const int n_round = (n_nodes + 31) & ~31;            // whole warps stay in the loop together
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool have = i < n_nodes;
+        const int k = L.node_begin + (have ? i : 0);
+        const int4 m = have ? meta[k] : make_int4(0, 0, 0, 0);
+        const bool big = have && m.x < 0 && m.w > 64;
         float total = 0.f, wx = 0.f, wy = 0.f, wz = 0.f;
-        if (m.x < 0) {
-            for (int q = m.z; q < m.z + m.w; ++q) {
-                const float4 p = posm[part_idx[q]];
-                total = __fadd_rn(total, p.w);
-                wx = __fadd_rn(wx, __fmul_rn(p.x, p.w));
-                wy = __fadd_rn(wy, __fmul_rn(p.y, p.w));
-                wz = __fadd_rn(wz, __fmul_rn(p.z, p.w));
-            }
-        } else {
+        if (have && !big) {
+            if (m.x < 0) {
+                for (int q = m.z; q < m.z + m.w; ++q) {
+                    const float4 p = posm[part_idx[q]];
+                    total = __fadd_rn(total, p.w);
+                    wx = __fadd_rn(wx, __fmul_rn(p.x, p.w));
+                    wy = __fadd_rn(wy, __fmul_rn(p.y, p.w));
+                    wz = __fadd_rn(wz, __fmul_rn(p.z, p.w));
+                }
+            } else {
 #pragma unroll
-            for (int d = 0; d < 8; ++d) {
-                const float4 c = com[m.x + d];
-                if (c.w > 0.f) {
-                    total = __fadd_rn(total, c.w);
-                    wx = __fadd_rn(wx, __fmul_rn(c.x, c.w));
-                    wy = __fadd_rn(wy, __fmul_rn(c.y, c.w));
-                    wz = __fadd_rn(wz, __fmul_rn(c.z, c.w));
+                for (int d = 0; d < 8; ++d) {
+                    const float4 c = com[m.x + d];
+                    if (c.w > 0.f) {
+                        total = __fadd_rn(total, c.w);
+                        wx = __fadd_rn(wx, __fmul_rn(c.x, c.w));
+                        wy = __fadd_rn(wy, __fmul_rn(c.y, c.w));
+                        wz = __fadd_rn(wz, __fmul_rn(c.z, c.w));
+                    }
                 }
             }
         }
-        float4 o = make_float4(0.f, 0.f, 0.f, total);
-        if (total > 0.f) {
-            o.x = __fdiv_rn(wx, total);
-            o.y = __fdiv_rn(wy, total);
-            o.z = __fdiv_rn(wz, total);
+        unsigned todo = __ballot_sync(FULL, big);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int off = __shfl_sync(FULL, m.z, src), np = __shfl_sync(FULL, m.w, src);
+            float t = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
+            for (int base = 0; base < np; base += 32) {
+                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (base + lane < np) p = posm[part_idx[off + base + lane]];
+                const int cnt = min(32, np - base);
+                for (int j = 0; j < cnt; ++j) {
+                    const float px = __shfl_sync(FULL, p.x, j), py = __shfl_sync(FULL, p.y, j);
+                    const float pz = __shfl_sync(FULL, p.z, j), pw = __shfl_sync(FULL, p.w, j);
+                    t = __fadd_rn(t, pw);
+                    sx = __fadd_rn(sx, __fmul_rn(px, pw));
+                    sy = __fadd_rn(sy, __fmul_rn(py, pw));
+                    sz = __fadd_rn(sz, __fmul_rn(pz, pw));
+                }
+            }
+            if (lane == src) { total = t; wx = sx; wy = sy; wz = sz; }
         }
-        com[k] = o;
+        if (have) {
+            float4 o = make_float4(0.f, 0.f, 0.f, total);
+            if (total > 0.f) {
+                o.x = __fdiv_rn(wx, total);
+                o.y = __fdiv_rn(wy, total);
+                o.z = __fdiv_rn(wz, total);
+            }
+            com[k] = o;
+        }
     }
 }
 
@@ -524,6 +560,8 @@ com_kernel(const TreeGlobals* __restrict__ g, int level, const int4* __restrict_
 // node that follows its subtree in depth-first order (meta.y), so "skip" is one
 // load and "open" is meta.x.  Accept test: IEEE sqrt/divide, no contraction, so
 // every lane takes exactly the decision the CPU code takes (:302-310).
+__device__ __forceinline__ bool accept_cell(float size, float d2, float theta);
+
 template <bool COUNT>
 __global__ void __launch_bounds__(128)
 walk_kernel(const float4* __restrict__ posm, const int* __restrict__ order, int i0, int n_targets,
@@ -559,8 +597,7 @@ walk_kernel(const float4* __restrict__ posm, const int* __restrict__ order, int 
             }
             const float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
             const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            const float r = __fsqrt_rn(d2);
-            if (__fdiv_rn(center[k].w, r) < theta) {                     // :309
+            if (accept_cell(center[k].w, d2, theta)) {                   // :309
                 const float r2 = d2 + eps2;
                 const float rinv = rsqrtf(r2);
                 const float f = c.w * rinv * rinv * rinv;                // :280-290
@@ -571,6 +608,100 @@ walk_kernel(const float4* __restrict__ posm, const int* __restrict__ order, int 
                 k = m.x;                                                 // :293-297
             }
         }
+        const size_t o = (size_t)(i - i0) * 3;
+        acc3[o + 0] = ax; acc3[o + 1] = ay; acc3[o + 2] = az;
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            c_vis += __shfl_down_sync(FULL, c_vis, s);
+            c_pc += __shfl_down_sync(FULL, c_pc, s);
+            c_pp += __shfl_down_sync(FULL, c_pp, s);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&g->counters[0], c_vis);
+            atomicAdd(&g->counters[1], c_pc);
+            atomicAdd(&g->counters[2], c_pp);
+        }
+    }
+}
+
+// The accept decision of satisfies_opening_criterion (:302-310), bit for bit, at a
+// fraction of its cost: size * rsqrt(d2) decides unless it lands within 1e-5 of
+// theta, in which case the exact IEEE sqrt/divide sequence of the CPU code is
+// evaluated (rsqrt.approx is good to ~2^-22, so the fast verdict is certain
+// outside that band).
+__device__ __forceinline__ bool accept_cell(float size, float d2, float theta) {
+    const float q = size * rsqrtf(d2);                 // d2 == 0 -> inf -> open, as size/0
+    if (fabsf(q - theta) > 1.0e-5f * theta) return q < theta;
+    return __fdiv_rn(size, __fsqrt_rn(d2)) < theta;
+}
+
+// Warp-cooperative walk: a warp owns 32 Morton-adjacent targets and walks the
+// UNION of their traversals in lockstep (node id is warp-uniform, so node and leaf
+// data are broadcast loads and control flow never diverges).  Every lane still
+// applies ITS OWN accept test: a lane that accepts a cell adds the monopole and
+// sleeps until the walk leaves that cell's subtree -- which is exactly when the
+// walk reaches the cell's skip pointer -- so each target receives precisely the
+// interactions, in precisely the depth-first order, of the CPU walk.
+template <bool COUNT>
+__global__ void __launch_bounds__(128)
+walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order, int i0, int n_targets,
+                 const float4* __restrict__ com, const float4* __restrict__ center,
+                 const int4* __restrict__ meta, const float4* __restrict__ part_pos, float theta,
+                 float* __restrict__ acc3, TreeGlobals* __restrict__ g) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = t < n_targets;
+    const int i = valid ? (order ? order[t] : (i0 + t)) : -1;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) p = posm[i];
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    const float eps2 = __fmul_rn(0.01f, 0.01f);                          // :281-282, :334-335
+    unsigned long long c_vis = 0, c_pc = 0, c_pp = 0;
+    constexpr int AWAKE = -2, NEVER = -3;
+    int wake = valid ? AWAKE : NEVER;     // node id at which a sleeping lane resumes
+    int k = 0;
+    while (k >= 0) {
+        if (wake == k) wake = AWAKE;
+        const bool active = (wake == AWAKE);
+        const float4 c = com[k];
+        const int4 m = meta[k];
+        if (COUNT && active) ++c_vis;
+        if (c.w == 0.0f) { k = m.y; continue; }                          // :260
+        if (m.x < 0) {                                                   // leaf :268-270
+            if (__any_sync(FULL, active)) {
+                for (int q = m.z; q < m.z + m.w; ++q) {
+                    const float4 s = part_pos[q];
+                    if (active && __float_as_int(s.w) != i) {            // :321
+                        const float dx = s.x - p.x, dy = s.y - p.y, dz = s.z - p.z;
+                        const float r2 = dx * dx + dy * dy + dz * dz + eps2;
+                        const float rinv = rsqrtf(r2);
+                        const float f = rinv * rinv * rinv;              // unit mass (:253, :340)
+                        ax += f * dx; ay += f * dy; az += f * dz;
+                        if (COUNT) ++c_pp;
+                    }
+                }
+            }
+            k = m.y;
+            continue;
+        }
+        bool open = false;
+        if (active) {
+            const float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            if (accept_cell(center[k].w, d2, theta)) {                   // :309
+                const float rinv = rsqrtf(d2 + eps2);
+                const float f = c.w * rinv * rinv * rinv;                // :280-290
+                ax += f * dx; ay += f * dy; az += f * dz;
+                if (COUNT) ++c_pc;
+                wake = m.y;                                              // sleep through this subtree
+            } else {
+                open = true;
+            }
+        }
+        k = __any_sync(FULL, open) ? m.x : m.y;                          // :293-297
+    }
+    if (valid) {
         const size_t o = (size_t)(i - i0) * 3;
         acc3[o + 0] = ax; acc3[o + 1] = ay; acc3[o + 2] = az;
     }
@@ -744,7 +875,17 @@ int tree_walk(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* acc
         ctx->launches += 1;
     }
     if (ctx->timing) B200_CUDA(cudaEventRecord(ctx->ev0, st));
-    if (T->counting)
+    const bool per_thread = getenv("B200_WALK_PER_THREAD") != nullptr;     // tuning hook
+    if (!per_thread) {
+        if (T->counting)
+            walk_warp_kernel<true><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
+                                                         T->com.as<float4>(), T->center.as<float4>(), T->meta.as<int4>(),
+                                                         T->part_pos.as<float4>(), theta, (float*)acc3, g);
+        else
+            walk_warp_kernel<false><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
+                                                          T->com.as<float4>(), T->center.as<float4>(), T->meta.as<int4>(),
+                                                          T->part_pos.as<float4>(), theta, (float*)acc3, g);
+    } else if (T->counting)
         walk_kernel<true><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
                                                 T->com.as<float4>(), T->center.as<float4>(), T->meta.as<int4>(),
                                                 T->part_pos.as<float4>(), theta, (float*)acc3, g);
