@@ -57,6 +57,8 @@ int b200_ctx_create(int device, size_t max_particles, b200_ctx** out);
 int b200_ctx_destroy(b200_ctx* ctx);
 int b200_ctx_device(const b200_ctx* ctx);
 int b200_ctx_sm_count(const b200_ctx* ctx);
+/* The context's own (non-blocking) cudaStream_t, for hosts that do not bring one. */
+void* b200_ctx_stream(const b200_ctx* ctx);
 /* Blocks until all work queued on stream (NULL = the context's own stream) is done. */
 int b200_ctx_sync(b200_ctx* ctx, void* stream);
 
@@ -182,6 +184,13 @@ int b200_pack_posm_dev(b200_ctx* ctx, const void* pos3, const void* mass, size_t
  * handle is a 64-byte cudaIpcMemHandle_t. */
 int b200_device_alloc(b200_ctx* ctx, size_t bytes, void** dev_ptr);   /* cudaMalloc: exportable */
 int b200_device_free(b200_ctx* ctx, void* dev_ptr);
+/* Stream-ordered copies for hosts that keep the state device-resident (the
+ * cudaMemcpy calls of LambdaCDMSimulation::copy_*_to_host, lambda_cdm_impl.cu).
+ * d2h blocks until the data has arrived; h2d is asynchronous for pinned memory. */
+int b200_memcpy_h2d(b200_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes, void* stream);
+int b200_memcpy_d2h(b200_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes, void* stream);
+/* posm4 (device) -> pos3 (device), the inverse of b200_pack_posm_dev */
+int b200_unpack_pos3_dev(b200_ctx* ctx, const void* posm4, size_t n, void* pos3, void* stream);
 int b200_ipc_export(b200_ctx* ctx, void* dev_ptr, unsigned char handle[64]);
 int b200_ipc_open(b200_ctx* ctx, const unsigned char handle[64], void** dev_ptr);
 int b200_ipc_close(b200_ctx* ctx, void* dev_ptr);

@@ -80,6 +80,8 @@ int b200_ctx_destroy(b200_ctx* ctx) {
 int b200_ctx_device(const b200_ctx* ctx) { return ctx ? ctx->device : -1; }
 int b200_ctx_sm_count(const b200_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
+void* b200_ctx_stream(const b200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
 int b200_ctx_sync(b200_ctx* ctx, void* stream) {
     if (!ctx) return B200_ERR_INVALID;
     B200_CUDA(cudaStreamSynchronize(stream ? (cudaStream_t)stream : ctx->stream));
@@ -324,6 +326,27 @@ int b200_device_free(b200_ctx* ctx, void* dev_ptr) {
     B200_CUDA(cudaSetDevice(ctx->device));
     if (dev_ptr) B200_CUDA(cudaFree(dev_ptr));
     return B200_OK;
+}
+
+int b200_memcpy_h2d(b200_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes, void* stream) {
+    if (!ctx || (bytes && (!dev_dst || !host_src))) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    B200_CUDA(cudaMemcpyAsync(dev_dst, host_src, bytes, cudaMemcpyHostToDevice, pick_stream(ctx, stream)));
+    return B200_OK;
+}
+
+int b200_memcpy_d2h(b200_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes, void* stream) {
+    if (!ctx || (bytes && (!host_dst || !dev_src))) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    B200_CUDA(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, pick_stream(ctx, stream)));
+    B200_CUDA(cudaStreamSynchronize(pick_stream(ctx, stream)));
+    return B200_OK;
+}
+
+int b200_unpack_pos3_dev(b200_ctx* ctx, const void* posm4, size_t n, void* pos3, void* stream) {
+    if (!ctx || (n && (!posm4 || !pos3))) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return unpack_pos3(ctx, posm4, n, pos3, pick_stream(ctx, stream));
 }
 
 int b200_ipc_export(b200_ctx* ctx, void* dev_ptr, unsigned char handle[64]) {

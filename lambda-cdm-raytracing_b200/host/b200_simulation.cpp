@@ -1,0 +1,123 @@
+// b200_simulation.cpp -- see the header.
+#include "b200_simulation.hpp"
+
+#include <cmath>
+#include <random>
+#include <stdexcept>
+#include <string>
+
+#include "b200grav.h"
+
+namespace physics {
+
+void B200LambdaCDMSimulation::check(int status, const char* where) const {
+    if (status != B200_OK) throw std::runtime_error(std::string(where) + ": " + b200_error_string(status));
+}
+
+B200LambdaCDMSimulation::B200LambdaCDMSimulation(size_t num_particles, float box_size, const CosmologyParams& params,
+                                                 int cuda_device)
+    : params_(params), cosmology_(params), num_particles_(num_particles), box_size_(box_size) {
+    // lambda_cdm_impl.cu:96-99: no suitable device -> throw (there is no CPU path)
+    check(b200_ctx_create(cuda_device, num_particles, &ctx_), "B200LambdaCDMSimulation");
+    stream_ = b200_ctx_stream(ctx_);
+    const size_t n = num_particles_ ? num_particles_ : 1;
+    check(b200_device_alloc(ctx_, n * 16, &d_posm_), "alloc positions");
+    check(b200_device_alloc(ctx_, n * 12 + 16, &d_vel_), "alloc velocities");
+    check(b200_device_alloc(ctx_, n * 12 + 16, &d_acc_), "alloc accelerations");
+    check(b200_device_alloc(ctx_, n * 12 + 16, &d_tmp3_), "alloc staging");
+}
+
+B200LambdaCDMSimulation::~B200LambdaCDMSimulation() {
+    if (!ctx_) return;
+    b200_device_free(ctx_, d_posm_);
+    b200_device_free(ctx_, d_vel_);
+    b200_device_free(ctx_, d_acc_);
+    b200_device_free(ctx_, d_tmp3_);
+    b200_ctx_destroy(ctx_);
+}
+
+void B200LambdaCDMSimulation::set_particles(const float* pos3, const float* vel3, const float* mass) {
+    const size_t n = num_particles_;
+    if (n == 0) return;
+    void* d_mass = nullptr;
+    check(b200_memcpy_h2d(ctx_, d_tmp3_, pos3, n * 12, stream_), "upload positions");
+    if (mass) {   // velocities' buffer doubles as the mass staging area before the velocities land
+        check(b200_memcpy_h2d(ctx_, d_vel_, mass, n * 4, stream_), "upload masses");
+        d_mass = d_vel_;
+    }
+    check(b200_pack_posm_dev(ctx_, d_tmp3_, d_mass, n, d_posm_, stream_), "pack");
+    check(b200_memcpy_h2d(ctx_, d_vel_, vel3, n * 12, stream_), "upload velocities");
+    check(b200_ctx_sync(ctx_, stream_), "sync");
+    have_forces_ = false;
+    current_step_ = 0;
+}
+
+void B200LambdaCDMSimulation::initialize_particles(uint32_t seed) {
+    // generate_initial_conditions (lambda_cdm_impl.cu:26-49): uniform positions in the box, Gaussian
+    // velocities with dispersion 100*sqrt(omega_m) (:153), unit masses -- seeded here.
+    std::mt19937 rng(seed);
+    std::uniform_real_distribution<float> uni(0.0f, box_size_);
+    std::normal_distribution<float> nrm(0.0f, 100.0f * (float)std::sqrt(params_.omega_m));
+    std::vector<float> pos(3 * num_particles_), vel(3 * num_particles_);
+    for (size_t i = 0; i < num_particles_; ++i) {
+        for (int k = 0; k < 3; ++k) pos[3 * i + k] = uni(rng);
+        for (int k = 0; k < 3; ++k) vel[3 * i + k] = nrm(rng);
+    }
+    set_particles(pos.data(), vel.data(), nullptr);
+}
+
+void B200LambdaCDMSimulation::set_force_method(B200ForceMethod m, float theta, int leaf_capacity, int max_depth) {
+    method_ = m; theta_ = theta; leaf_capacity_ = leaf_capacity; max_depth_ = max_depth;
+    have_forces_ = false;
+}
+
+void B200LambdaCDMSimulation::compute_forces() {
+    const size_t n = num_particles_;
+    if (n == 0) return;
+    if (method_ == B200ForceMethod::Tree) {
+        check(b200_tree_build_dev(ctx_, d_posm_, n, box_size_, leaf_capacity_, max_depth_, stream_), "tree build");
+        check(b200_tree_walk_dev(ctx_, 0, n, theta_, d_acc_, stream_), "tree walk");
+    } else {
+        const float box = (method_ == B200ForceMethod::Direct) ? box_size_ : 0.0f;   // K1/K2 are periodic
+        check(b200_direct_forces_dev(ctx_, d_posm_, n, 0, n, softening_, box, d_acc_, stream_), "direct forces");
+    }
+    have_forces_ = true;
+}
+
+void B200LambdaCDMSimulation::update_scale_factor(double dt) {
+    scale_factor_ += scale_factor_ * cosmology_.hubble_parameter_a(scale_factor_) * dt;   // lambda_cdm_impl.cu:261-269
+}
+
+void B200LambdaCDMSimulation::step(double dt) {
+    const size_t n = num_particles_;
+    if (n == 0) { ++current_step_; return; }
+    if (!have_forces_) compute_forces();
+    const float wrap = (method_ == B200ForceMethod::Tree || method_ == B200ForceMethod::DirectOpen) ? 0.0f : box_size_;
+    // lambda_cdm_impl.cu:167-213: kick(dt/2, a) -> drift(dt) -> a update -> forces -> kick(dt/2, a_new)
+    check(b200_leapfrog_dev(ctx_, d_posm_, d_vel_, d_acc_, n, 1, (float)(dt * 0.5), scale_factor_, (float)dt, wrap, stream_),
+          "kick+drift");
+    update_scale_factor(dt);
+    compute_forces();
+    check(b200_leapfrog_dev(ctx_, d_posm_, d_vel_, d_acc_, n, 1, (float)(dt * 0.5), scale_factor_, 0.0f, wrap, stream_),
+          "closing kick");
+    check(b200_ctx_sync(ctx_, stream_), "sync");
+    ++current_step_;
+}
+
+void B200LambdaCDMSimulation::copy_positions_to_host(float* positions) const {
+    if (!num_particles_) return;
+    check(b200_unpack_pos3_dev(ctx_, d_posm_, num_particles_, d_tmp3_, stream_), "unpack");
+    check(b200_memcpy_d2h(ctx_, positions, d_tmp3_, num_particles_ * 12, stream_), "download positions");
+}
+
+void B200LambdaCDMSimulation::copy_velocities_to_host(float* velocities) const {
+    if (!num_particles_) return;
+    check(b200_memcpy_d2h(ctx_, velocities, d_vel_, num_particles_ * 12, stream_), "download velocities");
+}
+
+void B200LambdaCDMSimulation::copy_forces_to_host(float* accelerations) const {
+    if (!num_particles_) return;
+    check(b200_memcpy_d2h(ctx_, accelerations, d_acc_, num_particles_ * 12, stream_), "download accelerations");
+}
+
+}  // namespace physics

@@ -1,0 +1,86 @@
+// b200_simulation.hpp -- device-resident Lambda-CDM leapfrog driver with the public
+// surface of the reference's physics::LambdaCDMSimulation
+// (include/physics/lambda_cdm.hpp:22-75; behaviour src/physics/lambda_cdm_impl.cu).
+// State (float4 positions+mass, velocities, accelerations) stays in HBM between
+// steps; every numerical call goes through the C ABI (include/b200grav.h).
+//
+// Differences from the reference class, on purpose:
+//  * step() orders kick -> drift -> forces -> kick on ONE stream (the reference
+//    races its kick and drift on two streams, lambda_cdm_impl.cu:170-189) and the
+//    first half-kick uses forces computed at the initial positions (the reference
+//    reads uninitialised memory there);
+//  * initialize_particles() is seeded (the reference seeds curand from the clock);
+//  * the force method is selectable: Direct (periodic minimum image, like the
+//    reference's K1/K2 kernels) or Tree (the CPU TreeForceComputer's semantics);
+//  * compute_energy() is a diagnostic outside the hot path and is not provided.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+#include "physics/cosmology_model.hpp"
+
+struct b200_ctx;
+
+namespace physics {
+
+enum class B200ForceMethod { Direct, DirectOpen, Tree };
+
+class B200LambdaCDMSimulation {
+    b200_ctx* ctx_ = nullptr;
+    void* stream_ = nullptr;                // the context's own cudaStream_t
+    CosmologyParams params_;
+    CosmologyModel cosmology_;
+    size_t num_particles_;
+    float box_size_;
+    double scale_factor_ = 1.0;
+    float softening_ = 0.01f;               // lambda_cdm_impl.cu:95
+    size_t current_step_ = 0;
+    B200ForceMethod method_ = B200ForceMethod::Direct;
+    float theta_ = 0.5f;
+    int leaf_capacity_ = 8, max_depth_ = 20;
+    bool have_forces_ = false;
+    void* d_posm_ = nullptr;                // float4[N]
+    void* d_vel_ = nullptr;                 // float[3N]
+    void* d_acc_ = nullptr;                 // float[3N]
+    void* d_tmp3_ = nullptr;                // float[3N] staging
+
+    void check(int status, const char* where) const;
+
+public:
+    B200LambdaCDMSimulation(size_t num_particles, float box_size, const CosmologyParams& params = CosmologyParams(),
+                            int cuda_device = 0);
+    ~B200LambdaCDMSimulation();
+    B200LambdaCDMSimulation(const B200LambdaCDMSimulation&) = delete;
+    B200LambdaCDMSimulation& operator=(const B200LambdaCDMSimulation&) = delete;
+
+    // Initialization (lambda_cdm.hpp:41-44)
+    void initialize_particles(uint32_t seed = 12345);          // uniform [0,box), v ~ N(0, 100*sqrt(omega_m)), m = 1
+    void set_particles(const float* pos3, const float* vel3, const float* mass);   // host arrays, mass may be null
+    void set_softening(float softening) { softening_ = softening; have_forces_ = false; }
+    void set_force_method(B200ForceMethod m, float theta = 0.5f, int leaf_capacity = 8, int max_depth = 20);
+
+    // Simulation methods (lambda_cdm.hpp:46-50)
+    void step(double dt);
+    void compute_forces();
+    void update_scale_factor(double dt);
+
+    // Cosmology functions (lambda_cdm.hpp:52-55)
+    double hubble_function(double a) const { return cosmology_.hubble_parameter_a(a); }
+    double growth_factor(double a) const { return cosmology_.growth_factor(a); }
+
+    // Data access (lambda_cdm.hpp:57-60)
+    void copy_positions_to_host(float* positions) const;       // float[3N]
+    void copy_velocities_to_host(float* velocities) const;     // float[3N]
+    void copy_forces_to_host(float* accelerations) const;      // float[3N]
+
+    // Accessors (lambda_cdm.hpp:62-71)
+    double get_scale_factor() const { return scale_factor_; }
+    double get_redshift() const { return 1.0 / scale_factor_ - 1.0; }
+    size_t get_num_particles() const { return num_particles_; }
+    float get_box_size() const { return box_size_; }
+    size_t get_current_step() const { return current_step_; }
+};
+
+}  // namespace physics

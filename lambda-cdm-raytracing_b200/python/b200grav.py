@@ -16,14 +16,14 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb200grav.so")
 
 EXPORTS = [
     "b200_error_string", "b200_abi_version", "b200_ctx_create", "b200_ctx_destroy",
-    "b200_ctx_device", "b200_ctx_sm_count", "b200_ctx_sync",
+    "b200_ctx_device", "b200_ctx_sm_count", "b200_ctx_stream", "b200_ctx_sync",
     "b200_direct_forces_host", "b200_direct_forces_dev", "b200_tiles_bytes",
     "b200_pack_tiles_dev", "b200_direct_forces_parts_dev",
     "b200_morton_keys_dev", "b200_sort_pairs_dev", "b200_tree_build_dev",
     "b200_tree_walk_dev", "b200_tree_forces_host", "b200_tree_stats", "b200_tree_export",
     "b200_tree_set_counting", "b200_tree_counters",
     "b200_leapfrog_dev", "b200_leapfrog_host", "b200_hubble_a", "b200_scale_factor_step", "b200_pack_posm_dev",
-    "b200_device_alloc", "b200_device_free", "b200_ipc_export", "b200_ipc_open", "b200_ipc_close",
+    "b200_device_alloc", "b200_device_free", "b200_memcpy_h2d", "b200_memcpy_d2h", "b200_unpack_pos3_dev", "b200_ipc_export", "b200_ipc_open", "b200_ipc_close",
     "b200_fp32_peak_probe", "b200_last_kernel_ms", "b200_set_timing", "b200_launch_count",
 ]
 
@@ -47,6 +47,8 @@ def load_library(path=None):
     L.b200_ctx_device.argtypes = [vp]
     L.b200_ctx_sm_count.argtypes = [vp]
     L.b200_ctx_sync.argtypes = [vp, vp]
+    L.b200_ctx_stream.argtypes = [vp]
+    L.b200_ctx_stream.restype = vp
     L.b200_direct_forces_host.argtypes = [vp, vp, vp, vp, sz, f32, f32]
     L.b200_direct_forces_dev.argtypes = [vp, vp, sz, sz, sz, f32, f32, vp, vp]
     L.b200_tiles_bytes.argtypes = [sz]
@@ -71,6 +73,9 @@ def load_library(path=None):
     L.b200_pack_posm_dev.argtypes = [vp, vp, vp, sz, vp, vp]
     L.b200_device_alloc.argtypes = [vp, sz, C.POINTER(vp)]
     L.b200_device_free.argtypes = [vp, vp]
+    L.b200_memcpy_h2d.argtypes = [vp, vp, vp, sz, vp]
+    L.b200_memcpy_d2h.argtypes = [vp, vp, vp, sz, vp]
+    L.b200_unpack_pos3_dev.argtypes = [vp, vp, sz, vp, vp]
     L.b200_ipc_export.argtypes = [vp, vp, vp]
     L.b200_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
     L.b200_ipc_close.argtypes = [vp, vp]

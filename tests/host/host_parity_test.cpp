@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "b200_force_computers.hpp"
+#include "b200_simulation.hpp"
 #include "core/simulation_context.hpp"
 #include "forces/tree_force_computer.hpp"
 
@@ -122,6 +123,50 @@ int main() {
         double mx = 0;
         for (size_t i = 0; i < 3 * m_n; ++i) mx = std::fmax(mx, std::fabs((double)x[i] - xc[i]));
         CHECK(a == ac && mx < 1e-4 * 100.0, "5 KDK steps through IIntegrator/ICosmologyModel: a = %.6f, max |dx| = %.2e (gate 1e-2)", a, mx);
+    }
+
+    {   // device-resident driver with the LambdaCDMSimulation call shape (examples/cuda_nbody_test.cpp:31-60):
+        // 10 steps of dt = 1e-3 on 4096 particles, tree forces, against the same loop on the reference CPU tree
+        const size_t m_n = 4096;
+        physics::B200LambdaCDMSimulation sim(m_n, 100.0f);
+        std::vector<float> x(pos.begin(), pos.begin() + 3 * m_n), v(3 * m_n), ms(m_n, 1.0f), fc(3 * m_n);
+        std::mt19937 g2(7);
+        std::normal_distribution<float> nv(0.0f, 55.0f);
+        for (auto& q : v) q = nv(g2);
+        sim.set_force_method(physics::B200ForceMethod::Tree);
+        sim.set_particles(x.data(), v.data(), ms.data());
+        std::vector<float> xc = x, vc = v;
+        physics::LambdaCDMModel cosmo("lcdm");
+        double ac = 1.0;
+        const double dt = 1e-3;
+        cpu_tree->compute_forces(xc.data(), ms.data(), fc.data(), m_n);
+        for (int s = 0; s < 10; ++s) {
+            sim.step(dt);
+            const float hdt = (float)(dt * 0.5), fdt = (float)dt;
+            float a2 = (float)(1.0f / (ac * ac));
+            for (size_t i = 0; i < 3 * m_n; ++i) { vc[i] += fc[i] * 1.0f * hdt * a2; xc[i] += vc[i] * fdt; }
+            cosmo.update_scale_factor(ac, dt);
+            cpu_tree->compute_forces(xc.data(), ms.data(), fc.data(), m_n);
+            a2 = (float)(1.0f / (ac * ac));
+            for (size_t i = 0; i < 3 * m_n; ++i) vc[i] += fc[i] * 1.0f * hdt * a2;
+        }
+        std::vector<float> xg(3 * m_n), vg(3 * m_n);
+        sim.copy_positions_to_host(xg.data());
+        sim.copy_velocities_to_host(vg.data());
+        double mx = 0;
+        for (size_t i = 0; i < 3 * m_n; ++i) mx = std::fmax(mx, std::fabs((double)xg[i] - xc[i]));
+        CHECK(sim.get_scale_factor() == ac && sim.get_current_step() == 10 && mx < 1e-4 * 100.0 && rel_l2(vg, vc) < 1e-4,
+              "B200LambdaCDMSimulation: 10 device-resident KDK steps, z = %.4f, max |dx| = %.2e, vel rel-L2 %.1e",
+              sim.get_redshift(), mx, rel_l2(vg, vc));
+        physics::B200LambdaCDMSimulation per(2048, 100.0f);      // periodic direct path, seeded ICs
+        per.initialize_particles(12345);
+        per.set_softening(0.1f);
+        for (int s = 0; s < 3; ++s) per.step(dt);
+        std::vector<float> xp(3 * 2048);
+        per.copy_positions_to_host(xp.data());
+        bool inside = true;
+        for (float q : xp) inside = inside && q >= 0.0f && q < 100.0f && std::isfinite(q);
+        CHECK(inside && per.get_current_step() == 3, "periodic direct driver keeps particles in [0, box)");
     }
 
     std::cout.rdbuf(quiet.rdbuf());
