@@ -67,7 +67,7 @@ int b200_ctx_destroy(b200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     tree_destroy(ctx);
-    ctx->src_tiles.release(); ctx->partials.release(); ctx->part_table.release(); ctx->mass_flag.release(); ctx->zero_flag.release();
+    ctx->src_tiles.release(); ctx->partials.release(); ctx->mass_flag.release(); ctx->zero_flag.release();
     ctx->h_pos3.release(); ctx->h_vel3.release(); ctx->h_mass.release(); ctx->h_posm4.release(); ctx->h_acc3.release();
     ctx->probe.release(); ctx->sort_scratch.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

@@ -52,7 +52,6 @@ struct b200_ctx {
     // direct sum scratch
     DevBuf src_tiles;       // tile-SoA sources
     DevBuf partials;        // per (CTA, target block) partial accelerations
-    DevBuf part_table;      // device copy of the source-part descriptor table
     DevBuf zero_flag;       // int that always reads 0 (equal-mass promise of the parts API)
     DevBuf mass_flag;       // int: number of sources whose mass differs from the first
     // host-entry staging

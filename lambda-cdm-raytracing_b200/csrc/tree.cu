@@ -487,8 +487,9 @@ __global__ void part_pos_kernel(const int* __restrict__ part_idx, const float4* 
 // SAME sequential sum from shuffled values, so the result keeps the reference's
 // summation order bit for bit while the memory latency is paid once per 32 particles.
 __global__ void __launch_bounds__(256)
-com_kernel(const TreeGlobals* __restrict__ g, int level, const int4* __restrict__ meta,
-           const int* __restrict__ part_idx, const float4* __restrict__ posm, float4* __restrict__ com) {
+com_kernel(const TreeGlobals* __restrict__ g, int level, int4* __restrict__ meta,
+           const float4* __restrict__ center, const int* __restrict__ part_idx,
+           const float4* __restrict__ posm, float4* __restrict__ com) {
     const LevelInfo L = g->lv[level];
     const int n_nodes = L.node_end - L.node_begin;
     const int lane = threadIdx.x & 31;
@@ -542,6 +543,8 @@ com_kernel(const TreeGlobals* __restrict__ g, int level, const int4* __restrict_
             }
             if (lane == src) { total = t; wx = sx; wy = sy; wz = sz; }
         }
+        if (have && m.x >= 0)       // walk-only field: an internal node's cell edge rides in meta.w
+            meta[k].w = __float_as_int(center[k].w);
         if (have) {
             float4 o = make_float4(0.f, 0.f, 0.f, total);
             if (total > 0.f) {
@@ -631,8 +634,14 @@ walk_kernel(const float4* __restrict__ posm, const int* __restrict__ order, int 
 // theta, in which case the exact IEEE sqrt/divide sequence of the CPU code is
 // evaluated (rsqrt.approx is good to ~2^-22, so the fast verdict is certain
 // outside that band).
+__device__ __forceinline__ float rsqrt_fast(float x) {   // one MUFU.RSQ, flush-to-zero
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ bool accept_cell(float size, float d2, float theta) {
-    const float q = size * rsqrtf(d2);                 // d2 == 0 -> inf -> open, as size/0
+    const float q = size * rsqrt_fast(d2);                 // d2 == 0 -> inf -> open, as size/0
     if (fabsf(q - theta) > 1.0e-5f * theta) return q < theta;
     return __fdiv_rn(size, __fsqrt_rn(d2)) < theta;
 }
@@ -670,17 +679,23 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
         if (c.w == 0.0f) { k = m.y; continue; }                          // :260
         if (m.x < 0) {                                                   // leaf :268-270
             if (__any_sync(FULL, active)) {
-                for (int q = m.z; q < m.z + m.w; ++q) {
-                    const float4 s = part_pos[q];
+                auto pair = [&](const float4& s) {
                     if (active && __float_as_int(s.w) != i) {            // :321
                         const float dx = s.x - p.x, dy = s.y - p.y, dz = s.z - p.z;
                         const float r2 = dx * dx + dy * dy + dz * dz + eps2;
-                        const float rinv = rsqrtf(r2);
+                        const float rinv = rsqrt_fast(r2);
                         const float f = rinv * rinv * rinv;              // unit mass (:253, :340)
                         ax += f * dx; ay += f * dy; az += f * dz;
                         if (COUNT) ++c_pp;
                     }
+                };
+                int q = m.z;
+                const int qe = m.z + m.w;
+                for (; q + 4 <= qe; q += 4) {            // 4 broadcast loads in flight, then 4 pairs
+                    const float4 s0 = part_pos[q], s1 = part_pos[q + 1], s2 = part_pos[q + 2], s3 = part_pos[q + 3];
+                    pair(s0); pair(s1); pair(s2); pair(s3);
                 }
+                for (; q < qe; ++q) pair(part_pos[q]);
             }
             k = m.y;
             continue;
@@ -689,8 +704,8 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
         if (active) {
             const float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
             const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            if (accept_cell(center[k].w, d2, theta)) {                   // :309
-                const float rinv = rsqrtf(d2 + eps2);
+            if (accept_cell(__int_as_float(m.w), d2, theta)) {       // cell edge rides in meta.w                   // :309
+                const float rinv = rsqrt_fast(d2 + eps2);
                 const float f = c.w * rinv * rinv * rinv;                // :280-290
                 ax += f * dx; ay += f * dy; az += f * dz;
                 if (COUNT) ++c_pc;
@@ -720,11 +735,7 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
     }
 }
 
-// keep only the targets of [i0, i0+n): order[] = sorted perm filtered (stable)
-__global__ void range_keys_kernel(const uint32_t* __restrict__ keys, int i0, int n, uint32_t* __restrict__ out) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) out[t] = keys[i0 + t];
-}
+// order[] of a target range holds range-local indices after the sort: shift to global
 __global__ void add_offset_kernel(int* __restrict__ v, int n, int off) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) v[t] += off;
@@ -834,7 +845,7 @@ int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_c
         const double lvl_nodes = (L < 10) ? (double)(1ull << (3 * L)) : 1e30;
         const size_t nb = (size_t)((lvl_nodes < (double)T->max_nodes) ? lvl_nodes : (double)T->max_nodes);
         const int cgrid = (int)((nb + 255) / 256 < (size_t)pgrid ? (nb + 255) / 256 : (size_t)pgrid);
-        com_kernel<<<cgrid, 256, 0, st>>>(g, L, meta, T->part_idx.as<int>(), T->posm, com);
+        com_kernel<<<cgrid, 256, 0, st>>>(g, L, meta, center, T->part_idx.as<int>(), T->posm, com);
         ctx->launches += 1;
     }
     B200_CUDA(cudaGetLastError());
