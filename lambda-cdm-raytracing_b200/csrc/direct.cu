@@ -422,6 +422,8 @@ int direct_forces(b200_ctx* ctx, const DirectSources& src, const void* targets4,
             B200_VARIANT(3, 512, 1) B200_VARIANT(6, 128, 2) B200_VARIANT(8, 128, 2) B200_VARIANT(7, 256, 1)
             B200_VARIANT(6, 384, 1) B200_VARIANT(5, 384, 1) B200_VARIANT(8, 192, 1) B200_VARIANT(6, 320, 1)
             B200_VARIANT(10, 256, 1) B200_VARIANT(5, 128, 3) B200_VARIANT(4, 128, 4)
+            B200_VARIANT(2, 256, 3) B200_VARIANT(2, 256, 4) B200_VARIANT(3, 256, 2) B200_VARIANT(3, 256, 3)
+            B200_VARIANT(2, 512, 2) B200_VARIANT(2, 1024, 1) B200_VARIANT(1, 256, 8) B200_VARIANT(1, 512, 4)
 #undef B200_VARIANT
             return B200_ERR_UNSUPPORTED;
         }

@@ -155,3 +155,31 @@ def test_tree_full_size(engine, oracle):
     assert np.isfinite(a).all()
     want = oracle.tree_forces(o, p, 0.5, i0=500000, n_targets=20000)
     assert rel_l2(a[500000:520000], want) < TOL_TREE
+
+
+def test_tree_zeldovich_c3(engine, oracle):
+    """BASELINE config 3 inputs: the reference's own "Zel'dovich" generator (grid 128 -> 2^20 particles,
+    seed 12345, z = 49, box 100), shifted to the centred convention; run live from the prebuilt
+    oracle/_ref (no /root/reference needed at run time)."""
+    import torch
+    from oracle.pyoracle import Ref
+    if not Ref.available():
+        pytest.skip("oracle/_ref not built")
+    n = 1 << 20
+    zp, zv, zm = Ref().zeldovich(n, grid=128, box=100.0, z_init=49.0, seed=12345)
+    p = (zp - np.float32(50.0)).astype(np.float32)
+    posm, t = _build_export(engine, p, zm, box=100.0, leaf_cap=8, max_depth=20)
+    o = oracle.tree_build(p, zm)
+    for k in TREE_KEYS:
+        assert np.array_equal(t[k], getattr(o, k)), k
+    engine.tree_set_counting(True)
+    acc = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    engine.tree_walk_dev(acc, 0, n, theta=0.5)
+    torch.cuda.synchronize()
+    engine.tree_set_counting(False)
+    want = oracle.tree_forces(o, p, 0.5, i0=300000, n_targets=30000)
+    assert rel_l2(acc[300000:330000].cpu().numpy(), want) < TOL_TREE
+    # Morton keys of the generator's box-convention output, bit-exact
+    keys = torch.empty(n, dtype=torch.int32, device="cuda")
+    engine.morton_keys_dev(_posm(zp, zm), n, 100.0, keys)
+    assert np.array_equal(keys.cpu().numpy().view(np.uint32), oracle.morton_keys(zp, 100.0))
