@@ -137,13 +137,68 @@ dual_probe_kernel(float* out, int iters, float a, float b) {
     if (s == 123.456f) out[0] = s;
 }
 
+// modes 8/9/10: register-operand pressure.  The peak probes above feed two of the three
+// FMA operands from uniform registers; the direct-sum accumulate step (acc = f*d + acc)
+// reads three DISTINCT per-thread registers (six 32-bit registers for the packed form).
+// 8: scalar FFMA, 3 register operands; 9: FFMA2, 3 register-pair operands;
+// 10: FFMA2 with 2 register-pair operands (a*a + c, the r^2 chain).
+template <int MODE>
+__global__ void __launch_bounds__(512, 2)      // 64 registers per thread: no spills
+regs_probe_kernel(float* out, int iters) {
+    float s = 0.f;
+    if (MODE == 8) {
+        float acc[CHAINS], x[CHAINS], y[CHAINS];
+#pragma unroll
+        for (int k = 0; k < CHAINS; ++k) {
+            acc[k] = (float)(threadIdx.x + k);
+            x[k] = 0.999f + 1e-6f * (float)(threadIdx.x + 3 * k);
+            y[k] = 1e-3f * (float)(threadIdx.x + 5 * k);
+        }
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < INNER; ++u)
+#pragma unroll
+                for (int k = 0; k < CHAINS; ++k)
+                    asm volatile("fma.rn.f32 %0, %1, %0, %2;" : "+f"(acc[k]) : "f"(x[k]), "f"(y[k]));
+        }
+#pragma unroll
+        for (int k = 0; k < CHAINS; ++k) s += acc[k];
+    } else {
+        unsigned long long acc[CHAINS / 2], x[CHAINS / 2], y[CHAINS / 2];
+#pragma unroll
+        for (int k = 0; k < CHAINS / 2; ++k) {
+            float a = (float)(threadIdx.x + k), b = 0.999f + 1e-6f * (float)(threadIdx.x + 3 * k),
+                  c = 1e-3f * (float)(threadIdx.x + 5 * k);
+            asm("mov.b64 %0, {%1, %1};" : "=l"(acc[k]) : "f"(a));
+            asm("mov.b64 %0, {%1, %1};" : "=l"(x[k]) : "f"(b));
+            asm("mov.b64 %0, {%1, %1};" : "=l"(y[k]) : "f"(c));
+        }
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < INNER; ++u)
+#pragma unroll
+                for (int k = 0; k < CHAINS / 2; ++k) {
+                    if (MODE == 9) asm volatile("fma.rn.f32x2 %0, %1, %0, %2;" : "+l"(acc[k]) : "l"(x[k]), "l"(y[k]));
+                    else asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc[k]) : "l"(x[k]));
+                }
+        }
+#pragma unroll
+        for (int k = 0; k < CHAINS / 2; ++k) {
+            float lo, hi;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[k]));
+            s += lo + hi;
+        }
+    }
+    if (s == 123.456f) out[0] = s;
+}
+
 }  // namespace
 
 int fp32_peak_probe(b200_ctx* ctx, int mode, int iters, double* tflops, float* ms_out) {
-    if (iters <= 0 || mode < 0 || mode > 7) return B200_ERR_INVALID;
+    if (iters <= 0 || mode < 0 || mode > 10) return B200_ERR_INVALID;
     B200_TRY(ctx->probe.reserve(256));
     cudaStream_t st = ctx->stream;
-    const int grid = ctx->sm_count * 2, block = 1024;
+    const int grid = ctx->sm_count * 2, block = (mode >= 8) ? 512 : 1024;
     for (int rep = 0; rep < 2; ++rep) {      // rep 0 warms up, rep 1 is timed
         B200_CUDA(cudaEventRecord(ctx->ev0, st));
         if (mode == 0) ffma_probe_kernel<<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
@@ -153,7 +208,10 @@ int fp32_peak_probe(b200_ctx* ctx, int mode, int iters, double* tflops, float* m
         else if (mode == 4) mix_probe_kernel<4><<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
         else if (mode == 5) mix_probe_kernel<5><<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
         else if (mode == 6) dual_probe_kernel<false><<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
-        else dual_probe_kernel<true><<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
+        else if (mode == 7) dual_probe_kernel<true><<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters, 0.999f, 0.001f);
+        else if (mode == 8) regs_probe_kernel<8><<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters);
+        else if (mode == 9) regs_probe_kernel<9><<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters);
+        else regs_probe_kernel<10><<<grid, block, 0, st>>>(ctx->probe.as<float>(), iters);
         B200_CUDA(cudaEventRecord(ctx->ev1, st));
         B200_CUDA(cudaGetLastError());
         B200_CUDA(cudaEventSynchronize(ctx->ev1));
