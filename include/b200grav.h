@@ -182,6 +182,28 @@ int b200_pack_posm_dev(b200_ctx* ctx, const void* pos3, const void* mass, size_t
  * caller's NCCL (torch.distributed) or pulled over NVLink by
  * b200_direct_forces_parts_dev from peer buffers mapped with these calls.
  * handle is a 64-byte cudaIpcMemHandle_t. */
+/* Shard bounds of rank `rank` of `world`: i0 = rank*n/world, n_local = (rank+1)*n/world - i0. */
+int b200_shard_range(size_t n, int rank, int world, size_t* i0, size_t* n_local);
+/* A communicator owned by the context, for hosts without one of their own (the C++
+ * plugin side).  Rank 0 calls b200_shard_unique_id and hands the 128 bytes
+ * (an ncclUniqueId) to the other ranks by any means (file, socket, MPI, threads of
+ * one process); every rank then calls b200_shard_init on its own context/device.
+ * NCCL is bound at run time (libnccl.so.2); B200_ERR_UNSUPPORTED if it is absent.
+ * world == 1 needs no id and makes the all-gather a no-op. */
+#define B200_SHARD_ID_BYTES 128
+int b200_shard_unique_id(unsigned char id[B200_SHARD_ID_BYTES]);
+int b200_shard_init(b200_ctx* ctx, const unsigned char id[B200_SHARD_ID_BYTES], int rank, int world);
+int b200_shard_finalize(b200_ctx* ctx);
+int b200_shard_info(const b200_ctx* ctx, int* rank, int* world);
+/* In-place all-gather of the float4 (x,y,z,m) shards: posm4_full is float4[n_total] on
+ * this rank's device with this rank's particles already at their b200_shard_range
+ * slice; when the stream reaches this point every slice holds its owner's data.
+ * Replaces ClusterCommunicator::gather_all_particles (src/mpi/cluster_comm.cpp:218-247:
+ * MPI_Allgather of counts + MPI_Allgatherv of host structs) -- device buffers, NVLink,
+ * no host staging.  Equal shards use one ncclAllGather; ragged ones a grouped
+ * broadcast per owner. */
+int b200_allgather_sources_dev(b200_ctx* ctx, void* posm4_full, size_t n_total, void* stream);
+
 int b200_device_alloc(b200_ctx* ctx, size_t bytes, void** dev_ptr);   /* cudaMalloc: exportable */
 int b200_device_free(b200_ctx* ctx, void* dev_ptr);
 /* Stream-ordered copies for hosts that keep the state device-resident (the

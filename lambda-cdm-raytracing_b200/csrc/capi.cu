@@ -7,6 +7,7 @@
 #include "direct.cuh"
 #include "leapfrog.cuh"
 #include "probe.cuh"
+#include "shard.cuh"
 #include "sort.cuh"
 #include "tree.cuh"
 
@@ -29,6 +30,7 @@ const char* b200_error_string(int status) {
         default: break;
     }
     if (status >= 1000 && status < 2000) return cudaGetErrorString((cudaError_t)(status - 1000));
+    if (status >= 2000 && status < 3000) return shard_error_string(status - 2000);
     return "unknown b200grav status";
 }
 
@@ -67,6 +69,7 @@ int b200_ctx_destroy(b200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     tree_destroy(ctx);
+    shard_finalize(ctx);
     ctx->src_tiles.release(); ctx->partials.release(); ctx->mass_flag.release(); ctx->zero_flag.release();
     ctx->h_pos3.release(); ctx->h_vel3.release(); ctx->h_mass.release(); ctx->h_posm4.release(); ctx->h_acc3.release();
     ctx->probe.release(); ctx->sort_scratch.release();
@@ -311,6 +314,47 @@ int b200_pack_posm_dev(b200_ctx* ctx, const void* pos3, const void* mass, size_t
     if (!ctx || (n && (!pos3 || !posm4))) return B200_ERR_INVALID;
     B200_CUDA(cudaSetDevice(ctx->device));
     return pack_posm(ctx, pos3, mass, n, posm4, pick_stream(ctx, stream));
+}
+
+// ---- multi-GPU: NCCL source all-gather ---------------------------------------
+int b200_shard_range(size_t n, int rank, int world, size_t* i0, size_t* n_local) {
+    if (world < 1 || rank < 0 || rank >= world) return B200_ERR_INVALID;
+    // 128-bit-safe form of [rank*n/world, (rank+1)*n/world)
+    const size_t q = n / (size_t)world, r = n % (size_t)world;
+    const size_t lo = (size_t)rank * q + ((size_t)rank * r) / (size_t)world;
+    const size_t hi = (size_t)(rank + 1) * q + ((size_t)(rank + 1) * r) / (size_t)world;
+    if (i0) *i0 = lo;
+    if (n_local) *n_local = hi - lo;
+    return B200_OK;
+}
+
+int b200_shard_unique_id(unsigned char id[B200_SHARD_ID_BYTES]) {
+    if (!id) return B200_ERR_INVALID;
+    return shard_unique_id(id);
+}
+
+int b200_shard_init(b200_ctx* ctx, const unsigned char id[B200_SHARD_ID_BYTES], int rank, int world) {
+    if (!ctx || (world > 1 && !id)) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return shard_init(ctx, id, rank, world);
+}
+
+int b200_shard_finalize(b200_ctx* ctx) {
+    if (!ctx) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->stream) B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    return shard_finalize(ctx);
+}
+
+int b200_shard_info(const b200_ctx* ctx, int* rank, int* world) {
+    if (!ctx) return B200_ERR_INVALID;
+    return shard_info(ctx, rank, world);
+}
+
+int b200_allgather_sources_dev(b200_ctx* ctx, void* posm4_full, size_t n_total, void* stream) {
+    if (!ctx || (n_total && !posm4_full)) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return shard_allgather(ctx, posm4_full, n_total, pick_stream(ctx, stream));
 }
 
 // ---- multi-GPU peer mapping ------------------------------------------------

@@ -38,7 +38,7 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
-namespace b200 { struct TreeState; }   // tree.cu
+namespace b200 { struct TreeState; struct ShardState; }   // tree.cu, shard.cu
 
 struct b200_ctx {
     int device = 0;
@@ -60,6 +60,7 @@ struct b200_ctx {
     DevBuf probe, sort_scratch;
 
     b200::TreeState* tree = nullptr;
+    b200::ShardState* shard = nullptr;    // NCCL communicator (b200_shard_init)
 };
 
 static inline int ceil_div_i(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -1,0 +1,16 @@
+// shard.cuh -- NCCL-backed source all-gather owned by the context (shard.cu).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+struct ShardState;
+
+int shard_unique_id(unsigned char id[B200_SHARD_ID_BYTES]);
+int shard_init(b200_ctx* ctx, const unsigned char id[B200_SHARD_ID_BYTES], int rank, int world);
+int shard_finalize(b200_ctx* ctx);
+int shard_info(const b200_ctx* ctx, int* rank, int* world);
+int shard_allgather(b200_ctx* ctx, void* posm4_full, size_t n_total, cudaStream_t st);
+const char* shard_error_string(int nccl_result);
+
+}  // namespace b200

@@ -16,7 +16,8 @@ void B200LambdaCDMSimulation::check(int status, const char* where) const {
 
 B200LambdaCDMSimulation::B200LambdaCDMSimulation(size_t num_particles, float box_size, const CosmologyParams& params,
                                                  int cuda_device)
-    : params_(params), cosmology_(params), num_particles_(num_particles), box_size_(box_size) {
+    : params_(params), cosmology_(params), num_particles_(num_particles), box_size_(box_size),
+      n_local_(num_particles) {
     // lambda_cdm_impl.cu:96-99: no suitable device -> throw (there is no CPU path)
     check(b200_ctx_create(cuda_device, num_particles, &ctx_), "B200LambdaCDMSimulation");
     stream_ = b200_ctx_stream(ctx_);
@@ -36,6 +37,14 @@ B200LambdaCDMSimulation::~B200LambdaCDMSimulation() {
     b200_ctx_destroy(ctx_);
 }
 
+void B200LambdaCDMSimulation::enable_sharding(const unsigned char* nccl_unique_id, int rank, int world) {
+    check(b200_shard_init(ctx_, nccl_unique_id, rank, world), "shard init");
+    rank_ = rank;
+    world_ = world;
+    check(b200_shard_range(num_particles_, rank, world, &i0_, &n_local_), "shard range");
+    have_forces_ = false;
+}
+
 void B200LambdaCDMSimulation::set_particles(const float* pos3, const float* vel3, const float* mass) {
     const size_t n = num_particles_;
     if (n == 0) return;
@@ -46,7 +55,8 @@ void B200LambdaCDMSimulation::set_particles(const float* pos3, const float* vel3
         d_mass = d_vel_;
     }
     check(b200_pack_posm_dev(ctx_, d_tmp3_, d_mass, n, d_posm_, stream_), "pack");
-    check(b200_memcpy_h2d(ctx_, d_vel_, vel3, n * 12, stream_), "upload velocities");
+    if (n_local_)
+        check(b200_memcpy_h2d(ctx_, d_vel_, vel3 + 3 * i0_, n_local_ * 12, stream_), "upload velocities");
     check(b200_ctx_sync(ctx_, stream_), "sync");
     have_forces_ = false;
     current_step_ = 0;
@@ -74,12 +84,14 @@ void B200LambdaCDMSimulation::set_force_method(B200ForceMethod m, float theta, i
 void B200LambdaCDMSimulation::compute_forces() {
     const size_t n = num_particles_;
     if (n == 0) return;
+    // every rank sees all sources (replicated positions), and evaluates its own targets only
     if (method_ == B200ForceMethod::Tree) {
         check(b200_tree_build_dev(ctx_, d_posm_, n, box_size_, leaf_capacity_, max_depth_, stream_), "tree build");
-        check(b200_tree_walk_dev(ctx_, 0, n, theta_, d_acc_, stream_), "tree walk");
+        check(b200_tree_walk_dev(ctx_, i0_, n_local_, theta_, d_acc_, stream_), "tree walk");
     } else {
         const float box = (method_ == B200ForceMethod::Direct) ? box_size_ : 0.0f;   // K1/K2 are periodic
-        check(b200_direct_forces_dev(ctx_, d_posm_, n, 0, n, softening_, box, d_acc_, stream_), "direct forces");
+        check(b200_direct_forces_dev(ctx_, d_posm_, n, i0_, n_local_, softening_, box, d_acc_, stream_),
+              "direct forces");
     }
     have_forces_ = true;
 }
@@ -94,11 +106,15 @@ void B200LambdaCDMSimulation::step(double dt) {
     if (!have_forces_) compute_forces();
     const float wrap = (method_ == B200ForceMethod::Tree || method_ == B200ForceMethod::DirectOpen) ? 0.0f : box_size_;
     // lambda_cdm_impl.cu:167-213: kick(dt/2, a) -> drift(dt) -> a update -> forces -> kick(dt/2, a_new)
-    check(b200_leapfrog_dev(ctx_, d_posm_, d_vel_, d_acc_, n, 1, (float)(dt * 0.5), scale_factor_, (float)dt, wrap, stream_),
+    void* my_posm = (char*)d_posm_ + i0_ * 16;
+    check(b200_leapfrog_dev(ctx_, my_posm, d_vel_, d_acc_, n_local_, 1, (float)(dt * 0.5), scale_factor_, (float)dt, wrap,
+                            stream_),
           "kick+drift");
     update_scale_factor(dt);
+    if (world_ > 1) check(b200_allgather_sources_dev(ctx_, d_posm_, n, stream_), "all-gather sources");
     compute_forces();
-    check(b200_leapfrog_dev(ctx_, d_posm_, d_vel_, d_acc_, n, 1, (float)(dt * 0.5), scale_factor_, 0.0f, wrap, stream_),
+    check(b200_leapfrog_dev(ctx_, my_posm, d_vel_, d_acc_, n_local_, 1, (float)(dt * 0.5), scale_factor_, 0.0f, wrap,
+                            stream_),
           "closing kick");
     check(b200_ctx_sync(ctx_, stream_), "sync");
     ++current_step_;
@@ -111,13 +127,13 @@ void B200LambdaCDMSimulation::copy_positions_to_host(float* positions) const {
 }
 
 void B200LambdaCDMSimulation::copy_velocities_to_host(float* velocities) const {
-    if (!num_particles_) return;
-    check(b200_memcpy_d2h(ctx_, velocities, d_vel_, num_particles_ * 12, stream_), "download velocities");
+    if (!n_local_) return;
+    check(b200_memcpy_d2h(ctx_, velocities, d_vel_, n_local_ * 12, stream_), "download velocities");
 }
 
 void B200LambdaCDMSimulation::copy_forces_to_host(float* accelerations) const {
-    if (!num_particles_) return;
-    check(b200_memcpy_d2h(ctx_, accelerations, d_acc_, num_particles_ * 12, stream_), "download accelerations");
+    if (!n_local_) return;
+    check(b200_memcpy_d2h(ctx_, accelerations, d_acc_, n_local_ * 12, stream_), "download accelerations");
 }
 
 }  // namespace physics

@@ -12,7 +12,12 @@
 //  * initialize_particles() is seeded (the reference seeds curand from the clock);
 //  * the force method is selectable: Direct (periodic minimum image, like the
 //    reference's K1/K2 kernels) or Tree (the CPU TreeForceComputer's semantics);
-//  * compute_energy() is a diagnostic outside the hot path and is not provided.
+//  * compute_energy() is a diagnostic outside the hot path and is not provided;
+//  * enable_sharding(): target-sharded data parallelism over several GPUs.
+//    One object per GPU (one process or one thread each); rank r integrates particles
+//    [r*N/G, (r+1)*N/G) and the float4 positions are all-gathered with NCCL every step
+//    (b200_allgather_sources_dev).  Every rank holds all positions; velocities and
+//    accelerations exist only for the local range.
 #pragma once
 
 #include <cstddef>
@@ -41,6 +46,8 @@ class B200LambdaCDMSimulation {
     float theta_ = 0.5f;
     int leaf_capacity_ = 8, max_depth_ = 20;
     bool have_forces_ = false;
+    int rank_ = 0, world_ = 1;              // enable_sharding()
+    size_t i0_ = 0, n_local_ = 0;           // this rank's particle range
     void* d_posm_ = nullptr;                // float4[N]
     void* d_vel_ = nullptr;                 // float[3N]
     void* d_acc_ = nullptr;                 // float[3N]
@@ -57,7 +64,12 @@ public:
 
     // Initialization (lambda_cdm.hpp:41-44)
     void initialize_particles(uint32_t seed = 12345);          // uniform [0,box), v ~ N(0, 100*sqrt(omega_m)), m = 1
-    void set_particles(const float* pos3, const float* vel3, const float* mass);   // host arrays, mass may be null
+    // host arrays of all N particles (every rank passes the same data), mass may be null
+    void set_particles(const float* pos3, const float* vel3, const float* mass);
+    // Multi-GPU: call once, before set_particles/initialize_particles, on every rank with the
+    // 128-byte id rank 0 obtained from b200_shard_unique_id().  Collective (blocks until all
+    // `world` ranks have called it).
+    void enable_sharding(const unsigned char* nccl_unique_id, int rank, int world);
     void set_softening(float softening) { softening_ = softening; have_forces_ = false; }
     void set_force_method(B200ForceMethod m, float theta = 0.5f, int leaf_capacity = 8, int max_depth = 20);
 
@@ -72,8 +84,12 @@ public:
 
     // Data access (lambda_cdm.hpp:57-60)
     void copy_positions_to_host(float* positions) const;       // float[3N]
-    void copy_velocities_to_host(float* velocities) const;     // float[3N]
-    void copy_forces_to_host(float* accelerations) const;      // float[3N]
+    void copy_velocities_to_host(float* velocities) const;     // float[3*local count]
+    void copy_forces_to_host(float* accelerations) const;      // float[3*local count]
+    size_t get_local_offset() const { return i0_; }            // first particle this rank integrates
+    size_t get_local_count() const { return n_local_; }        // == N unless sharded
+    int get_rank() const { return rank_; }
+    int get_world_size() const { return world_; }
 
     // Accessors (lambda_cdm.hpp:62-71)
     double get_scale_factor() const { return scale_factor_; }

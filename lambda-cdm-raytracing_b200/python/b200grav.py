@@ -24,6 +24,8 @@ EXPORTS = [
     "b200_tree_set_counting", "b200_tree_counters",
     "b200_leapfrog_dev", "b200_leapfrog_host", "b200_hubble_a", "b200_scale_factor_step", "b200_pack_posm_dev",
     "b200_device_alloc", "b200_device_free", "b200_memcpy_h2d", "b200_memcpy_d2h", "b200_unpack_pos3_dev", "b200_ipc_export", "b200_ipc_open", "b200_ipc_close",
+    "b200_shard_range", "b200_shard_unique_id", "b200_shard_init", "b200_shard_finalize", "b200_shard_info",
+    "b200_allgather_sources_dev",
     "b200_fp32_peak_probe", "b200_last_kernel_ms", "b200_set_timing", "b200_launch_count",
 ]
 
@@ -79,6 +81,12 @@ def load_library(path=None):
     L.b200_ipc_export.argtypes = [vp, vp, vp]
     L.b200_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
     L.b200_ipc_close.argtypes = [vp, vp]
+    L.b200_shard_range.argtypes = [sz, i32, i32, C.POINTER(sz), C.POINTER(sz)]
+    L.b200_shard_unique_id.argtypes = [vp]
+    L.b200_shard_init.argtypes = [vp, vp, i32, i32]
+    L.b200_shard_finalize.argtypes = [vp]
+    L.b200_shard_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+    L.b200_allgather_sources_dev.argtypes = [vp, vp, sz, vp]
     L.b200_fp32_peak_probe.argtypes = [vp, i32, i32, C.POINTER(f64), C.POINTER(f32)]
     L.b200_last_kernel_ms.argtypes = [vp, C.POINTER(f32)]
     L.b200_set_timing.argtypes = [vp, i32]
@@ -273,6 +281,27 @@ class Engine:
         self._check(self.L.b200_ipc_close(self._h, ptr))
 
     # -- measurement ---------------------------------------------------------
+    # ---- NCCL source all-gather owned by the context (hosts without torch.distributed) ----
+    def shard_unique_id(self):
+        buf = (C.c_ubyte * 128)()
+        self._check(self.L.b200_shard_unique_id(buf))
+        return bytes(buf)
+
+    def shard_init(self, unique_id, rank, world):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        self._check(self.L.b200_shard_init(self._h, buf, rank, world))
+
+    def shard_finalize(self):
+        self._check(self.L.b200_shard_finalize(self._h))
+
+    def shard_info(self):
+        r, w = C.c_int(), C.c_int()
+        self._check(self.L.b200_shard_info(self._h, C.byref(r), C.byref(w)))
+        return r.value, w.value
+
+    def allgather_sources_dev(self, posm_full, n_total, stream=None):
+        self._check(self.L.b200_allgather_sources_dev(self._h, _ptr(posm_full), n_total, _stream(stream)))
+
     def fp32_peak_probe(self, mode=0, iters=2000):
         t, ms = C.c_double(), C.c_float()
         self._check(self.L.b200_fp32_peak_probe(self._h, mode, iters, C.byref(t), C.byref(ms)))

@@ -63,3 +63,20 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 for tok in ("pyoracle", "liboracle", "oracle/", "oracle.h", "orc_", "lcdm_ref"):
                     assert tok not in txt, (os.path.join(dp, f), tok)
+
+
+def test_shard_range_matches_python_and_partitions():
+    import b200grav
+    lib = b200grav.load_library()
+    for n in (0, 1, 7, 12345, 1 << 20, (1 << 24) + 3):
+        for world in (1, 2, 3, 4, 8):
+            covered = 0
+            for rank in range(world):
+                i0, nl = C.c_size_t(), C.c_size_t()
+                assert lib.b200_shard_range(n, rank, world, C.byref(i0), C.byref(nl)) == 0
+                lo, hi = b200grav.shard_range(n, rank, world)
+                assert (i0.value, nl.value) == (lo, hi - lo)
+                assert i0.value == covered
+                covered += nl.value
+            assert covered == n
+    assert lib.b200_shard_range(10, 2, 2, None, None) == 1      # rank out of range

@@ -19,3 +19,17 @@ def test_host_plugin_parity():
     print(r.stdout[-4000:], r.stderr[-2000:])
     assert r.returncode == 0, r.stdout[-2000:]
     assert "HOST PARITY OK" in r.stdout and "FAIL" not in r.stdout
+
+
+def test_host_sharded_simulation_matches_single_gpu():
+    """C++ only, no Python in the loop: one B200LambdaCDMSimulation per GPU (threads), NCCL
+    all-gather through the C ABI, against the 1-GPU run.  Skips itself on a 1-GPU box."""
+    exe = os.path.join(ROOT, "tests", "host", "_bin", "shard_test")
+    if not os.path.exists(exe):
+        pytest.skip("tests/host/_bin/shard_test not built (needs the reference headers at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    print(r.stdout[-4000:], r.stderr[-2000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "FAIL" not in r.stdout
+    if "SKIP" in r.stdout:
+        pytest.skip(r.stdout.strip())
