@@ -66,6 +66,7 @@ struct TreeState {
     DevBuf center, com, meta, nstart, ncount, nsplit_rank;
     DevBuf ent_idx[2], ent_node[2], digit;
     DevBuf part_idx, part_pos;
+    DevBuf nodes;                 // walk records: {centre of mass float4, meta int4} interleaved, 32 B per node
     DevBuf globals;
     DevBuf tile_hist, tile_warp_prefix, node_tile_sum;
     DevBuf split_node, split_where, split_local, split_cstart;
@@ -74,7 +75,7 @@ struct TreeState {
     bool order_valid = false;
     void release() {
         DevBuf* all[] = {&center, &com, &meta, &nstart, &ncount, &nsplit_rank, &ent_idx[0],
-                         &ent_idx[1], &ent_node[0], &ent_node[1], &digit, &part_idx, &part_pos,
+                         &ent_idx[1], &ent_node[0], &ent_node[1], &digit, &part_idx, &part_pos, &nodes,
                          &globals, &tile_hist, &tile_warp_prefix, &node_tile_sum, &split_node,
                          &split_where, &split_local, &split_cstart, &keys, &keys_sorted, &perm,
                          &sort_scratch, &order};
@@ -557,6 +558,22 @@ com_kernel(const TreeGlobals* __restrict__ g, int level, int4* __restrict__ meta
     }
 }
 
+// Walk records: centre of mass + node record of node k side by side (one 32-byte sector),
+// written once the build is complete.  The node count is device-side state.
+__global__ void __launch_bounds__(256)
+pack_nodes_kernel(const TreeGlobals* __restrict__ g, int max_depth, const float4* __restrict__ com,
+                  const int4* __restrict__ meta, float4* __restrict__ nodes) {
+    int nn = 0;
+    for (int L = 0; L <= max_depth; ++L)
+        if (g->lv[L].node_end > g->lv[L].node_begin) nn = g->lv[L].node_end;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nn; k += gridDim.x * blockDim.x) {
+        const int4 m = meta[k];
+        nodes[2 * k] = com[k];
+        nodes[2 * k + 1] = make_float4(__int_as_float(m.x), __int_as_float(m.y), __int_as_float(m.z),
+                                       __int_as_float(m.w));
+    }
+}
+
 // ------------------------------------------------------------------ walk ---
 // One thread per target, targets taken in Morton order so the 32 lanes of a
 // warp walk nearly the same nodes.  Stackless: every node carries the id of the
@@ -653,11 +670,19 @@ __device__ __forceinline__ bool accept_cell(float size, float d2, float theta) {
 // sleeps until the walk leaves that cell's subtree -- which is exactly when the
 // walk reaches the cell's skip pointer -- so each target receives precisely the
 // interactions, in precisely the depth-first order, of the CPU walk.
+// size/|d| < theta taken as size^2 < theta^2 d^2 whenever the two sides differ by more than
+// 3e-5 relative (the roundings of either form are < 3e-7), else by the exact IEEE sequence.
+__device__ __forceinline__ bool accept_cell_sq(float size, float d2, float theta, float theta2) {
+    const float t = theta2 * d2;
+    const float diff = size * size - t;
+    if (fabsf(diff) > 3.0e-5f * t) return diff < 0.0f;       // d2 == 0 -> t == 0 -> open, as size/0 = inf
+    return __fdiv_rn(size, __fsqrt_rn(d2)) < theta;              // :302-310, bit for bit
+}
+
 template <bool COUNT>
 __global__ void __launch_bounds__(128)
 walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order, int i0, int n_targets,
-                 const float4* __restrict__ com, const float4* __restrict__ center,
-                 const int4* __restrict__ meta, const float4* __restrict__ part_pos, float theta,
+                 const float4* __restrict__ nodes, const float4* __restrict__ part_pos, float theta,
                  float* __restrict__ acc3, TreeGlobals* __restrict__ g) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = t < n_targets;
@@ -666,6 +691,7 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
     if (valid) p = posm[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
     const float eps2 = __fmul_rn(0.01f, 0.01f);                          // :281-282, :334-335
+    const float theta2 = theta > 0.f ? theta * theta : 0.f;              // theta <= 0: nothing is ever accepted
     unsigned long long c_vis = 0, c_pc = 0, c_pp = 0;
     constexpr int AWAKE = -2, NEVER = -3;
     int wake = valid ? AWAKE : NEVER;     // node id at which a sleeping lane resumes
@@ -673,48 +699,49 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
     while (k >= 0) {
         if (wake == k) wake = AWAKE;
         const bool active = (wake == AWAKE);
-        const float4 c = com[k];
-        const int4 m = meta[k];
+        const float4 c = nodes[2 * k];                                   // centre of mass, M
+        const float4 mf = nodes[2 * k + 1];                              // first child | skip | part_off | npart or size
+        const int first = __float_as_int(mf.x), skip = __float_as_int(mf.y);
         if (COUNT && active) ++c_vis;
-        if (c.w == 0.0f) { k = m.y; continue; }                          // :260
-        if (m.x < 0) {                                                   // leaf :268-270
+        if (c.w == 0.0f) { k = skip; continue; }                         // :260
+        if (first < 0) {                                                 // leaf :268-270
             if (__any_sync(FULL, active)) {
+                // branch-free pair: a lane that is asleep, or is the particle itself (:321), adds f = 0
                 auto pair = [&](const float4& s) {
-                    if (active && __float_as_int(s.w) != i) {            // :321
-                        const float dx = s.x - p.x, dy = s.y - p.y, dz = s.z - p.z;
-                        const float r2 = dx * dx + dy * dy + dz * dz + eps2;
-                        const float rinv = rsqrt_fast(r2);
-                        const float f = rinv * rinv * rinv;              // unit mass (:253, :340)
-                        ax += f * dx; ay += f * dy; az += f * dz;
-                        if (COUNT) ++c_pp;
-                    }
+                    const float dx = s.x - p.x, dy = s.y - p.y, dz = s.z - p.z;
+                    const float r2 = dx * dx + dy * dy + dz * dz + eps2;
+                    const float rinv = rsqrt_fast(r2);
+                    const bool on = active && __float_as_int(s.w) != i;
+                    const float f = on ? rinv * rinv * rinv : 0.f;       // unit mass (:253, :340)
+                    ax += f * dx; ay += f * dy; az += f * dz;
+                    if (COUNT && on) ++c_pp;
                 };
-                int q = m.z;
-                const int qe = m.z + m.w;
+                int q = __float_as_int(mf.z);
+                const int qe = q + __float_as_int(mf.w);
                 for (; q + 4 <= qe; q += 4) {            // 4 broadcast loads in flight, then 4 pairs
                     const float4 s0 = part_pos[q], s1 = part_pos[q + 1], s2 = part_pos[q + 2], s3 = part_pos[q + 3];
                     pair(s0); pair(s1); pair(s2); pair(s3);
                 }
                 for (; q < qe; ++q) pair(part_pos[q]);
             }
-            k = m.y;
+            k = skip;
             continue;
         }
         bool open = false;
         if (active) {
             const float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
             const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            if (accept_cell(__int_as_float(m.w), d2, theta)) {       // cell edge rides in meta.w                   // :309
+            if (accept_cell_sq(mf.w, d2, theta, theta2)) {               // cell edge rides in meta.w; :309
                 const float rinv = rsqrt_fast(d2 + eps2);
                 const float f = c.w * rinv * rinv * rinv;                // :280-290
                 ax += f * dx; ay += f * dy; az += f * dz;
                 if (COUNT) ++c_pc;
-                wake = m.y;                                              // sleep through this subtree
+                wake = skip;                                             // sleep through this subtree
             } else {
                 open = true;
             }
         }
-        k = __any_sync(FULL, open) ? m.x : m.y;                          // :293-297
+        k = __any_sync(FULL, open) ? first : skip;                       // :293-297
     }
     if (valid) {
         const size_t o = (size_t)(i - i0) * 3;
@@ -788,6 +815,7 @@ int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_c
     B200_TRY(T->digit.reserve(n));
     B200_TRY(T->part_idx.reserve(n * sizeof(int)));
     B200_TRY(T->part_pos.reserve(n * sizeof(float4)));
+    B200_TRY(T->nodes.reserve(T->max_nodes * 2 * sizeof(float4)));
     B200_TRY(T->globals.reserve(sizeof(TreeGlobals)));
     B200_TRY(T->tile_hist.reserve(T->max_tiles * 8 * sizeof(unsigned)));
     B200_TRY(T->tile_warp_prefix.reserve(T->max_tiles * 64 * sizeof(unsigned)));
@@ -848,6 +876,8 @@ int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_c
         com_kernel<<<cgrid, 256, 0, st>>>(g, L, meta, center, T->part_idx.as<int>(), T->posm, com);
         ctx->launches += 1;
     }
+    pack_nodes_kernel<<<pgrid, 256, 0, st>>>(g, max_depth, com, meta, T->nodes.as<float4>());
+    ctx->launches += 1;
     B200_CUDA(cudaGetLastError());
     T->built = true;
     return B200_OK;
@@ -890,12 +920,12 @@ int tree_walk(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* acc
     if (!per_thread) {
         if (T->counting)
             walk_warp_kernel<true><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
-                                                         T->com.as<float4>(), T->center.as<float4>(), T->meta.as<int4>(),
-                                                         T->part_pos.as<float4>(), theta, (float*)acc3, g);
+                                                         T->nodes.as<float4>(), T->part_pos.as<float4>(), theta,
+                                                         (float*)acc3, g);
         else
             walk_warp_kernel<false><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
-                                                          T->com.as<float4>(), T->center.as<float4>(), T->meta.as<int4>(),
-                                                          T->part_pos.as<float4>(), theta, (float*)acc3, g);
+                                                          T->nodes.as<float4>(), T->part_pos.as<float4>(), theta,
+                                                          (float*)acc3, g);
     } else if (T->counting)
         walk_kernel<true><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
                                                 T->com.as<float4>(), T->center.as<float4>(), T->meta.as<int4>(),
