@@ -100,6 +100,28 @@ int b200_direct_forces_parts_dev(b200_ctx* ctx, const void* const* parts,
                                  float eps, float box, int all_masses_equal,
                                  void* acc3, void* stream);
 
+/* ---- energy diagnostic -----------------------------------------
+ * Replaces compute_energy + launch_energy_computation
+ * (src/physics/lambda_cdm_kernels.cu:338-408, 492-516) and
+ * LambdaCDMSimulationImpl::compute_energy (src/physics/lambda_cdm_impl.cu:222-241).
+ * The O(N^2) pair sum runs in the direct-sum kernel (potential instance: 7-8 lane-ops
+ * + 1 MUFU per pair, FP64 outer sums) instead of one thread per particle looping over
+ * j > i from global memory.
+ * phi_i = sum_{j != i} m_j / sqrt(|d|^2 + eps^2) >= 0 for targets posm4[i0..i0+n_targets);
+ * box > 0: minimum image.  phi: float[n_targets] (device).  The pair loop has no self test;
+ * the i == i term m_i/eps is subtracted afterwards, which leaves an absolute error of about
+ * 1e-7 m_i/eps in phi_i (negligible unless phi_i << 1/eps, i.e. a handful of particles). */
+int b200_direct_potential_dev(b200_ctx* ctx, const void* posm4, size_t n_sources, size_t i0,
+                              size_t n_targets, float eps, float box, void* phi, void* stream);
+/* kinetic = sum 1/2 m v^2, potential = -1/2 sum m_i phi_i (G = 1) over the targets
+ * [i0, i0+n_targets); vel3 = float[3*n_targets] (device, the targets' velocities).
+ * Over all particles (i0 = 0, n_targets = n_sources) potential is the reference's
+ * sum_{i<j} -m_i m_j / r.  On a sharded run each rank gets its share: add them
+ * (b200_allreduce_sum_f64).  Blocks until the two HOST doubles are written. */
+int b200_energy_dev(b200_ctx* ctx, const void* posm4, size_t n_sources, size_t i0, size_t n_targets,
+                    const void* vel3, float eps, float box, double* kinetic, double* potential,
+                    void* stream);
+
 /* ---- Barnes-Hut (rows T1-T6) ----------------------------------------------
  * Morton keys: replaces compute_morton_codes_kernel + morton3D
  * (src/forces/barnes_hut_tree.cu:33-55, include/forces/barnes_hut_tree.hpp:11-27);
@@ -203,6 +225,10 @@ int b200_shard_info(const b200_ctx* ctx, int* rank, int* world);
  * no host staging.  Equal shards use one ncclAllGather; ragged ones a grouped
  * broadcast per owner. */
 int b200_allgather_sources_dev(b200_ctx* ctx, void* posm4_full, size_t n_total, void* stream);
+/* Sum `count` HOST doubles over the ranks of b200_shard_init (in place; blocking).
+ * The scalar diagnostics' MPI_Allreduce (src/mpi/cluster_comm.cpp:208-216 reduces forces;
+ * here only energies need it).  A no-op on an unsharded context. */
+int b200_allreduce_sum_f64(b200_ctx* ctx, double* values, size_t count);
 
 int b200_device_alloc(b200_ctx* ctx, size_t bytes, void** dev_ptr);   /* cudaMalloc: exportable */
 int b200_device_free(b200_ctx* ctx, void* dev_ptr);

@@ -71,6 +71,7 @@ int b200_ctx_destroy(b200_ctx* ctx) {
     tree_destroy(ctx);
     shard_finalize(ctx);
     ctx->src_tiles.release(); ctx->partials.release(); ctx->mass_flag.release(); ctx->zero_flag.release();
+    ctx->energy_part.release(); ctx->energy_phi.release(); ctx->energy_out.release();
     ctx->h_pos3.release(); ctx->h_vel3.release(); ctx->h_mass.release(); ctx->h_posm4.release(); ctx->h_acc3.release();
     ctx->probe.release(); ctx->sort_scratch.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -110,6 +111,49 @@ int b200_direct_forces_dev(b200_ctx* ctx, const void* posm4, size_t n_sources, s
     src.total_tiles = src.tile_end[0] = (int)((n_sources + DIRECT_TILE_J - 1) / DIRECT_TILE_J);
     return direct_forces(ctx, src, (const float4*)posm4 + i0, n_targets, eps, box, acc3,
                          ctx->mass_flag.as<int>(), st);
+}
+
+// ---- energy diagnostic ---------------------------------------------------------
+int b200_direct_potential_dev(b200_ctx* ctx, const void* posm4, size_t n_sources, size_t i0,
+                              size_t n_targets, float eps, float box, void* phi, void* stream) {
+    if (!ctx) return B200_ERR_INVALID;
+    if (n_targets == 0) return B200_OK;
+    if (!posm4 || !phi || i0 + n_targets > n_sources) return B200_ERR_INVALID;
+    if (!(eps > 0.f) || box < 0.f) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick_stream(ctx, stream);
+    B200_TRY(ctx->src_tiles.reserve(direct_tiles_bytes(n_sources)));
+    B200_TRY(ctx->mass_flag.reserve(sizeof(int)));
+    B200_TRY(direct_pack_tiles(ctx, posm4, n_sources, ctx->src_tiles.as<float>(), ctx->mass_flag.as<int>(), st));
+    DirectSources src;
+    memset(&src, 0, sizeof src);
+    src.n_parts = 1;
+    src.tiles[0] = ctx->src_tiles.as<float>();
+    src.total_tiles = src.tile_end[0] = (int)((n_sources + DIRECT_TILE_J - 1) / DIRECT_TILE_J);
+    return direct_potential(ctx, src, (const float4*)posm4 + i0, n_targets, eps, box, phi,
+                            ctx->mass_flag.as<int>(), st);
+}
+
+int b200_energy_dev(b200_ctx* ctx, const void* posm4, size_t n_sources, size_t i0, size_t n_targets,
+                    const void* vel3, float eps, float box, double* kinetic, double* potential,
+                    void* stream) {
+    if (!ctx || !kinetic || !potential) return B200_ERR_INVALID;
+    *kinetic = *potential = 0.0;
+    if (n_targets == 0) return B200_OK;
+    if (!posm4 || !vel3 || i0 + n_targets > n_sources) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick_stream(ctx, stream);
+    B200_TRY(ctx->energy_phi.reserve(n_targets * sizeof(float)));
+    B200_TRY(ctx->energy_out.reserve(2 * sizeof(double)));
+    B200_TRY(b200_direct_potential_dev(ctx, posm4, n_sources, i0, n_targets, eps, box, ctx->energy_phi.p, stream));
+    B200_TRY(energy_reduce(ctx, (const float4*)posm4 + i0, vel3, ctx->energy_phi.p, n_targets,
+                           ctx->energy_out.as<double>(), st));
+    double h[2];
+    B200_CUDA(cudaMemcpyAsync(h, ctx->energy_out.p, sizeof h, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    *kinetic = h[0];
+    *potential = h[1];
+    return B200_OK;
 }
 
 size_t b200_tiles_bytes(size_t n) { return direct_tiles_bytes(n); }
@@ -349,6 +393,12 @@ int b200_shard_finalize(b200_ctx* ctx) {
 int b200_shard_info(const b200_ctx* ctx, int* rank, int* world) {
     if (!ctx) return B200_ERR_INVALID;
     return shard_info(ctx, rank, world);
+}
+
+int b200_allreduce_sum_f64(b200_ctx* ctx, double* values, size_t count) {
+    if (!ctx || (count && !values)) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return shard_allreduce_f64(ctx, values, count);
 }
 
 int b200_allgather_sources_dev(b200_ctx* ctx, void* posm4_full, size_t n_total, void* stream) {

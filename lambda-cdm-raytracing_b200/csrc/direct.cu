@@ -145,7 +145,11 @@ __device__ __forceinline__ const float* tile_ptr(const DirectSources& src, int t
 // R targets per thread, THREADS threads per CTA, MINB CTAs per SM.
 // UNIT: every source has the same mass (runs only if *mass_diff == 0);
 // !UNIT: general masses (runs only if mass_diff is null or *mass_diff != 0).
-template <int R, int THREADS, int MINB, bool PERIODIC, bool UNIT>
+// POT: accumulate the potential sum_j m_j / sqrt(|d|^2 + eps^2) (the energy diagnostic,
+// compute_energy at src/physics/lambda_cdm_kernels.cu:338-408) instead of the
+// acceleration: 7 (equal masses) / 8 lane-ops + 1 MUFU per pair, component 0 of the
+// partial records only.
+template <int R, int THREADS, int MINB, bool PERIODIC, bool UNIT, bool POT = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 direct_kernel(const DirectSources src, const float4* __restrict__ targets, long long n_targets,
               float eps2, float box, double* __restrict__ partials, long long n_units, int n_tiles,
@@ -256,6 +260,11 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
                 float r2a, r2b;
                 unpk(r2, r2a, r2b);
                 u64 rinv = pk(rsqrt_approx(r2a), rsqrt_approx(r2b));
+                if constexpr (POT) {
+                    if constexpr (UNIT) ax[r] = add2(ax[r], rinv);
+                    else ax[r] = fma2(M, rinv, ax[r]);
+                    continue;
+                }
                 u64 f = mul2(rinv, rinv);
                 if constexpr (UNIT) f = mul2(f, rinv);
                 else f = mul2(f, mul2(M, rinv));
@@ -278,8 +287,10 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
         for (int r = 0; r < R; ++r) {
             float lo, hi;
             unpk(ax[r], lo, hi); dsum[(0 * R + r) * THREADS + tid] += (double)(lo + hi);
-            unpk(ay[r], lo, hi); dsum[(1 * R + r) * THREADS + tid] += (double)(lo + hi);
-            unpk(az[r], lo, hi); dsum[(2 * R + r) * THREADS + tid] += (double)(lo + hi);
+            if constexpr (!POT) {
+                unpk(ay[r], lo, hi); dsum[(1 * R + r) * THREADS + tid] += (double)(lo + hi);
+                unpk(az[r], lo, hi); dsum[(2 * R + r) * THREADS + tid] += (double)(lo + hi);
+            }
         }
         __syncthreads();      // every warp is done with stage s -> it may be refilled
 
@@ -290,8 +301,10 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 rec[0 * BLOCK_I + r * THREADS + tid] = dsum[(0 * R + r) * THREADS + tid];
-                rec[1 * BLOCK_I + r * THREADS + tid] = dsum[(1 * R + r) * THREADS + tid];
-                rec[2 * BLOCK_I + r * THREADS + tid] = dsum[(2 * R + r) * THREADS + tid];
+                if constexpr (!POT) {
+                    rec[1 * BLOCK_I + r * THREADS + tid] = dsum[(1 * R + r) * THREADS + tid];
+                    rec[2 * BLOCK_I + r * THREADS + tid] = dsum[(2 * R + r) * THREADS + tid];
+                }
             }
             if (t == n_tiles) {
                 t = 0;
@@ -332,12 +345,63 @@ __global__ void direct_finalize_kernel(const double* __restrict__ partials, floa
     acc3[3 * i + 2] = (float)sz;
 }
 
-template <int R, int THREADS, int MINB, bool PERIODIC>
+// Potential: phi_i = sum of the block's partial records minus the i == i term (the pair loop
+// has no self test: with d = 0 it added m_i * rsqrt(eps^2), the very value subtracted here).
+__global__ void potential_finalize_kernel(const double* __restrict__ partials, const float4* __restrict__ targets,
+                                          float* __restrict__ phi, long long n_targets, int block_i,
+                                          long long n_units, int n_tiles, int G, float eps2,
+                                          const int* __restrict__ mass_diff,
+                                          const float* __restrict__ first_tile) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_targets) return;
+    long long b = i / block_i;
+    int o = (int)(i % block_i);
+    long long uf = b * n_tiles, ul = uf + n_tiles - 1;
+    long long cf = ((uf + 1) * G - 1) / n_units;
+    long long cl = ((ul + 1) * G - 1) / n_units;
+    double s = 0.0;
+    for (long long c = cf; c <= cl; ++c) s += partials[(size_t)(c + b) * 3 * block_i + o];
+    const double self = (double)rsqrt_approx(eps2);
+    if (mass_diff != nullptr && *mass_diff == 0) s = (s - self) * (double)first_tile[3 * DIRECT_TILE_J];
+    else s -= self * (double)targets[i].w;
+    phi[i] = (float)s;
+}
+
+// KE = sum 1/2 m v^2 and PE = -1/2 sum m_i phi_i over the targets, FP64, two fixed-order stages.
+constexpr int ENERGY_BLOCKS = 296;
+__global__ void __launch_bounds__(256)
+energy_partial_kernel(const float4* __restrict__ targets, const float* __restrict__ vel3,
+                      const float* __restrict__ phi, long long n, double* __restrict__ part /*[2][gridDim.x]*/) {
+    __shared__ double sk[256], sp[256];
+    double ke = 0.0, pe = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float4 p = targets[i];
+        const double vx = vel3[3 * i], vy = vel3[3 * i + 1], vz = vel3[3 * i + 2];
+        ke += 0.5 * (double)p.w * (vx * vx + vy * vy + vz * vz);
+        pe -= 0.5 * (double)p.w * (double)phi[i];
+    }
+    sk[threadIdx.x] = ke; sp[threadIdx.x] = pe;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { sk[threadIdx.x] += sk[threadIdx.x + s]; sp[threadIdx.x] += sp[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { part[blockIdx.x] = sk[0]; part[gridDim.x + blockIdx.x] = sp[0]; }
+}
+__global__ void energy_final_kernel(const double* __restrict__ part, int nblocks, double* __restrict__ out2) {
+    if (threadIdx.x < 2) {
+        double s = 0.0;
+        for (int b = 0; b < nblocks; ++b) s += part[threadIdx.x * nblocks + b];
+        out2[threadIdx.x] = s;
+    }
+}
+
+template <int R, int THREADS, int MINB, bool PERIODIC, bool POT = false>
 int launch_direct(b200_ctx* ctx, const DirectSources& src, const float4* targets, size_t n_targets,
                   float eps, float box, float* acc3, const int* mass_diff, cudaStream_t st) {
     constexpr int BLOCK_I = THREADS * R;
-    auto kern_g = direct_kernel<R, THREADS, MINB, PERIODIC, false>;
-    auto kern_u = direct_kernel<R, THREADS, MINB, PERIODIC, true>;
+    auto kern_g = direct_kernel<R, THREADS, MINB, PERIODIC, false, POT>;
+    auto kern_u = direct_kernel<R, THREADS, MINB, PERIODIC, true, POT>;
     const size_t smem = STAGES * TILE_BYTES + 64 + (size_t)3 * R * THREADS * sizeof(double);
     static bool configured = false;     // per template instantiation
     static int blocks_per_sm = 0;
@@ -366,9 +430,14 @@ int launch_direct(b200_ctx* ctx, const DirectSources& src, const float4* targets
     if (ctx->timing) B200_CUDA(cudaEventRecord(ctx->ev1, st));
     B200_CUDA(cudaGetLastError());
     const int fb = 256;
-    direct_finalize_kernel<<<(unsigned)((n_targets + fb - 1) / fb), fb, 0, st>>>(
-        ctx->partials.as<double>(), acc3, (long long)n_targets, BLOCK_I, U, NT, (int)G, mass_diff,
-        src.tiles[0]);
+    if constexpr (POT)
+        potential_finalize_kernel<<<(unsigned)((n_targets + fb - 1) / fb), fb, 0, st>>>(
+            ctx->partials.as<double>(), targets, acc3, (long long)n_targets, BLOCK_I, U, NT, (int)G, eps * eps,
+            mass_diff, src.tiles[0]);
+    else
+        direct_finalize_kernel<<<(unsigned)((n_targets + fb - 1) / fb), fb, 0, st>>>(
+            ctx->partials.as<double>(), acc3, (long long)n_targets, BLOCK_I, U, NT, (int)G, mass_diff,
+            src.tiles[0]);
     B200_CUDA(cudaGetLastError());
     ctx->launches += mass_diff ? 3 : 2;
     return B200_OK;
@@ -434,6 +503,39 @@ int direct_forces(b200_ctx* ctx, const DirectSources& src, const void* targets4,
     }
     return small ? launch_direct<2, 256, 2, false>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st)
                  : launch_direct<6, 256, 1, false>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
+}
+
+// Per-target potential phi_i = sum_{j != i} m_j / sqrt(|d|^2 + eps^2) (positive, G = 1).
+int direct_potential(b200_ctx* ctx, const DirectSources& src, const void* targets4, size_t n_targets,
+                     float eps, float box, void* phi, const int* mass_diff, cudaStream_t st) {
+    if (!(eps > 0.f) || box < 0.f) return B200_ERR_INVALID;
+    if (n_targets == 0) return B200_OK;
+    if (src.total_tiles <= 0) {
+        B200_CUDA(cudaMemsetAsync(phi, 0, n_targets * sizeof(float), st));
+        return B200_OK;
+    }
+    const float4* tg = (const float4*)targets4;
+    float* out = (float*)phi;
+    const long long units6 = (((long long)n_targets + 1535) / 1536) * (long long)src.total_tiles;
+    const bool small = n_targets < 4 * 1536 || units6 < 4ll * ctx->sm_count;
+    if (box > 0.f)
+        return small ? launch_direct<2, 256, 2, true, true>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st)
+                     : launch_direct<4, 256, 1, true, true>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
+    return small ? launch_direct<2, 256, 2, false, true>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st)
+                 : launch_direct<6, 256, 1, false, true>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
+}
+
+// out2 (device): [0] = sum 1/2 m v^2, [1] = -1/2 sum m phi over the n targets.
+int energy_reduce(b200_ctx* ctx, const void* targets4, const void* vel3, const void* phi, size_t n,
+                  double* out2, cudaStream_t st) {
+    B200_TRY(ctx->energy_part.reserve(2 * ENERGY_BLOCKS * sizeof(double)));
+    energy_partial_kernel<<<ENERGY_BLOCKS, 256, 0, st>>>((const float4*)targets4, (const float*)vel3,
+                                                         (const float*)phi, (long long)n,
+                                                         ctx->energy_part.as<double>());
+    energy_final_kernel<<<1, 32, 0, st>>>(ctx->energy_part.as<double>(), ENERGY_BLOCKS, out2);
+    B200_CUDA(cudaGetLastError());
+    ctx->launches += 2;
+    return B200_OK;
 }
 
 }  // namespace b200

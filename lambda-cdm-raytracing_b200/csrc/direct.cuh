@@ -20,5 +20,9 @@ int direct_pack_tiles(b200_ctx* ctx, const void* posm4, size_t n, float* tiles, 
                       cudaStream_t st);
 int direct_forces(b200_ctx* ctx, const DirectSources& src, const void* targets4, size_t n_targets,
                   float eps, float box, void* acc3, const int* mass_diff, cudaStream_t st);
+int direct_potential(b200_ctx* ctx, const DirectSources& src, const void* targets4, size_t n_targets,
+                     float eps, float box, void* phi, const int* mass_diff, cudaStream_t st);
+int energy_reduce(b200_ctx* ctx, const void* targets4, const void* vel3, const void* phi, size_t n,
+                  double* out2, cudaStream_t st);
 
 }  // namespace b200

@@ -31,6 +31,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -55,6 +56,7 @@ void load_nccl() {
     B200_SYM(CommDestroy, "ncclCommDestroy")
     B200_SYM(AllGather, "ncclAllGather")
     B200_SYM(Broadcast, "ncclBroadcast")
+    B200_SYM(AllReduce, "ncclAllReduce")
     B200_SYM(GroupStart, "ncclGroupStart")
     B200_SYM(GroupEnd, "ncclGroupEnd")
     B200_SYM(GetErrorString, "ncclGetErrorString")
@@ -159,6 +161,20 @@ int shard_allgather(b200_ctx* ctx, void* posm4_full, size_t n_total, cudaStream_
         if (e != ncclSuccess) { api->GroupEnd(); return 2000 + (int)e; }
     }
     B200_NCCL(api->GroupEnd());
+    return B200_OK;
+}
+
+// Sum `count` host doubles over the ranks (diagnostics: energies).  Blocking.
+int shard_allreduce_f64(b200_ctx* ctx, double* values, size_t count) {
+    ShardState* s = ctx->shard;
+    if (!s || s->world == 1 || count == 0) return B200_OK;
+    const NcclApi* api = nccl();
+    if (!api) return B200_ERR_UNSUPPORTED;
+    B200_TRY(ctx->energy_out.reserve(count * sizeof(double)));
+    B200_CUDA(cudaMemcpyAsync(ctx->energy_out.p, values, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    B200_NCCL(api->AllReduce(ctx->energy_out.p, ctx->energy_out.p, count, ncclDouble, ncclSum, s->comm, ctx->stream));
+    B200_CUDA(cudaMemcpyAsync(values, ctx->energy_out.p, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
 }
 

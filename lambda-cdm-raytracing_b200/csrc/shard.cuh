@@ -11,6 +11,7 @@ int shard_init(b200_ctx* ctx, const unsigned char id[B200_SHARD_ID_BYTES], int r
 int shard_finalize(b200_ctx* ctx);
 int shard_info(const b200_ctx* ctx, int* rank, int* world);
 int shard_allgather(b200_ctx* ctx, void* posm4_full, size_t n_total, cudaStream_t st);
+int shard_allreduce_f64(b200_ctx* ctx, double* values, size_t count);
 const char* shard_error_string(int nccl_result);
 
 }  // namespace b200

@@ -96,6 +96,18 @@ void B200LambdaCDMSimulation::compute_forces() {
     have_forces_ = true;
 }
 
+void B200LambdaCDMSimulation::compute_energy() {
+    // launch_energy_computation (lambda_cdm_kernels.cu:492-516): periodic minimum image whenever the
+    // force method is (Direct); open boundary for DirectOpen and Tree.
+    const float box = (method_ == B200ForceMethod::Direct) ? box_size_ : 0.0f;
+    double e[2] = {0.0, 0.0};
+    check(b200_energy_dev(ctx_, d_posm_, num_particles_, i0_, n_local_, d_vel_, softening_, box, &e[0], &e[1], stream_),
+          "energy");
+    if (world_ > 1) check(b200_allreduce_sum_f64(ctx_, e, 2), "energy all-reduce");
+    kinetic_energy_ = e[0];
+    potential_energy_ = e[1];
+}
+
 void B200LambdaCDMSimulation::update_scale_factor(double dt) {
     scale_factor_ += scale_factor_ * cosmology_.hubble_parameter_a(scale_factor_) * dt;   // lambda_cdm_impl.cu:261-269
 }

@@ -12,7 +12,9 @@
 //  * initialize_particles() is seeded (the reference seeds curand from the clock);
 //  * the force method is selectable: Direct (periodic minimum image, like the
 //    reference's K1/K2 kernels) or Tree (the CPU TreeForceComputer's semantics);
-//  * compute_energy() is a diagnostic outside the hot path and is not provided;
+//  * compute_energy() runs the O(N^2) pair sum in the direct-sum kernel's potential
+//    instance and returns doubles (the reference keeps float atomics, lambda_cdm_kernels.cu:402-407);
+//    on a sharded run the two sums are all-reduced, so every rank reports the totals;
 //  * enable_sharding(): target-sharded data parallelism over several GPUs.
 //    One object per GPU (one process or one thread each); rank r integrates particles
 //    [r*N/G, (r+1)*N/G) and the float4 positions are all-gathered with NCCL every step
@@ -46,6 +48,7 @@ class B200LambdaCDMSimulation {
     float theta_ = 0.5f;
     int leaf_capacity_ = 8, max_depth_ = 20;
     bool have_forces_ = false;
+    double kinetic_energy_ = 0.0, potential_energy_ = 0.0;
     int rank_ = 0, world_ = 1;              // enable_sharding()
     size_t i0_ = 0, n_local_ = 0;           // this rank's particle range
     void* d_posm_ = nullptr;                // float4[N]
@@ -77,6 +80,7 @@ public:
     void step(double dt);
     void compute_forces();
     void update_scale_factor(double dt);
+    void compute_energy();                                     // lambda_cdm_impl.cu:222-241
 
     // Cosmology functions (lambda_cdm.hpp:52-55)
     double hubble_function(double a) const { return cosmology_.hubble_parameter_a(a); }
@@ -97,6 +101,9 @@ public:
     size_t get_num_particles() const { return num_particles_; }
     float get_box_size() const { return box_size_; }
     size_t get_current_step() const { return current_step_; }
+    double get_kinetic_energy() const { return kinetic_energy_; }        // after compute_energy()
+    double get_potential_energy() const { return potential_energy_; }
+    double get_total_energy() const { return kinetic_energy_ + potential_energy_; }
 };
 
 }  // namespace physics

@@ -25,7 +25,7 @@ EXPORTS = [
     "b200_leapfrog_dev", "b200_leapfrog_host", "b200_hubble_a", "b200_scale_factor_step", "b200_pack_posm_dev",
     "b200_device_alloc", "b200_device_free", "b200_memcpy_h2d", "b200_memcpy_d2h", "b200_unpack_pos3_dev", "b200_ipc_export", "b200_ipc_open", "b200_ipc_close",
     "b200_shard_range", "b200_shard_unique_id", "b200_shard_init", "b200_shard_finalize", "b200_shard_info",
-    "b200_allgather_sources_dev",
+    "b200_allgather_sources_dev", "b200_allreduce_sum_f64", "b200_direct_potential_dev", "b200_energy_dev",
     "b200_fp32_peak_probe", "b200_last_kernel_ms", "b200_set_timing", "b200_launch_count",
 ]
 
@@ -87,6 +87,9 @@ def load_library(path=None):
     L.b200_shard_finalize.argtypes = [vp]
     L.b200_shard_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     L.b200_allgather_sources_dev.argtypes = [vp, vp, sz, vp]
+    L.b200_allreduce_sum_f64.argtypes = [vp, vp, sz]
+    L.b200_direct_potential_dev.argtypes = [vp, vp, sz, sz, sz, f32, f32, vp, vp]
+    L.b200_energy_dev.argtypes = [vp, vp, sz, sz, sz, vp, f32, f32, C.POINTER(f64), C.POINTER(f64), vp]
     L.b200_fp32_peak_probe.argtypes = [vp, i32, i32, C.POINTER(f64), C.POINTER(f32)]
     L.b200_last_kernel_ms.argtypes = [vp, C.POINTER(f32)]
     L.b200_set_timing.argtypes = [vp, i32]
@@ -281,6 +284,26 @@ class Engine:
         self._check(self.L.b200_ipc_close(self._h, ptr))
 
     # -- measurement ---------------------------------------------------------
+    # ---- energy diagnostic ----
+    def direct_potential_dev(self, posm, phi, i0=0, n_targets=None, eps=0.01, box=0.0, stream=None):
+        n = posm.shape[0]
+        nt = n - i0 if n_targets is None else n_targets
+        self._check(self.L.b200_direct_potential_dev(self._h, _ptr(posm), n, i0, nt, eps, box, _ptr(phi), _stream(stream)))
+
+    def energy_dev(self, posm, vel, i0=0, n_targets=None, eps=0.01, box=0.0, stream=None):
+        """(kinetic, potential) of targets [i0, i0+n_targets) as host floats; vel = their velocities."""
+        n = posm.shape[0]
+        nt = n - i0 if n_targets is None else n_targets
+        ke, pe = C.c_double(), C.c_double()
+        self._check(self.L.b200_energy_dev(self._h, _ptr(posm), n, i0, nt, _ptr(vel), eps, box,
+                                           C.byref(ke), C.byref(pe), _stream(stream)))
+        return ke.value, pe.value
+
+    def allreduce_sum_f64(self, values):
+        arr = np.ascontiguousarray(values, np.float64)
+        self._check(self.L.b200_allreduce_sum_f64(self._h, arr.ctypes.data, arr.size))
+        return arr
+
     # ---- NCCL source all-gather owned by the context (hosts without torch.distributed) ----
     def shard_unique_id(self):
         buf = (C.c_ubyte * 128)()

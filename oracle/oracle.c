@@ -118,6 +118,45 @@ void orc_direct_periodic_f32(const float* pos3, const float* mass, size_t n,
     }
 }
 
+/* ------------------------------------------------------------------ K6 --- */
+/* compute_energy (src/physics/lambda_cdm_kernels.cu:338-408): kinetic
+ * 1/2 m v^2 (:364) and potential -G m_i m_j / sqrt(|d|^2 + eps^2) over pairs
+ * j > i (:367-386), d by minimum_image (:122-141, half-box compare) when
+ * box > 0.  The reference adds float partial sums with atomics (:402-407),
+ * which has no defined order; this restatement keeps the FP32 pair arithmetic
+ * (:375-385) and accumulates in double, so it is the exact value the
+ * reference's sum scatters around.  eps2 is the reference's `softening2`. */
+void orc_energy(const float* pos3, const float* vel3, const float* mass, size_t n,
+                float eps2, float box, double* kinetic, double* potential) {
+    double ke = 0.0, pe = 0.0;
+    const float half_box = box * 0.5f;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : ke, pe)
+    for (long long ii = 0; ii < (long long)n; ++ii) {
+        size_t i = (size_t)ii;
+        float mi = mass ? mass[i] : 1.0f;
+        float vx = vel3[3 * i], vy = vel3[3 * i + 1], vz = vel3[3 * i + 2];
+        ke += (double)(0.5f * mi * (vx * vx + vy * vy + vz * vz));      /* :364 */
+        double p = 0.0;
+        for (size_t j = i + 1; j < n; ++j) {                            /* :367 */
+            float dx = pos3[3 * j + 0] - pos3[3 * i + 0];               /* :375-378 */
+            float dy = pos3[3 * j + 1] - pos3[3 * i + 1];
+            float dz = pos3[3 * j + 2] - pos3[3 * i + 2];
+            if (box > 0.0f) {                                           /* :122-141 */
+                if (dx > half_box) dx -= box; else if (dx < -half_box) dx += box;
+                if (dy > half_box) dy -= box; else if (dy < -half_box) dy += box;
+                if (dz > half_box) dz -= box; else if (dz < -half_box) dz += box;
+            }
+            float r2 = dx * dx + dy * dy + dz * dz + eps2;              /* :381 */
+            float r = sqrtf(r2);                                        /* :382 */
+            float mj = mass ? mass[j] : 1.0f;
+            p += (double)(-1.0f * mi * mj / r);                         /* :385, G_CONSTANT = 1 (:114) */
+        }
+        pe += p;
+    }
+    *kinetic = ke;
+    *potential = pe;
+}
+
 /* ------------------------------------------------------------------ T1 --- */
 /* include/forces/barnes_hut_tree.hpp:11-17 */
 uint32_t orc_expand_bits(uint32_t v) {

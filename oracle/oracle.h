@@ -45,6 +45,10 @@ void orc_direct_periodic_f32(const float* pos3, const float* mass, size_t n,
 
 /* ---- T1: Morton keys (include/forces/barnes_hut_tree.hpp:11-27,
  *          src/forces/barnes_hut_tree.cu:33-55) ----------------------------- */
+/* K6: compute_energy (src/physics/lambda_cdm_kernels.cu:338-408); box <= 0 = open boundary */
+void orc_energy(const float* pos3, const float* vel3, const float* mass, size_t n,
+                float eps2, float box, double* kinetic, double* potential);
+
 uint32_t orc_expand_bits(uint32_t v);
 uint32_t orc_morton3d(float x, float y, float z);          /* inputs in [0,1] */
 void orc_morton_keys(const float* pos3, size_t n, float box, uint32_t* keys);

@@ -87,6 +87,7 @@ class Oracle:
         L.orc_direct_f32.argtypes = [_f32p, C.c_void_p, sz, sz, sz, C.c_float, _f32p]
         L.orc_direct_f64.argtypes = [_f32p, C.c_void_p, sz, sz, sz, C.c_double, _f64p]
         L.orc_direct_periodic_f32.argtypes = [_f32p, C.c_void_p, sz, sz, sz, C.c_float, C.c_float, _f32p]
+        L.orc_energy.argtypes = [_f32p, _f32p, C.c_void_p, sz, C.c_float, C.c_float, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.orc_expand_bits.argtypes = [C.c_uint32]; L.orc_expand_bits.restype = C.c_uint32
         L.orc_morton3d.argtypes = [C.c_float] * 3; L.orc_morton3d.restype = C.c_uint32
         L.orc_morton_keys.argtypes = [_f32p, sz, C.c_float, _u32p]
@@ -127,6 +128,15 @@ class Oracle:
         out = np.empty((nt, 3), np.float32)
         self.lib.orc_direct_periodic_f32(pos, _mass_arg(mass), n, i0, nt, eps, box, out)
         return out
+
+    def energy(self, pos, vel, mass, eps, box=0.0):
+        """(kinetic, potential) as the reference's compute_energy defines them; eps is the softening LENGTH."""
+        pos = np.ascontiguousarray(pos, np.float32)
+        vel = np.ascontiguousarray(vel, np.float32)
+        ke, pe = C.c_double(), C.c_double()
+        self.lib.orc_energy(pos, vel, _mass_arg(mass), pos.shape[0], np.float32(eps) * np.float32(eps), box,
+                            C.byref(ke), C.byref(pe))
+        return ke.value, pe.value
 
     # -- keys / sort ---------------------------------------------------------
     def expand_bits(self, v):

@@ -139,3 +139,16 @@ def test_oracle_vs_reference_live(oracle, ref):
     assert np.array_equal(oracle.morton_keys(p + 50, 100.0), ref.morton_keys(p + 50, 100.0))
     for a in (0.1, 0.5, 1.0, 1.7):
         assert oracle.hubble_a(a) == ref.hubble_a(a)
+
+
+def test_energy_known_answer(oracle):
+    """Two bodies: KE = 1/2*1*1 + 1/2*3*4, PE = -3/sqrt(1 + eps^2) (compute_energy, lambda_cdm_kernels.cu:364-385);
+    across the periodic box the pair sits 0.2 apart."""
+    pos = np.array([[0, 0, 0], [1, 0, 0]], np.float32)
+    vel = np.array([[1, 0, 0], [0, 2, 0]], np.float32)
+    m = np.array([1, 3], np.float32)
+    ke, pe = oracle.energy(pos, vel, m, 0.01)
+    assert ke == 6.5 and abs(pe + 3.0 / np.sqrt(1.0001)) < 1e-6
+    pos2 = np.array([[0.1, 5, 5], [99.9, 5, 5]], np.float32)
+    _, pe2 = oracle.energy(pos2, vel, m, 0.01, box=100.0)
+    assert abs(pe2 + 3.0 / np.sqrt(0.04 + 1e-4)) < 1e-3      # 99.9f - 0.1f carries FP32 rounding
