@@ -39,7 +39,7 @@ enum b200_status {
     B200_ERR_STATE = 3,        /* call out of order (walk before build ...) */
     B200_ERR_NOMEM = 4,
     B200_ERR_UNSUPPORTED = 5
-    /* 1000 + cudaError_t, 2000 + ncclResult_t */
+    /* 1000 + cudaError_t, 2000 + ncclResult_t, 3000 + cufftResult */
 };
 
 const char* b200_error_string(int status);
@@ -191,6 +191,34 @@ int b200_leapfrog_host(b200_ctx* ctx, float* pos3, float* vel3, const float* acc
 double b200_hubble_a(double a, double omega_m, double omega_k, double omega_lambda, double h);
 double b200_scale_factor_step(double a, double dt, double omega_m, double omega_k,
                               double omega_lambda, double h);
+
+/* ---- initial conditions ------------------------------------------
+ * Zel'dovich particles on the device.  Everything the reference's
+ * InitialConditionsGenerator defines is kept -- BBKS-form P(k) = k^n_s T^2 normalised to
+ * sigma_8 (src/physics/initial_conditions.cpp:83-171), Carroll-et-al. growth factor and
+ * f = Omega_m(a)^0.55 (include/physics/cosmology_model.hpp:79-97), cell-centre grid, flat
+ * index i*G*G + j*G + k, wrap into [0, box), v = a H f D psi, unit masses, stride subsample
+ * (:279-298, 334-380, 412-418) -- except its displacement step (:304-332), which skips the
+ * inverse Fourier transform; here psi(x) is the inverse FFT of i k delta_k / k^2 (cuFFT,
+ * bound at run time; B200_ERR_UNSUPPORTED if libcufft is absent).  White noise comes from
+ * a counter-based hash of (seed, cell), so the field does not depend on launch shape. */
+typedef struct b200_ic_params {
+    int grid;                 /* G: grid points per dimension (even, 4..2048) */
+    float box;                /* box edge, Mpc/h */
+    double z_initial;
+    uint32_t seed;
+    double omega_m, omega_lambda, omega_k, h, sigma_8, n_s;
+    float particle_mass;      /* written to posm4.w (<= 0 means 1) */
+    float origin_shift;       /* subtracted from every coordinate after the wrap: box/2 gives the
+                                 origin-centred convention of the CPU tree's root cube */
+} b200_ic_params;
+void b200_ic_params_default(b200_ic_params* p);   /* the reference's defaults: 256, 100, z 49, seed 12345, ... */
+/* n_particles <= G^3: particle p is grid point p * max(1, G^3 / n_particles).
+ * posm4: float4[n_particles], vel3: float[3*n_particles] (device).  stats (host, may be NULL):
+ * [0] r.m.s. displacement, [1] largest displacement (Mpc/h), [2] growth factor D(a_init),
+ * [3] a H f.  Blocking. */
+int b200_zeldovich_ics_dev(b200_ctx* ctx, const b200_ic_params* params, size_t n_particles,
+                           void* posm4, void* vel3, double stats[4], void* stream);
 
 /* ---- layout helpers --------------------------------------------------------
  * pos3 + mass (device) -> float4 x,y,z,m (device); mass == NULL -> 1. */

@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "direct.cuh"
+#include "ics.cuh"
 #include "leapfrog.cuh"
 #include "probe.cuh"
 #include "shard.cuh"
@@ -31,6 +32,7 @@ const char* b200_error_string(int status) {
     }
     if (status >= 1000 && status < 2000) return cudaGetErrorString((cudaError_t)(status - 1000));
     if (status >= 2000 && status < 3000) return shard_error_string(status - 2000);
+    if (status >= 3000 && status < 4000) return "cuFFT error (status - 3000 is the cufftResult)";
     return "unknown b200grav status";
 }
 
@@ -72,6 +74,7 @@ int b200_ctx_destroy(b200_ctx* ctx) {
     shard_finalize(ctx);
     ctx->src_tiles.release(); ctx->partials.release(); ctx->mass_flag.release(); ctx->zero_flag.release();
     ctx->energy_part.release(); ctx->energy_phi.release(); ctx->energy_out.release();
+    ctx->ic_wk.release(); ctx->ic_tmp.release(); ctx->ic_psi.release(); ctx->ic_stats.release();
     ctx->h_pos3.release(); ctx->h_vel3.release(); ctx->h_mass.release(); ctx->h_posm4.release(); ctx->h_acc3.release();
     ctx->probe.release(); ctx->sort_scratch.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -358,6 +361,33 @@ int b200_pack_posm_dev(b200_ctx* ctx, const void* pos3, const void* mass, size_t
     if (!ctx || (n && (!pos3 || !posm4))) return B200_ERR_INVALID;
     B200_CUDA(cudaSetDevice(ctx->device));
     return pack_posm(ctx, pos3, mass, n, posm4, pick_stream(ctx, stream));
+}
+
+// ---- initial conditions --------------------------------------------------------
+void b200_ic_params_default(b200_ic_params* p) {
+    if (!p) return;
+    p->grid = 256;               // InitialConditionsParams defaults, initial_conditions.hpp:22-41
+    p->box = 100.0f;
+    p->z_initial = 49.0;
+    p->seed = 12345u;
+    p->omega_m = 0.31;           // CosmologyParams defaults, cosmology_model.hpp:11-18
+    p->omega_lambda = 0.69;
+    p->omega_k = 0.0;
+    p->h = 0.67;
+    p->sigma_8 = 0.81;
+    p->n_s = 0.965;
+    p->particle_mass = 1.0f;
+    p->origin_shift = 0.0f;
+}
+
+int b200_zeldovich_ics_dev(b200_ctx* ctx, const b200_ic_params* params, size_t n_particles, void* posm4,
+                           void* vel3, double stats[4], void* stream) {
+    if (!ctx || !params || !posm4 || !vel3) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    const int s = zeldovich_ics(ctx, params, n_particles, posm4, vel3, stats, pick_stream(ctx, stream));
+    // three G^3 planes are a one-off: give them back
+    ctx->ic_wk.release(); ctx->ic_tmp.release(); ctx->ic_psi.release();
+    return s;
 }
 
 // ---- multi-GPU: NCCL source all-gather ---------------------------------------

@@ -26,8 +26,17 @@ EXPORTS = [
     "b200_device_alloc", "b200_device_free", "b200_memcpy_h2d", "b200_memcpy_d2h", "b200_unpack_pos3_dev", "b200_ipc_export", "b200_ipc_open", "b200_ipc_close",
     "b200_shard_range", "b200_shard_unique_id", "b200_shard_init", "b200_shard_finalize", "b200_shard_info",
     "b200_allgather_sources_dev", "b200_allreduce_sum_f64", "b200_direct_potential_dev", "b200_energy_dev",
+    "b200_ic_params_default", "b200_zeldovich_ics_dev",
     "b200_fp32_peak_probe", "b200_last_kernel_ms", "b200_set_timing", "b200_launch_count",
 ]
+
+
+class ICParams(C.Structure):
+    """b200_ic_params (include/b200grav.h)."""
+    _fields_ = [("grid", C.c_int), ("box", C.c_float), ("z_initial", C.c_double), ("seed", C.c_uint32),
+                ("omega_m", C.c_double), ("omega_lambda", C.c_double), ("omega_k", C.c_double), ("h", C.c_double),
+                ("sigma_8", C.c_double), ("n_s", C.c_double), ("particle_mass", C.c_float),
+                ("origin_shift", C.c_float)]
 
 
 class B200Error(RuntimeError):
@@ -90,6 +99,9 @@ def load_library(path=None):
     L.b200_allreduce_sum_f64.argtypes = [vp, vp, sz]
     L.b200_direct_potential_dev.argtypes = [vp, vp, sz, sz, sz, f32, f32, vp, vp]
     L.b200_energy_dev.argtypes = [vp, vp, sz, sz, sz, vp, f32, f32, C.POINTER(f64), C.POINTER(f64), vp]
+    L.b200_ic_params_default.argtypes = [C.POINTER(ICParams)]
+    L.b200_ic_params_default.restype = None
+    L.b200_zeldovich_ics_dev.argtypes = [vp, C.POINTER(ICParams), sz, vp, vp, C.POINTER(f64), vp]
     L.b200_fp32_peak_probe.argtypes = [vp, i32, i32, C.POINTER(f64), C.POINTER(f32)]
     L.b200_last_kernel_ms.argtypes = [vp, C.POINTER(f32)]
     L.b200_set_timing.argtypes = [vp, i32]
@@ -284,6 +296,22 @@ class Engine:
         self._check(self.L.b200_ipc_close(self._h, ptr))
 
     # -- measurement ---------------------------------------------------------
+    # ---- initial conditions ----
+    def zeldovich_ics_dev(self, posm, vel, n_particles=None, stream=None, **params):
+        """Fill posm float4[n] / vel float[3n] (device) with Zel'dovich particles; params override the
+        reference's defaults (grid, box, z_initial, seed, omega_m, ..., particle_mass, origin_shift).
+        Returns (rms displacement, largest displacement, growth factor, a*H*f)."""
+        p = ICParams()
+        self.L.b200_ic_params_default(C.byref(p))
+        for k, v in params.items():
+            if not hasattr(p, k):
+                raise TypeError(f"unknown initial-conditions parameter {k!r}")
+            setattr(p, k, v)
+        n = p.grid ** 3 if n_particles is None else n_particles
+        st = (C.c_double * 4)()
+        self._check(self.L.b200_zeldovich_ics_dev(self._h, C.byref(p), n, _ptr(posm), _ptr(vel), st, _stream(stream)))
+        return tuple(st)
+
     # ---- energy diagnostic ----
     def direct_potential_dev(self, posm, phi, i0=0, n_targets=None, eps=0.01, box=0.0, stream=None):
         n = posm.shape[0]

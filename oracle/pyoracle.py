@@ -229,6 +229,8 @@ class Ref:
                                     C.POINTER(sz), C.POINTER(sz)] + [C.c_void_p] * 8
         L.ref_hubble_a.argtypes = [C.c_double] * 5; L.ref_hubble_a.restype = C.c_double
         L.ref_zeldovich.argtypes = [sz, C.c_float, C.c_double, C.c_uint32, sz, _f32p, _f32p, _f32p]
+        if hasattr(L, "ref_ic_scalars"):
+            L.ref_ic_scalars.argtypes = [C.c_double, sz, _f64p, _f64p] + [C.POINTER(C.c_double)] * 3
         L.ref_random_particles.argtypes = [sz, C.c_float, C.c_uint32, _f32p, _f32p, _f32p]
         L.ref_expand_bits.argtypes = [C.c_uint32]; L.ref_expand_bits.restype = C.c_uint32
         L.ref_morton3d.argtypes = [C.c_float] * 3; L.ref_morton3d.restype = C.c_uint32
@@ -285,6 +287,15 @@ class Ref:
         rc = self.lib.ref_zeldovich(grid, box, z_init, seed, n, pos, vel, m)
         assert rc == 0, rc
         return pos, vel, m
+
+    def ic_scalars(self, k, z_init=49.0):
+        """Normalised P(k) of the IC generator and (D, f, H) at a_init, from the reference's own code."""
+        k = np.ascontiguousarray(k, np.float64)
+        pk = np.empty_like(k)
+        d, f, h = C.c_double(), C.c_double(), C.c_double()
+        rc = self.lib.ref_ic_scalars(z_init, k.size, k, pk, C.byref(d), C.byref(f), C.byref(h))
+        assert rc == 0, rc
+        return pk, d.value, f.value, h.value
 
     def random_particles(self, n, box=100.0, seed=12345):
         pos = np.empty((n, 3), np.float32); vel = np.empty((n, 3), np.float32); m = np.empty(n, np.float32)

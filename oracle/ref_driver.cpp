@@ -179,6 +179,32 @@ int ref_zeldovich(size_t grid, float box, double z_init, uint32_t seed, size_t n
     }
 }
 
+// Scalars of the IC generator: normalised P(k) (InitialConditionsGenerator::get_power_spectrum,
+// initial_conditions.cpp:173-199, after normalize_power_spectrum :131-144) and the growth
+// factor / growth rate / H at a_init (cosmology_model.hpp:49-97).
+int ref_ic_scalars(double z_init, size_t nk, const double* k, double* pk, double* growth,
+                   double* rate, double* hubble) {
+    try {
+        Quiet q;
+        physics::CosmologyParams cp;
+        cp.omega_m = 0.31; cp.omega_lambda = 0.69; cp.h = 0.67; cp.sigma_8 = 0.81; cp.n_s = 0.965;
+        physics::CosmologyModel cosmo(cp);
+        physics::InitialConditionsParams ip;
+        ip.grid_size = 8; ip.box_size = 100.0f; ip.z_initial = z_init;
+        ip.ps_type = physics::PowerSpectrumType::EISENSTEIN_HU;
+        ip.normalize_at_z0 = true;
+        physics::InitialConditionsGenerator gen(ip, cosmo);
+        for (size_t i = 0; i < nk; ++i) pk[i] = gen.get_power_spectrum(k[i]);
+        const double a = cosmo.z_to_a(z_init);
+        *growth = cosmo.growth_factor(a);
+        *rate = cosmo.growth_rate(a);
+        *hubble = cosmo.hubble_parameter_a(a);
+        return 0;
+    } catch (const std::exception&) {
+        return 1;
+    }
+}
+
 // initial_conditions_utils::generate_random_particles (initial_conditions.cpp:800-821)
 int ref_random_particles(size_t n, float box, uint32_t seed, float* pos3, float* vel3, float* mass) {
     std::vector<float3> p, v; std::vector<float> m;

@@ -22,9 +22,25 @@ from inputs import masses_np, uniform_mt, uniform_np, clustered_np  # noqa: E402
 from oracle.pyoracle import Ref, build  # noqa: E402
 
 
+def ic_scalars(r):
+    """Normalised P(k) and (D, f, H)(a_init) of the reference's IC generator / CosmologyModel."""
+    k = np.exp(np.linspace(np.log(0.005), np.log(20.0), 48))
+    out = {"k": k}
+    for z in (49.0, 9.0, 0.0):
+        pk, d, f, h = r.ic_scalars(k, z)
+        out[f"pk_z{int(z)}"] = pk
+        out[f"dfh_z{int(z)}"] = np.array([d, f, h])
+    np.savez_compressed(os.path.join(HERE, "ic_scalars.npz"), **out)
+
+
 def main():
     build(ref=True)
     r = Ref()
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "ic":
+        ic_scalars(r)
+        print("wrote ic_scalars.npz")
+        return
+    ic_scalars(r)
     out = {}
 
     # D1: the reference's only CPU direct sum (one root leaf), unit masses

@@ -1,0 +1,72 @@
+"""-m gpu: Zel'dovich initial conditions on the device (b200_zeldovich_ics_dev)
+against the numpy restatement oracle/ics_np.py (same hash RNG, numpy FFT in double)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ics_np
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(engine, grid, n=None, **kw):
+    n = grid ** 3 if n is None else n
+    posm = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    vel = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    stats = engine.zeldovich_ics_dev(posm, vel, n_particles=n, grid=grid, **kw)
+    torch.cuda.synchronize()
+    return posm.cpu().numpy(), vel.cpu().numpy(), stats
+
+
+@pytest.mark.parametrize("grid,n,shift,seed,z", [(32, None, 0.0, 12345, 49.0), (64, 4096, 50.0, 7, 9.0),
+                                                  (16, 4096, 50.0, 1, 49.0), (48, 1000, 0.0, 99, 24.0)])
+def test_zeldovich_vs_numpy(engine, grid, n, shift, seed, z):
+    posm, vel, stats = _run(engine, grid, n, seed=seed, z_initial=z, origin_shift=shift)
+    pos0, vel0, (rms0, D0, vfac0) = ics_np.zeldovich(grid, 100.0, z, seed, n, shift)
+    box = 100.0
+    d = np.abs(posm[:, :3] - pos0)
+    d = np.minimum(d, box - d)                      # a particle a float ulp from the wrap may land on either side
+    # float FFT (cuFFT) vs double FFT: displacements agree to ~1e-6 of their r.m.s.
+    assert d.max() < 2e-5 * box * max(D0 / 0.02, 1.0)
+    assert np.abs(vel - vel0).max() < 2e-4 * np.abs(vel0).max()
+    assert np.all(posm[:, 3] == 1.0)
+    assert posm[:, :3].min() >= -shift and posm[:, :3].max() < box - shift
+    assert abs(stats[0] / rms0 - 1.0) < 1e-4 and abs(stats[2] / D0 - 1.0) < 1e-12 and abs(stats[3] / vfac0 - 1.0) < 1e-12
+    assert stats[1] >= stats[0]
+
+
+def test_zeldovich_is_deterministic_and_seeded(engine):
+    a, va, _ = _run(engine, 32, seed=5)
+    b, vb, _ = _run(engine, 32, seed=5)
+    c, _, _ = _run(engine, 32, seed=6)
+    assert np.array_equal(a, b) and np.array_equal(va, vb)
+    assert not np.array_equal(a, c)
+
+
+def test_zeldovich_feeds_the_tree(engine, oracle):
+    """The generated particles go straight into the Barnes-Hut path (device-resident), and the result
+    equals the CPU walk on the same particles."""
+    n = 32 ** 3
+    posm = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    vel = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    engine.zeldovich_ics_dev(posm, vel, grid=32, origin_shift=50.0)
+    engine.tree_build_dev(posm, n, 100.0, 8, 20)
+    acc = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    engine.tree_walk_dev(acc, 0, n, theta=0.5)
+    torch.cuda.synchronize()
+    h = posm.cpu().numpy()
+    t = oracle.tree_build(h[:, :3].copy(), h[:, 3].copy())
+    want = oracle.tree_forces(t, h[:, :3].copy(), 0.5)
+    got = acc.cpu().numpy()
+    assert np.sqrt(((got - want) ** 2).sum() / (want ** 2).sum()) < 1e-3
+
+
+def test_zeldovich_rejects_bad_parameters(engine):
+    import b200grav
+    posm = torch.empty((64, 4), dtype=torch.float32, device="cuda")
+    vel = torch.empty((64, 3), dtype=torch.float32, device="cuda")
+    for kw in (dict(grid=3), dict(grid=15), dict(grid=4, box=-1.0), dict(grid=4, sigma_8=0.0)):
+        with pytest.raises(b200grav.B200Error):
+            engine.zeldovich_ics_dev(posm, vel, n_particles=64, **kw)
+    with pytest.raises(b200grav.B200Error):
+        engine.zeldovich_ics_dev(posm, vel, n_particles=65, grid=4)      # more particles than grid points
