@@ -99,31 +99,58 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------- CPU baseline
+TREE_SAMPLE = 65536          # particles per single-threaded reference tree evaluation (~1 s per core)
+DIRECT_SAMPLE = 16384
+
+
 def _ref_worker(args):
-    kind, n, seed, reps = args
+    workload, kind, n, seed, reps = args
     sys.path.insert(0, ROOT)
     from oracle.pyoracle import Oracle, Ref
-    pos, _ = make_particles(n, seed)
-    t0 = time.perf_counter()
-    if kind == "reference":
-        r = Ref()
-        for _ in range(reps):
-            r.direct(pos)                      # TreeForceComputer, one root leaf: the CPU direct sum
-    else:
+    pos, mass = make_particles(n, seed)
+    if kind != "reference":
         os.environ["OMP_NUM_THREADS"] = "1"
-        o = Oracle()
-        for _ in range(reps):
-            o.direct_f32(pos, None, eps=EPS)
+    t0 = time.perf_counter()
+    if workload == "direct":
+        if kind == "reference":
+            r = Ref()
+            for _ in range(reps):
+                r.direct(pos)                  # TreeForceComputer, one root leaf: the CPU direct sum
+        else:
+            o = Oracle()
+            for _ in range(reps):
+                o.direct_f32(pos, None, eps=EPS)
+    else:
+        if kind == "reference":
+            r = Ref()
+            for _ in range(reps):
+                r.tree_forces(pos, mass, 0.5, 8, 20, 100.0)      # TreeForceComputer::compute_forces: build + walk
+        else:
+            o = Oracle()
+            for _ in range(reps):
+                o.tree_forces(o.tree_build(pos, mass), pos, 0.5)
     return time.perf_counter() - t0
 
 
-def cpu_reference_batch(cores, n_sample, reps, pool, kind):
-    """One bounded batch: every core runs the reference's single-threaded CPU direct
-    sum on its own n_sample-particle subsample.  Returns (interactions, seconds)."""
+def _tree_sample_interactions(n_sample):
+    """Cell + pair interactions of ONE reference tree evaluation of an n_sample uniform set (counted
+    once, untimed, by the restated oracle whose counters equal the reference walk's by construction)."""
+    from oracle.pyoracle import Oracle
+    o = Oracle()
+    pos, mass = make_particles(n_sample, 1000)
+    _, cnt = o.tree_forces(o.tree_build(pos, mass), pos, 0.5, counters=True)
+    return float(cnt[1] + cnt[2])
+
+
+def cpu_reference_batch(cores, n_sample, reps, pool, kind, workload="direct", per_eval=None):
+    """One bounded batch: every core runs the reference's single-threaded CPU path on its own
+    n_sample-particle subsample.  Returns (interactions, seconds)."""
     t0 = time.perf_counter()
-    list(pool.map(_ref_worker, [(kind, n_sample, 1000 + c, reps) for c in range(cores)]))
+    list(pool.map(_ref_worker, [(workload, kind, n_sample, 1000 + c, reps) for c in range(cores)]))
     dt = time.perf_counter() - t0
-    return cores * reps * float(n_sample) * float(n_sample), dt
+    if per_eval is None:
+        per_eval = float(n_sample) * float(n_sample)
+    return cores * reps * per_eval, dt
 
 
 def cpu_kind():
@@ -131,21 +158,28 @@ def cpu_kind():
     return "reference" if Ref.available() else "port"
 
 
-def run_cpu_baseline(target_seconds=12.0):
+def _cpu_sample(workload):
+    if workload == "direct":
+        return DIRECT_SAMPLE, None, ("the reference CPU direct sum (TreeForceComputer, leaf_capacity>N => leaf "
+                                     "pair loop)")
+    return TREE_SAMPLE, _tree_sample_interactions(TREE_SAMPLE), ("the reference CPU TreeForceComputer "
+                                                                 "(theta 0.5, leaf 8: build + walk)")
+
+
+def run_cpu_baseline(workload="direct", target_seconds=12.0):
     from concurrent.futures import ProcessPoolExecutor
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     kind = cpu_kind()
-    n_sample = 16384
+    n_sample, per_eval, what = _cpu_sample(workload)
     with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("spawn")) as pool:
-        cpu_reference_batch(cores, 2048, 1, pool, kind)                   # warm: spawn workers, page in
-        inter, dt = cpu_reference_batch(cores, n_sample, 1, pool, kind)   # calibrate on the real sample size
+        cpu_reference_batch(cores, 2048, 1, pool, kind, workload)                   # warm: spawn workers, page in
+        inter, dt = cpu_reference_batch(cores, n_sample, 1, pool, kind, workload, per_eval)   # calibrate
         reps = max(1, int(round(target_seconds / dt)))
-        inter, dt = cpu_reference_batch(cores, n_sample, reps, pool, kind)
+        inter, dt = cpu_reference_batch(cores, n_sample, reps, pool, kind, workload, per_eval)
     return {"value": inter / dt, "unit": "interactions/s", "cores": cores, "kind": kind,
-            "sample": f"{cores} independent single-threaded instances of the reference CPU direct sum "
-                      f"(TreeForceComputer, leaf_capacity>N => leaf pair loop), {n_sample} particles each x {reps} "
-                      f"evaluations; {inter:.3e} interactions in {dt:.1f} s"}
+            "sample": f"{cores} independent single-threaded instances of {what}, {n_sample} uniform particles each x "
+                      f"{reps} evaluations; {inter:.3e} interactions in {dt:.1f} s"}
 
 
 def bench_reference(args):
@@ -157,20 +191,23 @@ def bench_reference(args):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     kind = cpu_kind()
-    n_sample, reps = 16384, 1
+    n_sample, per_eval, what = _cpu_sample(args.workload)
+    reps = 1
     times, inter = [], 0.0
     with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("spawn")) as pool:
-        cpu_reference_batch(cores, 2048, 1, pool, kind)
+        cpu_reference_batch(cores, 2048, 1, pool, kind, args.workload)
         for _ in range(args.warmup):
-            cpu_reference_batch(cores, n_sample, reps, pool, kind)
+            cpu_reference_batch(cores, n_sample, reps, pool, kind, args.workload, per_eval)
         for _ in range(args.steps):
-            inter, dt = cpu_reference_batch(cores, n_sample, reps, pool, kind)
+            inter, dt = cpu_reference_batch(cores, n_sample, reps, pool, kind, args.workload, per_eval)
             times.append(dt)
     total = sum(times)
     value = inter * args.steps / total
-    sample = (f"each step = {cores} independent single-threaded instances of the reference CPU direct sum, "
-              f"{n_sample} particles each ({inter:.3e} interactions/step); rate is per-interaction so it "
-              f"transfers to the 2^20 workload")
+    sample = (f"each step = {cores} independent single-threaded instances of {what}, "
+              f"{n_sample} uniform particles each ({inter:.3e} interactions/step); the rate is per interaction, "
+              f"so it transfers to the {args.particles}-particle workload" +
+              ("" if args.workload == "direct" else " (a larger tree does more interactions per particle, "
+                                                    "at the same cost per interaction)"))
     line = {"impl": "reference", "metric": "pairwise_interactions_per_s", "value": value, "unit": "interactions/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -178,11 +215,28 @@ def bench_reference(args):
             "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if args.workload == "tree":
+        line["particle_steps_per_s"] = cores * reps * n_sample * args.steps / total
     print(json.dumps(line))
+
+
+def zeldovich_grid(n):
+    """Power-of-two grid with at least n points: 128 for 2^20 (stride-2 subsample of the
+    grid, grid_to_particles), 256 for 2^24 (the first n grid points)."""
+    g = 4
+    while g ** 3 < n:
+        g *= 2
+    return g
 
 
 def workload_config(args):
     cfg = _workload_config(args)
+    if getattr(args, "ic", "uniform") == "zeldovich":
+        cfg["workload"] = cfg["workload"].replace(
+            "uniform [-50,50)^3",
+            f"Zel'dovich ICs (b200_zeldovich_ics_dev: {zeldovich_grid(args.particles)}^3 grid, 100 Mpc/h box, "
+            f"z = {args.z_initial:g}, seed 12345, sigma_8 0.81, origin-centred)")
+        cfg["ic"] = "zeldovich"
     if getattr(args, "kdk", False):
         cfg["workload"] += "; each step = full KDK leapfrog step (omega_m 0.31, omega_lambda 0.69, h 0.67, a0 1, dt 1e-4)"
     return cfg
@@ -221,11 +275,23 @@ def bench_gpu(args):
     eng = b200grav.Engine(local)
 
     n = args.particles
-    pos, mass = make_particles(n)
     lo, hi = rank * n // world, (rank + 1) * n // world
     nl = hi - lo
-    posm_host = np.ascontiguousarray(np.concatenate([pos, mass[:, None]], 1), np.float32)
-    posm = torch.from_numpy(posm_host).to(dev)             # full source set, resident in HBM
+    if args.ic == "zeldovich":
+        # generated on the device by the engine's own IC step (b200_zeldovich_ics_dev): every rank
+        # produces the same replicated particle set (counter-based RNG), origin-centred convention
+        posm = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        vel_ic = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        ic_stats = eng.zeldovich_ics_dev(posm, vel_ic, n_particles=n, grid=zeldovich_grid(n), box=100.0,
+                                         z_initial=args.z_initial, seed=12345, origin_shift=50.0)
+        del vel_ic
+        torch.cuda.synchronize()
+        posm_host = posm.cpu().numpy()
+        pos, mass = np.ascontiguousarray(posm_host[:, :3]), np.ascontiguousarray(posm_host[:, 3])
+    else:
+        pos, mass = make_particles(n)
+        posm_host = np.ascontiguousarray(np.concatenate([pos, mass[:, None]], 1), np.float32)
+        posm = torch.from_numpy(posm_host).to(dev)             # full source set, resident in HBM
     shard = posm[lo:hi].clone() if world > 1 else posm     # this rank's particles (all-gather input)
     acc = torch.zeros((nl, 3), dtype=torch.float32, device=dev)
     vel = torch.zeros((nl, 3), dtype=torch.float32, device=dev)
@@ -418,7 +484,8 @@ def bench_gpu(args):
                 src = "fallback 6532.2 GB/s (MEASURED_PEAKS.json not on this box)"
             gbs = tree_bytes / kern_s / 1e9
             line["roofline"] = {
-                "bound": "hbm", "kernel": "walk_kernel (stackless theta walk, one thread per Morton-ordered target)",
+                "bound": "hbm", "kernel": "walk_warp_kernel (stackless theta walk; a warp walks the union of the "
+                                          "traversals of 32 Morton-adjacent targets, per-lane accept test)",
                 "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": traffic,
                 "peak_source": src,
                 "note": "algorithmic bytes = 32 B x nodes visited + 16 B x leaf-pair sources + 28 B x targets; most of it "
@@ -428,7 +495,7 @@ def bench_gpu(args):
                 "interactions_per_s_walk_only": per_launch / kern_s,
             }
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = run_cpu_baseline()
+            line["cpu_baseline"] = run_cpu_baseline(args.workload)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -446,6 +513,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="direct", choices=["direct", "tree"])
     ap.add_argument("--particles", type=int, default=1 << 20)
+    ap.add_argument("--ic", default="uniform", choices=["uniform", "zeldovich"],
+                    help="synthetic inputs: uniform random (default) or Zel'dovich initial conditions generated on "
+                         "the device")
+    ap.add_argument("--z-initial", type=float, default=49.0, help="redshift of the Zel'dovich ICs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--sources", default="allgather", choices=["allgather", "peer"],
                     help="N>1 direct sum: NCCL all-gather of the shards (default) or peer-mapped source tiles "
