@@ -433,11 +433,13 @@ def bench_gpu(args):
         tree_bytes = 32.0 * float(cnt[0]) + 16.0 * float(cnt[2]) + 28.0 * nl
         tree_counts = [int(x) for x in cnt]
 
-    traffic = None
+    traffic = l2_bytes = l1_bytes = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        if world == 1:
+        if world == 1 and args.ic == "uniform":
             traffic = tr.get(args.workload, {}).get(str(n))
+            l2_bytes = tr.get(args.workload + "_l2_bytes", {}).get(str(n))
+            l1_bytes = tr.get(args.workload + "_l1_bytes", {}).get(str(n))
     except Exception:
         pass
 
@@ -490,7 +492,12 @@ def bench_gpu(args):
                 "peak_source": src,
                 "note": "algorithmic bytes = 32 B x nodes visited + 16 B x leaf-pair sources + 28 B x targets; most of it "
                         "is served by L1/L2 (a warp's 32 Morton-adjacent targets visit nearly the same nodes), so this is "
-                        "an L2/L1 figure quoted against the HBM peak, see profiles/ for dram__bytes and lts__t_bytes",
+                        "an L1/L2 figure quoted against the HBM peak and can exceed it; the ncu capture of the same launch (traffic = DRAM "
+                        "bytes, ncu_l2_bytes, ncu_l1_bytes; profiles/r1_walk_warp_kernel_ncu_full.txt) shows a kernel bound by "
+                        "instruction issue (73 % of issue slots, l1tex 60 %), not by any memory level",
+                "ncu_l2_bytes": l2_bytes, "ncu_l1_bytes": l1_bytes,
+                "ncu_l2_gbs": (l2_bytes / kern_s / 1e9) if l2_bytes else None,
+                "ncu_l1_gbs": (l1_bytes / kern_s / 1e9) if l1_bytes else None,
                 "walk_counters_nodes_cells_pairs": tree_counts, "kernel_ms": 1e3 * kern_s,
                 "interactions_per_s_walk_only": per_launch / kern_s,
             }

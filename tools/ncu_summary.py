@@ -27,6 +27,8 @@ KEYS = [
     "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sectors.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
     "l1tex__t_bytes.sum", "l1tex__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
