@@ -50,6 +50,39 @@ __global__ void morton_kernel(const float4* __restrict__ posm, long long n, floa
     keys[i] = morton3d(x, y, z);
 }
 
+// Hilbert-curve keys on the same 1024^3 lattice (Skilling's transpose algorithm, then bit
+// interleave).  Internal use only: the ORDER in which the walk groups targets into warps.
+// A Hilbert curve has no jumps, so 32 consecutive targets form a more compact set than 32
+// consecutive Morton keys do, and the union of their traversals is smaller.  The lattice is
+// centred so that the origin-centred root cube [-box/2, box/2) maps onto it without wrapping.
+__global__ void hilbert_kernel(const float4* __restrict__ posm, long long n, float box,
+                               uint32_t* __restrict__ keys) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = posm[i];
+    const float s = 1024.0f / box;
+    uint32_t X[3];
+    X[0] = (uint32_t)fminf(fmaxf(p.x * s + 512.0f, 0.0f), 1023.0f);
+    X[1] = (uint32_t)fminf(fmaxf(p.y * s + 512.0f, 0.0f), 1023.0f);
+    X[2] = (uint32_t)fminf(fmaxf(p.z * s + 512.0f, 0.0f), 1023.0f);
+    const uint32_t M = 1u << 9;
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {              // inverse undo
+        const uint32_t P = Q - 1;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (X[d] & Q) X[0] ^= P;
+            else { const uint32_t t = (X[0] ^ X[d]) & P; X[0] ^= t; X[d] ^= t; }
+        }
+    }
+    X[1] ^= X[0];                                       // Gray encode
+    X[2] ^= X[1];
+    uint32_t t = 0;
+    for (uint32_t Q = M; Q > 1; Q >>= 1)
+        if (X[2] & Q) t ^= Q - 1;
+    X[0] ^= t; X[1] ^= t; X[2] ^= t;
+    keys[i] = expand_bits(X[0]) * 4 + expand_bits(X[1]) * 2 + expand_bits(X[2]);
+}
+
 // warp w of the CTA owns keys [tile*RS_TILE + w*512, +512), 16 rows of 32: the
 // (warp, row, lane) order is the key order, which is what makes ranks stable.
 __device__ __forceinline__ long long item_index(long long tile, int warp, int row, int lane) {
@@ -194,6 +227,17 @@ int morton_keys(b200_ctx* ctx, const void* posm4, size_t n, float box, uint32_t*
     if (n == 0) return B200_OK;
     if (!(box > 0.f)) return B200_ERR_INVALID;
     morton_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float4*)posm4, (long long)n,
+                                                               box, keys);
+    B200_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return B200_OK;
+}
+
+int hilbert_keys(b200_ctx* ctx, const void* posm4, size_t n, float box, uint32_t* keys,
+                cudaStream_t st) {
+    if (n == 0) return B200_OK;
+    if (!(box > 0.f)) return B200_ERR_INVALID;
+    hilbert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float4*)posm4, (long long)n,
                                                                box, keys);
     B200_CUDA(cudaGetLastError());
     ctx->launches += 1;

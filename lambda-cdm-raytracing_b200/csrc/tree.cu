@@ -890,7 +890,12 @@ static int tree_target_order(b200_ctx* ctx, TreeState* T, size_t i0, size_t n_ta
     B200_TRY(T->keys_sorted.reserve(n_targets * sizeof(uint32_t)));
     B200_TRY(T->order.reserve(n_targets * sizeof(int)));
     B200_TRY(T->sort_scratch.reserve(sort_scratch_bytes(n_targets)));
-    B200_TRY(morton_keys(ctx, T->posm + i0, n_targets, T->box, T->keys.as<uint32_t>(), st));
+    // warp grouping of the targets: Hilbert order (B200_WALK_ORDER=morton: the 30-bit Morton keys of row T1)
+    const char* ord = getenv("B200_WALK_ORDER");
+    if (ord && ord[0] == 'm')
+        B200_TRY(morton_keys(ctx, T->posm + i0, n_targets, T->box, T->keys.as<uint32_t>(), st));
+    else
+        B200_TRY(hilbert_keys(ctx, T->posm + i0, n_targets, T->box, T->keys.as<uint32_t>(), st));
     B200_TRY(sort_pairs(ctx, T->keys.as<uint32_t>(), n_targets, T->keys_sorted.as<uint32_t>(),
                         T->order.as<int>(), 30, T->sort_scratch.p, st));
     if (i0) {
