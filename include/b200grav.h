@@ -149,6 +149,23 @@ int b200_tree_forces_host(b200_ctx* ctx, const float* pos3, const float* mass,
                           float* acc3, size_t n, float theta, int leaf_cap,
                           int max_depth, float box);
 
+/* "Fixed physics" Barnes-Hut -- NOT the reference's tree.  The CPU
+ * TreeForceComputer keeps the first leaf_cap particles of a node where they are when it splits
+ * (src/forces/tree_force_computer.cpp:144-171; ~30 % of the mass never becomes a source), sums leaf
+ * pairs with unit masses (:253, :340), centres its root cube on the origin whatever the data
+ * (:132-133) and hard-codes eps = 0.01 (:281, :334): at theta = 0.5 its force is 0.3 (relative L2)
+ * away from the direct sum.  This mode keeps the octant rule, the child geometry, the centre-of-mass
+ * pass and the opening criterion, and removes those four: splitting nodes pass every particle on,
+ * leaf pairs use the sources' masses, the root cube is fitted to the data (centre = bounding-box
+ * midpoint, edge = largest extent * 1.00001), eps is a parameter.  Same kernels, same walk
+ * (b200_tree_walk_dev / _stats / _export / _counters apply).  Checked against the FP64 direct
+ * sum: 1.3e-3 relative L2 at theta = 0.5, 7e-5 at theta = 0.2 (uniform, leaf_cap 8). */
+int b200_tree_build_fixed_dev(b200_ctx* ctx, const void* posm4, size_t n, int leaf_cap,
+                              int max_depth, float eps, void* stream);
+int b200_tree_forces_fixed_host(b200_ctx* ctx, const float* pos3, const float* mass /* NULL = 1 */,
+                                float* acc3, size_t n, float theta, int leaf_cap, int max_depth,
+                                float eps);
+
 /* Tree introspection (TreeForceComputer::get_node_count / get_leaf_count /
  * get_tree_depth, src/forces/tree_force_computer.cpp:410-464) and a canonical
  * breadth-first export for the bit-exact topology check.  Sizes first, then

@@ -246,7 +246,39 @@ int b200_tree_build_dev(b200_ctx* ctx, const void* posm4, size_t n, float box, i
                         int max_depth, void* stream) {
     if (!ctx) return B200_ERR_INVALID;
     B200_CUDA(cudaSetDevice(ctx->device));
-    return tree_build(ctx, posm4, n, box, leaf_cap, max_depth, pick_stream(ctx, stream));
+    return tree_build(ctx, posm4, n, box, leaf_cap, max_depth, false, 0.01f, pick_stream(ctx, stream));
+}
+
+int b200_tree_build_fixed_dev(b200_ctx* ctx, const void* posm4, size_t n, int leaf_cap, int max_depth,
+                              float eps, void* stream) {
+    if (!ctx) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return tree_build(ctx, posm4, n, 0.f, leaf_cap, max_depth, true, eps, pick_stream(ctx, stream));
+}
+
+int b200_tree_forces_fixed_host(b200_ctx* ctx, const float* pos3, const float* mass, float* acc3, size_t n,
+                                float theta, int leaf_cap, int max_depth, float eps) {
+    if (!ctx) return B200_ERR_INVALID;
+    if (n == 0) return B200_OK;
+    if (!pos3 || !acc3) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    B200_TRY(ctx->h_pos3.reserve(n * 3 * sizeof(float)));
+    B200_TRY(ctx->h_posm4.reserve(n * 4 * sizeof(float)));
+    B200_TRY(ctx->h_acc3.reserve(n * 3 * sizeof(float)));
+    B200_CUDA(cudaMemcpyAsync(ctx->h_pos3.p, pos3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    const float* d_mass = nullptr;
+    if (mass) {
+        B200_TRY(ctx->h_mass.reserve(n * sizeof(float)));
+        B200_CUDA(cudaMemcpyAsync(ctx->h_mass.p, mass, n * sizeof(float), cudaMemcpyHostToDevice, st));
+        d_mass = ctx->h_mass.as<float>();
+    }
+    B200_TRY(pack_posm(ctx, ctx->h_pos3.p, d_mass, n, ctx->h_posm4.p, st));
+    B200_TRY(tree_build(ctx, ctx->h_posm4.p, n, 0.f, leaf_cap, max_depth, true, eps, st));
+    B200_TRY(tree_walk(ctx, 0, n, theta, ctx->h_acc3.p, st));
+    B200_CUDA(cudaMemcpyAsync(acc3, ctx->h_acc3.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
 }
 
 int b200_tree_walk_dev(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* acc3,
@@ -270,7 +302,7 @@ int b200_tree_forces_host(b200_ctx* ctx, const float* pos3, const float* mass, f
     B200_CUDA(cudaMemcpyAsync(ctx->h_pos3.p, pos3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaMemcpyAsync(ctx->h_mass.p, mass, n * sizeof(float), cudaMemcpyHostToDevice, st));
     B200_TRY(pack_posm(ctx, ctx->h_pos3.p, ctx->h_mass.p, n, ctx->h_posm4.p, st));
-    B200_TRY(tree_build(ctx, ctx->h_posm4.p, n, box, leaf_cap, max_depth, st));
+    B200_TRY(tree_build(ctx, ctx->h_posm4.p, n, box, leaf_cap, max_depth, false, 0.01f, st));
     B200_TRY(tree_walk(ctx, 0, n, theta, ctx->h_acc3.p, st));
     B200_CUDA(cudaMemcpyAsync(acc3, ctx->h_acc3.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));

@@ -55,16 +55,19 @@ __global__ void morton_kernel(const float4* __restrict__ posm, long long n, floa
 // A Hilbert curve has no jumps, so 32 consecutive targets form a more compact set than 32
 // consecutive Morton keys do, and the union of their traversals is smaller.  The lattice is
 // centred so that the origin-centred root cube [-box/2, box/2) maps onto it without wrapping.
+// root_dev (nullable): device float[4] = cube centre and edge (the fixed tree's data-fitted root).
 __global__ void hilbert_kernel(const float4* __restrict__ posm, long long n, float box,
-                               uint32_t* __restrict__ keys) {
+                               const float* __restrict__ root_dev, uint32_t* __restrict__ keys) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 p = posm[i];
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (root_dev) { cx = root_dev[0]; cy = root_dev[1]; cz = root_dev[2]; box = root_dev[3]; }
     const float s = 1024.0f / box;
     uint32_t X[3];
-    X[0] = (uint32_t)fminf(fmaxf(p.x * s + 512.0f, 0.0f), 1023.0f);
-    X[1] = (uint32_t)fminf(fmaxf(p.y * s + 512.0f, 0.0f), 1023.0f);
-    X[2] = (uint32_t)fminf(fmaxf(p.z * s + 512.0f, 0.0f), 1023.0f);
+    X[0] = (uint32_t)fminf(fmaxf((p.x - cx) * s + 512.0f, 0.0f), 1023.0f);
+    X[1] = (uint32_t)fminf(fmaxf((p.y - cy) * s + 512.0f, 0.0f), 1023.0f);
+    X[2] = (uint32_t)fminf(fmaxf((p.z - cz) * s + 512.0f, 0.0f), 1023.0f);
     const uint32_t M = 1u << 9;
     for (uint32_t Q = M; Q > 1; Q >>= 1) {              // inverse undo
         const uint32_t P = Q - 1;
@@ -233,12 +236,12 @@ int morton_keys(b200_ctx* ctx, const void* posm4, size_t n, float box, uint32_t*
     return B200_OK;
 }
 
-int hilbert_keys(b200_ctx* ctx, const void* posm4, size_t n, float box, uint32_t* keys,
-                cudaStream_t st) {
+int hilbert_keys(b200_ctx* ctx, const void* posm4, size_t n, float box, const float* root_dev,
+                 uint32_t* keys, cudaStream_t st) {
     if (n == 0) return B200_OK;
-    if (!(box > 0.f)) return B200_ERR_INVALID;
+    if (!root_dev && !(box > 0.f)) return B200_ERR_INVALID;
     hilbert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float4*)posm4, (long long)n,
-                                                               box, keys);
+                                                               box, root_dev, keys);
     B200_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return B200_OK;

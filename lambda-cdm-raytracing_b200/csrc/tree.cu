@@ -53,6 +53,8 @@ struct TreeGlobals {
     int error;                  // 1 = node table overflow
     int stored_total;
     unsigned long long counters[3];
+    int bbox[6];                // fixed mode: order-preserving int codes of min x,y,z / max x,y,z
+    float root[4];              // fixed mode: root cube centre and edge
 };
 
 struct TreeState {
@@ -63,6 +65,8 @@ struct TreeState {
     size_t max_nodes = 0, max_split = 0, max_tiles = 0, max_node_tiles = 0;
     bool built = false;
     bool counting = false;
+    bool fixed = false;          // "fixed physics" tree: no orphans, data-fitted root, real leaf masses
+    float eps = 0.01f;           // softening of the walk (0.01f literal in the faithful mode)
     DevBuf center, com, meta, nstart, ncount, nsplit_rank;
     DevBuf ent_idx[2], ent_node[2], digit;
     DevBuf part_idx, part_pos;
@@ -95,8 +99,51 @@ constexpr int NODE_TILE = 2048;                        // nodes per scan tile (2
 constexpr unsigned FULL = 0xffffffffu;
 
 // ------------------------------------------------------------------ init ---
+// Fixed mode: bounding box of the particles -> root cube (centre = midpoint, edge = largest
+// extent * 1.00001f; 1 when all particles coincide), one rounding per operation.
+__device__ __forceinline__ int float_code(float f) {        // order-preserving float -> int
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float code_float(int c) { return __int_as_float(c >= 0 ? c : c ^ 0x7fffffff); }
+
+__global__ void bbox_init_kernel(TreeGlobals* g) {
+    if (threadIdx.x < 3) { g->bbox[threadIdx.x] = 0x7fffffff; g->bbox[3 + threadIdx.x] = (int)0x80000000; }
+}
+__global__ void __launch_bounds__(256)
+bbox_kernel(const float4* __restrict__ posm, int n, TreeGlobals* g) {
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = posm[i];
+        lo[0] = fminf(lo[0], p.x); hi[0] = fmaxf(hi[0], p.x);
+        lo[1] = fminf(lo[1], p.y); hi[1] = fmaxf(hi[1], p.y);
+        lo[2] = fminf(lo[2], p.z); hi[2] = fmaxf(hi[2], p.z);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(FULL, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(FULL, hi[k], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&g->bbox[k], float_code(lo[k]));
+            atomicMax(&g->bbox[3 + k], float_code(hi[k]));
+        }
+    }
+}
+__global__ void root_cube_kernel(TreeGlobals* g) {
+    float ext = 0.0f;
+    for (int k = 0; k < 3; ++k) {
+        const float lo = code_float(g->bbox[k]), hi = code_float(g->bbox[3 + k]);
+        g->root[k] = __fmul_rn(__fadd_rn(lo, hi), 0.5f);
+        ext = fmaxf(ext, __fsub_rn(hi, lo));
+    }
+    g->root[3] = ext > 0.0f ? __fmul_rn(ext, 1.00001f) : 1.0f;
+}
+
 __global__ void tree_init_kernel(TreeGlobals* g, float4* center, float4* com, int4* meta, int* nstart,
-                                 int* ncount, int* ent_idx, int* ent_node, int n, float box) {
+                                 int* ncount, int* ent_idx, int* ent_node, int n, float box, int fixed) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         for (int l = 0; l < MAX_LEVELS + 2; ++l) {
@@ -109,7 +156,8 @@ __global__ void tree_init_kernel(TreeGlobals* g, float4* center, float4* com, in
         g->error = 0;
         g->stored_total = 0;
         g->counters[0] = g->counters[1] = g->counters[2] = 0;
-        center[0] = make_float4(0.f, 0.f, 0.f, box);     // tree_force_computer.cpp:132-133
+        center[0] = fixed ? make_float4(g->root[0], g->root[1], g->root[2], g->root[3])
+                          : make_float4(0.f, 0.f, 0.f, box);     // tree_force_computer.cpp:132-133
         com[0] = make_float4(0.f, 0.f, 0.f, 0.f);
         meta[0] = make_int4(-1, -1, 0, 0);
         nstart[0] = 0;
@@ -123,9 +171,10 @@ __global__ void tree_init_kernel(TreeGlobals* g, float4* center, float4* com, in
 
 // ----------------------------------------------------- K1: classify nodes ---
 // value per node: (split ? 1 : 0) << 40 | stored particles (leaf members or orphans)
-__device__ __forceinline__ u64 node_value(int count, int cap, bool may_split) {
+// keep = arrivals a splitting node retains: cap in the reference's tree (orphans), 0 in the fixed tree
+__device__ __forceinline__ u64 node_value(int count, int cap, bool may_split, int keep) {
     const bool split = may_split && count > cap;
-    return split ? ((1ull << 40) | (u64)cap) : (u64)count;
+    return split ? ((1ull << 40) | (u64)keep) : (u64)count;
 }
 
 __device__ __forceinline__ u64 block_reduce_u64(u64 v, u64* sh /* >= 8 */) {
@@ -141,7 +190,7 @@ __device__ __forceinline__ u64 block_reduce_u64(u64 v, u64* sh /* >= 8 */) {
 }
 
 __global__ void __launch_bounds__(256)
-node_reduce_kernel(const TreeGlobals* __restrict__ g, int level, int cap, int max_depth,
+node_reduce_kernel(const TreeGlobals* __restrict__ g, int level, int cap, int keep, int max_depth,
                    const int* __restrict__ ncount, u64* __restrict__ tile_sum) {
     __shared__ u64 sh[8];
     const LevelInfo L = g->lv[level];
@@ -153,7 +202,7 @@ node_reduce_kernel(const TreeGlobals* __restrict__ g, int level, int cap, int ma
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             int k = tile * NODE_TILE + threadIdx.x * 8 + j;
-            if (k < n_nodes) v += node_value(ncount[L.node_begin + k], cap, may_split);
+            if (k < n_nodes) v += node_value(ncount[L.node_begin + k], cap, may_split, keep);
         }
         u64 t = block_reduce_u64(v, sh);
         if (threadIdx.x == 0) tile_sum[tile] = t;
@@ -216,7 +265,7 @@ node_scan_kernel(TreeGlobals* __restrict__ g, int level, u64* __restrict__ tile_
 }
 
 __global__ void __launch_bounds__(256)
-node_apply_kernel(const TreeGlobals* __restrict__ g, int level, int cap, int max_depth,
+node_apply_kernel(const TreeGlobals* __restrict__ g, int level, int cap, int keep, int max_depth,
                   const int* __restrict__ ncount, const u64* __restrict__ tile_sum,
                   int4* __restrict__ meta, int* __restrict__ nsplit_rank, int* __restrict__ split_node) {
     __shared__ u64 wsum[8];
@@ -231,7 +280,7 @@ node_apply_kernel(const TreeGlobals* __restrict__ g, int level, int cap, int max
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             int k = tile * NODE_TILE + threadIdx.x * 8 + j;
-            v[j] = (k < n_nodes) ? node_value(ncount[L.node_begin + k], cap, may_split) : 0ull;
+            v[j] = (k < n_nodes) ? node_value(ncount[L.node_begin + k], cap, may_split, keep) : 0ull;
             tsum += v[j];
         }
         u64 x = tsum;
@@ -277,7 +326,7 @@ __device__ __forceinline__ unsigned digit_mask(unsigned bv, unsigned b0, unsigne
 }
 
 __global__ void __launch_bounds__(ET_THREADS)
-entry_digit_kernel(const TreeGlobals* __restrict__ g, int level, int cap,
+entry_digit_kernel(const TreeGlobals* __restrict__ g, int level, int keep,
                    const float4* __restrict__ posm, const float4* __restrict__ center,
                    const int4* __restrict__ meta, const int* __restrict__ nstart,
                    const int* __restrict__ nsplit_rank, const int* __restrict__ ent_idx,
@@ -303,13 +352,13 @@ entry_digit_kernel(const TreeGlobals* __restrict__ g, int level, int cap,
                 const int k = ent_node[p];
                 const int4 m = meta[k];
                 const int rel = p - nstart[k];
-                if (m.x < 0 || rel < cap) {
+                if (m.x < 0 || rel < keep) {
                     part_idx[m.z + rel] = idx;          // leaf member, or orphan of a split node
                 } else {
                     const float4 c = center[k];
                     const float4 x = posm[idx];
                     d = (x.x > c.x ? 1 : 0) | (x.y > c.y ? 2 : 0) | (x.z > c.z ? 4 : 0);   // :188-194
-                    if (rel == cap) { first_live = true; sr = nsplit_rank[k]; }
+                    if (rel == keep) { first_live = true; sr = nsplit_rank[k]; }
                 }
                 digit[p] = (unsigned char)d;
             }
@@ -471,13 +520,15 @@ entry_scatter_kernel(const TreeGlobals* __restrict__ g, int level, const int4* _
 }
 
 // ------------------------------------------------------- centre of mass ---
+// leaf sources in stored order: (x, y, z, particle index bits) -- or, in the fixed mode, the float4
+// as it is (x, y, z, mass): that walk uses real masses and needs no self test
 __global__ void part_pos_kernel(const int* __restrict__ part_idx, const float4* __restrict__ posm, int n,
-                                float4* __restrict__ part_pos) {
+                                float4* __restrict__ part_pos, int fixed) {
     int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     const int idx = part_idx[q];
     float4 p = posm[idx];
-    p.w = __int_as_float(idx);
+    if (!fixed) p.w = __int_as_float(idx);
     part_pos[q] = p;
 }
 
@@ -679,18 +730,20 @@ __device__ __forceinline__ bool accept_cell_sq(float size, float d2, float theta
     return __fdiv_rn(size, __fsqrt_rn(d2)) < theta;              // :302-310, bit for bit
 }
 
-template <bool COUNT>
+// FIXED: the "fixed physics" walk -- leaf sources carry their real mass in .w and there is no
+// self test (with eps > 0 the self pair adds exactly 0; it is counted), softening = eps.
+template <bool COUNT, bool FIXED>
 __global__ void __launch_bounds__(128)
 walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order, int i0, int n_targets,
                  const float4* __restrict__ nodes, const float4* __restrict__ part_pos, float theta,
-                 float* __restrict__ acc3, TreeGlobals* __restrict__ g) {
+                 float eps, float* __restrict__ acc3, TreeGlobals* __restrict__ g) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = t < n_targets;
     const int i = valid ? (order ? order[t] : (i0 + t)) : -1;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) p = posm[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
-    const float eps2 = __fmul_rn(0.01f, 0.01f);                          // :281-282, :334-335
+    const float eps2 = FIXED ? eps * eps : __fmul_rn(0.01f, 0.01f);      // :281-282, :334-335
     const float theta2 = theta > 0.f ? theta * theta : 0.f;              // theta <= 0: nothing is ever accepted
     unsigned long long c_vis = 0, c_pc = 0, c_pp = 0;
     constexpr int AWAKE = -2, NEVER = -3;
@@ -711,8 +764,8 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
                     const float dx = s.x - p.x, dy = s.y - p.y, dz = s.z - p.z;
                     const float r2 = dx * dx + dy * dy + dz * dz + eps2;
                     const float rinv = rsqrt_fast(r2);
-                    const bool on = active && __float_as_int(s.w) != i;
-                    const float f = on ? rinv * rinv * rinv : 0.f;       // unit mass (:253, :340)
+                    const bool on = FIXED ? active : (active && __float_as_int(s.w) != i);
+                    const float f = on ? (FIXED ? s.w * rinv * rinv * rinv : rinv * rinv * rinv) : 0.f;   // unit mass (:253, :340)
                     ax += f * dx; ay += f * dy; az += f * dz;
                     if (COUNT && on) ++c_pp;
                 };
@@ -788,17 +841,23 @@ void tree_destroy(b200_ctx* ctx) {
 }
 
 int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_cap, int max_depth,
-               cudaStream_t st) {
-    if (!posm4 || n == 0 || !(box > 0.f)) return B200_ERR_INVALID;
+               bool fixed, float eps, cudaStream_t st) {
+    if (!posm4 || n == 0) return B200_ERR_INVALID;
+    if (fixed ? !(eps > 0.f) : !(box > 0.f)) return B200_ERR_INVALID;
     if (leaf_cap < 1 || max_depth < 0 || max_depth > MAX_LEVELS - 2) return B200_ERR_UNSUPPORTED;
     if (n >= (1ull << 30)) return B200_ERR_UNSUPPORTED;
     TreeState* T = state(ctx);
     T->built = false;
     T->order_valid = false;
     T->n = n; T->box = box; T->cap = leaf_cap; T->max_depth = max_depth;
+    T->fixed = fixed;
+    T->eps = fixed ? eps : 0.01f;
     T->posm = (const float4*)posm4;
-    // every internal node keeps exactly leaf_cap particles => at most n/leaf_cap internal nodes
-    T->max_split = n / (size_t)leaf_cap + 1;
+    // reference tree: every internal node keeps exactly leaf_cap particles => at most n/leaf_cap
+    // internal nodes.  Fixed tree: internal nodes of one level hold disjoint sets of > leaf_cap
+    // particles, typically ~n/(3 leaf_cap) in all; room for n/2 (deep chains under close pairs) --
+    // a tree that needs more reports B200_ERR_NOMEM through tree_stats/tree_export.
+    T->max_split = fixed ? n / 2 + 64 : n / (size_t)leaf_cap + 1;
     T->max_nodes = 8 * T->max_split + 1;
     T->max_tiles = (n + ENT_TILE - 1) / ENT_TILE + 1;
     T->max_node_tiles = (T->max_nodes + NODE_TILE - 1) / NODE_TILE + 1;
@@ -833,9 +892,16 @@ int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_c
     int* ncount = T->ncount.as<int>();
     int* nsr = T->nsplit_rank.as<int>();
     const int pgrid = ctx->sm_count * 8;      // persistent grids: 8 x 256-thread CTAs per SM
+    const int keep = fixed ? 0 : leaf_cap;
 
+    if (fixed) {
+        bbox_init_kernel<<<1, 32, 0, st>>>(g);
+        bbox_kernel<<<pgrid, 256, 0, st>>>(T->posm, (int)n, g);
+        root_cube_kernel<<<1, 1, 0, st>>>(g);
+        ctx->launches += 3;
+    }
     tree_init_kernel<<<pgrid, 256, 0, st>>>(g, center, com, meta, nstart, ncount, T->ent_idx[0].as<int>(),
-                                            T->ent_node[0].as<int>(), (int)n, box);
+                                            T->ent_node[0].as<int>(), (int)n, box, fixed ? 1 : 0);
     ctx->launches += 1;
     for (int L = 0; L <= max_depth; ++L) {
         const int cur = L & 1, nxt = cur ^ 1;
@@ -845,12 +911,12 @@ int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_c
         const int ngrid = (int)((nb + NODE_TILE - 1) / NODE_TILE < (size_t)pgrid ? (nb + NODE_TILE - 1) / NODE_TILE : (size_t)pgrid);
         const int egrid = (int)(T->max_tiles < (size_t)pgrid ? T->max_tiles : (size_t)pgrid);
         const int sgrid = (int)((nb + 255) / 256 < (size_t)pgrid ? (nb + 255) / 256 : (size_t)pgrid);
-        node_reduce_kernel<<<ngrid, 256, 0, st>>>(g, L, leaf_cap, max_depth, ncount, T->node_tile_sum.as<u64>());
+        node_reduce_kernel<<<ngrid, 256, 0, st>>>(g, L, leaf_cap, keep, max_depth, ncount, T->node_tile_sum.as<u64>());
         node_scan_kernel<<<1, 1024, 0, st>>>(g, L, T->node_tile_sum.as<u64>(), (int)T->max_nodes);
-        node_apply_kernel<<<ngrid, 256, 0, st>>>(g, L, leaf_cap, max_depth, ncount, T->node_tile_sum.as<u64>(),
+        node_apply_kernel<<<ngrid, 256, 0, st>>>(g, L, leaf_cap, keep, max_depth, ncount, T->node_tile_sum.as<u64>(),
                                                  meta, nsr, T->split_node.as<int>());
         entry_digit_kernel<<<egrid, ET_THREADS, 0, st>>>(
-            g, L, leaf_cap, T->posm, center, meta, nstart, nsr, T->ent_idx[cur].as<int>(),
+            g, L, keep, T->posm, center, meta, nstart, nsr, T->ent_idx[cur].as<int>(),
             T->ent_node[cur].as<int>(), T->digit.as<unsigned char>(), T->part_idx.as<int>(),
             T->tile_hist.as<unsigned>(), T->tile_warp_prefix.as<unsigned>(), T->split_where.as<int>(),
             T->split_local.as<unsigned>());
@@ -867,7 +933,7 @@ int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_c
         ctx->launches += 7;
     }
     part_pos_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(T->part_idx.as<int>(), T->posm, (int)n,
-                                                                 T->part_pos.as<float4>());
+                                                                 T->part_pos.as<float4>(), fixed ? 1 : 0);
     ctx->launches += 1;
     for (int L = max_depth; L >= 0; --L) {
         const double lvl_nodes = (L < 10) ? (double)(1ull << (3 * L)) : 1e30;
@@ -892,10 +958,11 @@ static int tree_target_order(b200_ctx* ctx, TreeState* T, size_t i0, size_t n_ta
     B200_TRY(T->sort_scratch.reserve(sort_scratch_bytes(n_targets)));
     // warp grouping of the targets: Hilbert order (B200_WALK_ORDER=morton: the 30-bit Morton keys of row T1)
     const char* ord = getenv("B200_WALK_ORDER");
-    if (ord && ord[0] == 'm')
+    if (ord && ord[0] == 'm' && !T->fixed)
         B200_TRY(morton_keys(ctx, T->posm + i0, n_targets, T->box, T->keys.as<uint32_t>(), st));
     else
-        B200_TRY(hilbert_keys(ctx, T->posm + i0, n_targets, T->box, T->keys.as<uint32_t>(), st));
+        B200_TRY(hilbert_keys(ctx, T->posm + i0, n_targets, T->box,
+                              T->fixed ? T->globals.as<TreeGlobals>()->root : nullptr, T->keys.as<uint32_t>(), st));
     B200_TRY(sort_pairs(ctx, T->keys.as<uint32_t>(), n_targets, T->keys_sorted.as<uint32_t>(),
                         T->order.as<int>(), 30, T->sort_scratch.p, st));
     if (i0) {
@@ -921,16 +988,25 @@ int tree_walk(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* acc
         ctx->launches += 1;
     }
     if (ctx->timing) B200_CUDA(cudaEventRecord(ctx->ev0, st));
-    const bool per_thread = getenv("B200_WALK_PER_THREAD") != nullptr;     // tuning hook
-    if (!per_thread) {
+    const bool per_thread = !T->fixed && getenv("B200_WALK_PER_THREAD") != nullptr;     // tuning hook
+    if (T->fixed) {
         if (T->counting)
-            walk_warp_kernel<true><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
-                                                         T->nodes.as<float4>(), T->part_pos.as<float4>(), theta,
-                                                         (float*)acc3, g);
+            walk_warp_kernel<true, true><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
+                                                               T->nodes.as<float4>(), T->part_pos.as<float4>(), theta,
+                                                               T->eps, (float*)acc3, g);
         else
-            walk_warp_kernel<false><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
-                                                          T->nodes.as<float4>(), T->part_pos.as<float4>(), theta,
-                                                          (float*)acc3, g);
+            walk_warp_kernel<false, true><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
+                                                                T->nodes.as<float4>(), T->part_pos.as<float4>(), theta,
+                                                                T->eps, (float*)acc3, g);
+    } else if (!per_thread) {
+        if (T->counting)
+            walk_warp_kernel<true, false><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
+                                                                T->nodes.as<float4>(), T->part_pos.as<float4>(), theta,
+                                                                T->eps, (float*)acc3, g);
+        else
+            walk_warp_kernel<false, false><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
+                                                                 T->nodes.as<float4>(), T->part_pos.as<float4>(), theta,
+                                                                 T->eps, (float*)acc3, g);
     } else if (T->counting)
         walk_kernel<true><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
                                                 T->com.as<float4>(), T->center.as<float4>(), T->meta.as<int4>(),

@@ -3,7 +3,7 @@
 namespace b200 {
 void tree_destroy(b200_ctx* ctx);
 int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_cap, int max_depth,
-               cudaStream_t st);
+               bool fixed, float eps, cudaStream_t st);
 int tree_walk(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* acc3, cudaStream_t st);
 int tree_set_counting(b200_ctx* ctx, int enabled);
 int tree_counters(b200_ctx* ctx, uint64_t counters[3]);

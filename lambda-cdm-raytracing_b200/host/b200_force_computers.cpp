@@ -78,11 +78,15 @@ void B200TreeForceComputer::compute_forces(const float* positions, const float* 
     float theta = theta_;
     size_t cap = leaf_capacity_;
     int depth = max_depth_;
+    float eps = softening_;
     if (const ForceComputeParameters* p = params_of(params)) {
-        theta = p->theta; cap = p->leaf_capacity; depth = p->tree_max_depth;
+        theta = p->theta; cap = p->leaf_capacity; depth = p->tree_max_depth; eps = p->softening_length;
     }
-    const int rc = b200_tree_forces_host(ctx_, positions, masses, forces, num_particles, theta, (int)cap,
-                                         depth, box_size_);
+    const int rc = fixed_physics_
+                       ? b200_tree_forces_fixed_host(ctx_, positions, masses, forces, num_particles, theta, (int)cap,
+                                                     depth, eps)
+                       : b200_tree_forces_host(ctx_, positions, masses, forces, num_particles, theta, (int)cap,
+                                               depth, box_size_);
     if (rc != B200_OK) {
         std::cerr << "TreeForceComputer::compute_forces failed: " << b200_error_string(rc) << std::endl;
         fail("TreeForceComputer::compute_forces", rc);

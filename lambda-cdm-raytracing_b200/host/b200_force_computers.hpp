@@ -82,6 +82,8 @@ class B200TreeForceComputer : public B200ComputerBase {
     size_t leaf_capacity_ = 8;
     int max_depth_ = 20;
     float box_size_ = 100.0f;
+    bool fixed_physics_ = false;                // see set_fixed_physics
+    float softening_ = 0.01f;                   // fixed-physics mode only (the reference hard-codes 0.01)
 public:
     explicit B200TreeForceComputer(const std::string& name) : B200ComputerBase(name) {}
     B200TreeForceComputer(const std::string& name, float theta, size_t leaf_capacity = 8, int max_depth = 20)
@@ -98,6 +100,13 @@ public:
     size_t get_leaf_capacity() const { return leaf_capacity_; }
     int get_max_depth() const { return max_depth_; }
     float get_box_size() const { return box_size_; }
+    // Not in the reference: Barnes-Hut without the CPU tree's quirks (no orphaned particles, real
+    // masses in leaf pairs, root cube fitted to the data, softening from set_softening() or
+    // ForceComputeParameters::softening_length) -- b200_tree_build_fixed_dev.  Off by default:
+    // the default is the reference's tree, node for node.
+    void set_fixed_physics(bool on) { fixed_physics_ = on; }
+    bool get_fixed_physics() const { return fixed_physics_; }
+    void set_softening(float eps) { softening_ = eps; }
     // tree_force_computer.hpp:100-103 (valid after a compute_forces call)
     size_t get_tree_depth() const;
     size_t get_node_count() const;

@@ -85,8 +85,12 @@ void B200LambdaCDMSimulation::compute_forces() {
     const size_t n = num_particles_;
     if (n == 0) return;
     // every rank sees all sources (replicated positions), and evaluates its own targets only
-    if (method_ == B200ForceMethod::Tree) {
-        check(b200_tree_build_dev(ctx_, d_posm_, n, box_size_, leaf_capacity_, max_depth_, stream_), "tree build");
+    if (method_ == B200ForceMethod::Tree || method_ == B200ForceMethod::TreeFixed) {
+        if (method_ == B200ForceMethod::Tree)
+            check(b200_tree_build_dev(ctx_, d_posm_, n, box_size_, leaf_capacity_, max_depth_, stream_), "tree build");
+        else
+            check(b200_tree_build_fixed_dev(ctx_, d_posm_, n, leaf_capacity_, max_depth_, softening_, stream_),
+                  "tree build (fixed physics)");
         check(b200_tree_walk_dev(ctx_, i0_, n_local_, theta_, d_acc_, stream_), "tree walk");
     } else {
         const float box = (method_ == B200ForceMethod::Direct) ? box_size_ : 0.0f;   // K1/K2 are periodic
@@ -116,7 +120,7 @@ void B200LambdaCDMSimulation::step(double dt) {
     const size_t n = num_particles_;
     if (n == 0) { ++current_step_; return; }
     if (!have_forces_) compute_forces();
-    const float wrap = (method_ == B200ForceMethod::Tree || method_ == B200ForceMethod::DirectOpen) ? 0.0f : box_size_;
+    const float wrap = (method_ == B200ForceMethod::Direct) ? box_size_ : 0.0f;     // only K1/K2 are periodic
     // lambda_cdm_impl.cu:167-213: kick(dt/2, a) -> drift(dt) -> a update -> forces -> kick(dt/2, a_new)
     void* my_posm = (char*)d_posm_ + i0_ * 16;
     check(b200_leapfrog_dev(ctx_, my_posm, d_vel_, d_acc_, n_local_, 1, (float)(dt * 0.5), scale_factor_, (float)dt, wrap,

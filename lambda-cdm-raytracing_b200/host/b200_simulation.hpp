@@ -32,7 +32,7 @@ struct b200_ctx;
 
 namespace physics {
 
-enum class B200ForceMethod { Direct, DirectOpen, Tree };
+enum class B200ForceMethod { Direct, DirectOpen, Tree, TreeFixed };   // TreeFixed: b200_tree_build_fixed_dev
 
 class B200LambdaCDMSimulation {
     b200_ctx* ctx_ = nullptr;

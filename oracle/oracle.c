@@ -408,8 +408,11 @@ orc_tree* orc_tree_build_insert(const float* pos3, const float* mass, size_t n,
 }
 
 /* -- builder 2: closed form, level by level -------------------------------- */
-orc_tree* orc_tree_build_levels(const float* pos3, const float* mass, size_t n,
-                                float box, size_t leaf_cap, int max_depth) {
+static orc_tree* build_levels_impl(const float* pos3, const float* mass, size_t n,
+                                   const float root_center[3], float root_size, size_t leaf_cap,
+                                   int max_depth, size_t keep) {
+    /* keep = arrivals a splitting node retains: leaf_cap in the reference's tree (they are
+     * never redistributed, :144-171), 0 in the fixed-physics tree (everything moves down) */
     /* growing node arrays */
     size_t ncap = 1024, nn = 0;
     int32_t* level = (int32_t*)malloc(ncap * sizeof(int32_t));
@@ -437,7 +440,8 @@ orc_tree* orc_tree_build_levels(const float* pos3, const float* mass, size_t n,
     int32_t* stored = (int32_t*)malloc((n ? n : 1) * sizeof(int32_t));
     int64_t nstored = 0;
     for (size_t i = 0; i < n; ++i) cur[i] = (int32_t)i;
-    level[0] = 0; center[0] = center[1] = center[2] = 0.0f; size[0] = box;
+    level[0] = 0; center[0] = root_center[0]; center[1] = root_center[1]; center[2] = root_center[2];
+    size[0] = root_size;
     arrivals[0] = (int64_t)n; seg_start[0] = 0; nn = 1;
     size_t lv_begin = 0, lv_end = 1;
     for (int lv = 0; lv_begin < lv_end; ++lv) {
@@ -455,12 +459,12 @@ orc_tree* orc_tree_build_levels(const float* pos3, const float* mass, size_t n,
                 st_cnt[k] = cnt;
                 continue;
             }
-            for (int64_t s = 0; s < (int64_t)leaf_cap; ++s) stored[nstored++] = seg[s];
-            st_cnt[k] = (int64_t)leaf_cap;
+            for (int64_t s = 0; s < (int64_t)keep; ++s) stored[nstored++] = seg[s];
+            st_cnt[k] = (int64_t)keep;
             GROW(nn + 8);
             first_child[k] = (int32_t)nn;
             int64_t ccount[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            for (int64_t s = (int64_t)leaf_cap; s < cnt; ++s)
+            for (int64_t s = (int64_t)keep; s < cnt; ++s)
                 ccount[octant_of(&pos3[3 * (size_t)seg[s]], &center[3 * k])]++;
             int64_t cbase[8];
             for (int ch = 0; ch < 8; ++ch) {
@@ -474,7 +478,7 @@ orc_tree* orc_tree_build_levels(const float* pos3, const float* mass, size_t n,
                 cbase[ch] = nxt_fill;
                 nxt_fill += ccount[ch];
             }
-            for (int64_t s = (int64_t)leaf_cap; s < cnt; ++s) {   /* stable split */
+            for (int64_t s = (int64_t)keep; s < cnt; ++s) {   /* stable split */
                 int o = octant_of(&pos3[3 * (size_t)seg[s]], &center[3 * k]);
                 nxt[cbase[o]++] = seg[s];
             }
@@ -499,6 +503,43 @@ orc_tree* orc_tree_build_levels(const float* pos3, const float* mass, size_t n,
     free(seg_start); free(st_off); free(st_cnt); free(cur); free(nxt); free(stored);
     tree_com(t, pos3, mass);
     return t;
+}
+
+orc_tree* orc_tree_build_levels(const float* pos3, const float* mass, size_t n,
+                                float box, size_t leaf_cap, int max_depth) {
+    const float origin[3] = {0.0f, 0.0f, 0.0f};                /* :132-133 */
+    return build_levels_impl(pos3, mass, n, origin, box, leaf_cap, max_depth, leaf_cap);
+}
+
+/* -- "fixed physics" tree: NOT the reference's tree.  Same octant rule
+ * (:188-194), same child geometry (:173-186), same centre-of-mass pass (:196-243), but
+ *   - a node that splits hands ALL its particles to its children (no orphans),
+ *   - the root cube is fitted to the data: centre = midpoint of the bounding box, edge =
+ *     largest extent * 1.00001f (1.0f when every particle coincides).
+ * Its purpose is a physically meaningful Barnes-Hut force, validated against the FP64
+ * direct sum rather than against the reference's tree. */
+void orc_fixed_root(const float* pos3, size_t n, float center[3], float* size) {
+    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    for (size_t i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) {
+            float v = pos3[3 * i + k];
+            if (i == 0 || v < lo[k]) lo[k] = v;
+            if (i == 0 || v > hi[k]) hi[k] = v;
+        }
+    float ext = 0.0f;
+    for (int k = 0; k < 3; ++k) {
+        center[k] = (lo[k] + hi[k]) * 0.5f;
+        float e = hi[k] - lo[k];
+        if (e > ext) ext = e;
+    }
+    *size = ext > 0.0f ? ext * 1.00001f : 1.0f;
+}
+
+orc_tree* orc_tree_build_fixed(const float* pos3, const float* mass, size_t n,
+                               size_t leaf_cap, int max_depth) {
+    float c[3], sz;
+    orc_fixed_root(pos3, n, c, &sz);
+    return build_levels_impl(pos3, mass, n, c, sz, leaf_cap, max_depth, 0);
 }
 
 int orc_tree_equal(const orc_tree* a, const orc_tree* b) {
@@ -579,6 +620,61 @@ void orc_tree_forces(const orc_tree* t, const float* pos3, float theta,
                 fx += f * dx; fy += f * dy; fz += f * dz;
                 ++c_pc;
             } else {                                            /* :293-297, children 0..7 */
+                for (int ch = 7; ch >= 0; --ch) stack[sp++] = t->first_child[k] + ch;
+            }
+        }
+        out3[3 * tt + 0] = fx;
+        out3[3 * tt + 1] = fy;
+        out3[3 * tt + 2] = fz;
+    }
+    if (counters) { counters[0] = c_vis; counters[1] = c_pc; counters[2] = c_pp; }
+}
+
+/* Fixed-physics walk: the reference's walk (:257-310) with the two leaf quirks removed --
+ * leaf pairs use the sources' real masses and the softening is a parameter -- on a tree
+ * without orphans.  No j == i test: with eps > 0 the self pair adds exactly 0 (it IS
+ * counted in counters[2]). */
+void orc_tree_forces_fixed(const orc_tree* t, const float* pos3, const float* mass, float theta,
+                           float eps, size_t i0, size_t n_targets, float* out3,
+                           uint64_t* counters) {
+    uint64_t c_vis = 0, c_pc = 0, c_pp = 0;
+    const float eps2 = eps * eps;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : c_vis, c_pc, c_pp)
+    for (long long tt = 0; tt < (long long)n_targets; ++tt) {
+        size_t i = i0 + (size_t)tt;
+        float px = pos3[3 * i + 0], py = pos3[3 * i + 1], pz = pos3[3 * i + 2];
+        float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+        int32_t stack[8 * 64];
+        int sp = 0;
+        stack[sp++] = 0;
+        while (sp > 0) {
+            size_t k = (size_t)stack[--sp];
+            ++c_vis;
+            if (t->mass[k] == 0.0f) continue;
+            if (t->first_child[k] < 0) {
+                for (int64_t q = t->part_off[k]; q < t->part_off[k + 1]; ++q) {
+                    size_t j = (size_t)t->part_idx[q];
+                    float dx = pos3[3 * j + 0] - px;
+                    float dy = pos3[3 * j + 1] - py;
+                    float dz = pos3[3 * j + 2] - pz;
+                    float r2 = dx * dx + dy * dy + dz * dz + eps2;
+                    float r = sqrtf(r2);
+                    float f = (mass ? mass[j] : 1.0f) / (r2 * r);
+                    fx += f * dx; fy += f * dy; fz += f * dz;
+                    ++c_pp;
+                }
+                continue;
+            }
+            float dx = t->com[3 * k + 0] - px;
+            float dy = t->com[3 * k + 1] - py;
+            float dz = t->com[3 * k + 2] - pz;
+            float d2 = dx * dx + dy * dy + dz * dz;
+            if ((t->size[k] / sqrtf(d2)) < theta) {
+                float r2 = d2 + eps2;
+                float f = t->mass[k] / (r2 * sqrtf(r2));
+                fx += f * dx; fy += f * dy; fz += f * dz;
+                ++c_pc;
+            } else {
                 for (int ch = 7; ch >= 0; --ch) stack[sp++] = t->first_child[k] + ch;
             }
         }

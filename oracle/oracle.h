@@ -85,6 +85,14 @@ orc_tree* orc_tree_build_insert(const float* pos3, const float* mass, size_t n,
  * "first leaf_cap arrivals stay" orphan rule.  Must equal the above. */
 orc_tree* orc_tree_build_levels(const float* pos3, const float* mass, size_t n,
                                 float box, size_t leaf_cap, int max_depth);
+/* Fixed-physics tree and walk: no orphans, data-fitted root cube, real masses in
+ * leaf pairs, eps parameter.  Not the reference's tree; validated against orc_direct_f64. */
+void orc_fixed_root(const float* pos3, size_t n, float center[3], float* size);
+orc_tree* orc_tree_build_fixed(const float* pos3, const float* mass, size_t n,
+                               size_t leaf_cap, int max_depth);
+void orc_tree_forces_fixed(const orc_tree* t, const float* pos3, const float* mass, float theta,
+                           float eps, size_t i0, size_t n_targets, float* out3,
+                           uint64_t* counters);
 void orc_tree_free(orc_tree* t);
 /* 1 if the two canonical tables are identical (topology, stored particles,
  * centres, sizes, mass, com bit patterns), else 0. */

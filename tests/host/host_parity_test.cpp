@@ -93,6 +93,31 @@ int main() {
         CHECK(rel_l2(b, a_cpu) > 1e-3, "softening_length from ForceComputeParameters is honoured");
     }
 
+    {   // fixed-physics mode (not in the reference): against an FP64 direct sum, where the reference's
+        // own tree semantics are ~0.3 away (orphans, unit-mass leaves)
+        const size_t m_n = 6000;
+        std::vector<float> f_fixed(3 * m_n), f_faithful(3 * m_n);
+        std::vector<double> want(3 * m_n, 0.0);
+        for (size_t i = 0; i < m_n; ++i)
+            for (size_t j = 0; j < m_n; ++j) {
+                const double dx = (double)pos[3 * j] - pos[3 * i], dy = (double)pos[3 * j + 1] - pos[3 * i + 1],
+                             dz = (double)pos[3 * j + 2] - pos[3 * i + 2];
+                const double r2 = dx * dx + dy * dy + dz * dz + 1e-4;
+                const double f = mass[j] / (r2 * std::sqrt(r2));
+                want[3 * i] += f * dx; want[3 * i + 1] += f * dy; want[3 * i + 2] += f * dz;
+            }
+        std::vector<float> wantf(want.begin(), want.end());
+        bt->set_fixed_physics(true);
+        bt->set_softening(0.01f);
+        tree->compute_forces(pos.data(), mass.data(), f_fixed.data(), m_n);
+        const size_t stored_nodes = bt->get_node_count();
+        bt->set_fixed_physics(false);
+        tree->compute_forces(pos.data(), mass.data(), f_faithful.data(), m_n);
+        CHECK(rel_l2(f_fixed, wantf) < 4e-3 && rel_l2(f_faithful, wantf) > 0.1 && stored_nodes > 0,
+              "fixed-physics tree vs FP64 direct sum: rel-L2 %.2e (the reference's tree semantics: %.2e)",
+              rel_l2(f_fixed, wantf), rel_l2(f_faithful, wantf));
+    }
+
     {   // KDK: IIntegrator + IForceComputer + ICosmologyModel, 5 steps, against the same loop on the CPU tree
         physics::B200LeapfrogIntegrator integ("leapfrog");
         physics::LambdaCDMModel cosmo("lcdm");

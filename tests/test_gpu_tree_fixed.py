@@ -1,0 +1,97 @@
+"""-m gpu: the "fixed physics" Barnes-Hut mode: no orphans, data-fitted root cube,
+real masses in leaf pairs, eps parameter.  Topology bit-exact against the oracle's fixed builder,
+forces against the oracle's fixed walk, and -- the point of the mode -- against the FP64 direct sum."""
+import numpy as np
+import pytest
+import torch
+
+from inputs import clustered_np, masses_np, rel_l2, uniform_mt, uniform_np
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("level", "first_child", "part_off", "part_idx", "center", "size", "com", "mass")
+
+
+def _posm(pos, mass):
+    return torch.from_numpy(np.concatenate([pos, mass[:, None]], 1).astype(np.float32)).cuda()
+
+
+def _cases():
+    yield "uniform", uniform_mt(20000, seed=3), masses_np(20000, seed=4), 8, 20
+    yield "box_convention", uniform_np(6000, seed=5, lo=0.0, hi=100.0), masses_np(6000, seed=6), 8, 20
+    yield "clustered_small_leaves", clustered_np(15000, seed=7), masses_np(15000, seed=8), 3, 20
+    yield "shallow", clustered_np(5000, seed=9), np.ones(5000, np.float32), 4, 5
+    p = uniform_mt(3000, seed=10)
+    p[100:140] = p[50]                                  # 41 coincident particles: a max-depth chain
+    yield "duplicates", p, masses_np(3000, seed=11), 8, 20
+    yield "tiny", uniform_mt(5, seed=12), masses_np(5, seed=13), 8, 20
+    yield "one", uniform_mt(1, seed=14), masses_np(1, seed=15), 8, 20
+
+
+@pytest.mark.parametrize("name,pos,mass,cap,depth", list(_cases()), ids=[c[0] for c in _cases()])
+def test_fixed_tree_topology_and_forces(engine, oracle, name, pos, mass, cap, depth):
+    n = pos.shape[0]
+    posm = _posm(pos, mass)
+    engine.tree_build_fixed_dev(posm, n, cap, depth, eps=0.02)
+    acc = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    engine.tree_set_counting(True)
+    engine.tree_walk_dev(acc, 0, n, theta=0.5)
+    torch.cuda.synchronize()
+    cnt = engine.tree_counters()
+    engine.tree_set_counting(False)
+    t = oracle.tree_build_fixed(pos, mass, cap, depth)
+    exp = engine.tree_export()
+    for k in KEYS:
+        assert np.array_equal(exp[k], getattr(t, k)), k               # bit-exact, centres of mass included
+    assert int(t.part_off[-1]) == n                                    # every particle is a leaf member
+    want, c0 = oracle.tree_forces_fixed(t, pos, mass, 0.5, 0.02, counters=True)
+    assert [int(x) for x in cnt] == [int(x) for x in c0]               # same visits / cells / pairs
+    if n > 1:
+        assert rel_l2(acc.cpu().numpy(), want) < 1e-5
+
+
+def test_fixed_tree_converges_to_direct_sum(engine, oracle):
+    n = 30000
+    pos, mass = clustered_np(n, seed=21), masses_np(n, seed=22)
+    ref = oracle.direct_f64(pos, mass, eps=0.01)
+    posm = _posm(pos, mass)
+    engine.tree_build_fixed_dev(posm, n, 8, 20, eps=0.01)
+    acc = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    errs = []
+    for theta in (0.7, 0.5, 0.3, 0.2):
+        engine.tree_walk_dev(acc, 0, n, theta=theta)
+        torch.cuda.synchronize()
+        errs.append(rel_l2(acc.cpu().numpy(), ref))
+    assert errs[1] < 4e-3 and errs[3] < 2e-4, errs                      # monopole Barnes-Hut error at theta 0.5 / 0.2
+    assert errs[0] > errs[1] > errs[2] > errs[3], errs
+    # the reference's own tree semantics on the same particles, for the record: ~0.3-0.6 away
+    engine.tree_build_dev(posm, n, 100.0, 8, 20)
+    engine.tree_walk_dev(acc, 0, n, theta=0.5)
+    torch.cuda.synchronize()
+    assert rel_l2(acc.cpu().numpy(), ref) > 0.1
+
+
+def test_fixed_tree_host_entry_and_shards(engine, oracle):
+    n = 9001
+    pos, mass = uniform_mt(n, seed=31), masses_np(n, seed=32)
+    full = engine.tree_forces_fixed_host(pos, mass, theta=0.4, leaf_cap=8, max_depth=20, eps=0.05)
+    t = oracle.tree_build_fixed(pos, mass, 8, 20)
+    assert rel_l2(full, oracle.tree_forces_fixed(t, pos, mass, 0.4, 0.05)) < 1e-5
+    posm = _posm(pos, mass)
+    engine.tree_build_fixed_dev(posm, n, 8, 20, eps=0.05)
+    parts = []
+    for lo, hi in ((0, 3000), (3000, 3001), (3001, n)):                 # target shards: bitwise the same forces
+        a = torch.empty((hi - lo, 3), dtype=torch.float32, device="cuda")
+        engine.tree_walk_dev(a, lo, hi - lo, theta=0.4)
+        parts.append(a.cpu().numpy())
+    assert np.array_equal(np.concatenate(parts), full)
+    unit = engine.tree_forces_fixed_host(pos, None, theta=0.4, eps=0.05)                 # mass == NULL -> 1
+    assert rel_l2(unit, oracle.tree_forces_fixed(oracle.tree_build_fixed(pos, np.ones(n, np.float32)), pos,
+                                                 np.ones(n, np.float32), 0.4, 0.05)) < 1e-5
+
+
+def test_fixed_tree_rejects_bad_eps(engine):
+    import b200grav
+    posm = _posm(uniform_mt(100, seed=1), np.ones(100, np.float32))
+    with pytest.raises(b200grav.B200Error):
+        engine.tree_build_fixed_dev(posm, 100, 8, 20, eps=0.0)
