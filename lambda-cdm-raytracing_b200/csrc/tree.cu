@@ -70,7 +70,9 @@ struct TreeState {
     DevBuf center, com, meta, nstart, ncount, nsplit_rank;
     DevBuf ent_idx[2], ent_node[2], digit;
     DevBuf part_idx, part_pos;
-    DevBuf nodes;                 // walk records: {centre of mass float4, meta int4} interleaved, 32 B per node
+    DevBuf nodes;                 // walk records, 32 B per node: {centre of mass, M} {first, skip, edge, leaf count}
+    DevBuf leaf_pos, leaf_off, lscan, leaf_tile_sum;   // leaf sources grouped by parent (walk-only copies)
+    DevBuf slot_node;             // node that stores slot q of part_idx
     DevBuf globals;
     DevBuf tile_hist, tile_warp_prefix, node_tile_sum;
     DevBuf split_node, split_where, split_local, split_cstart;
@@ -79,7 +81,7 @@ struct TreeState {
     bool order_valid = false;
     void release() {
         DevBuf* all[] = {&center, &com, &meta, &nstart, &ncount, &nsplit_rank, &ent_idx[0],
-                         &ent_idx[1], &ent_node[0], &ent_node[1], &digit, &part_idx, &part_pos, &nodes,
+                         &ent_idx[1], &ent_node[0], &ent_node[1], &digit, &part_idx, &part_pos, &nodes, &leaf_pos, &leaf_off, &lscan, &leaf_tile_sum, &slot_node,
                          &globals, &tile_hist, &tile_warp_prefix, &node_tile_sum, &split_node,
                          &split_where, &split_local, &split_cstart, &keys, &keys_sorted, &perm,
                          &sort_scratch, &order};
@@ -331,7 +333,8 @@ entry_digit_kernel(const TreeGlobals* __restrict__ g, int level, int keep,
                    const int4* __restrict__ meta, const int* __restrict__ nstart,
                    const int* __restrict__ nsplit_rank, const int* __restrict__ ent_idx,
                    const int* __restrict__ ent_node, unsigned char* __restrict__ digit,
-                   int* __restrict__ part_idx, unsigned* __restrict__ tile_hist,
+                   int* __restrict__ part_idx, int* __restrict__ slot_node,
+                   unsigned* __restrict__ tile_hist,
                    unsigned* __restrict__ tile_warp_prefix, int* __restrict__ split_where,
                    unsigned* __restrict__ split_local) {
     __shared__ unsigned wtot[ET_WARPS][8];
@@ -354,6 +357,7 @@ entry_digit_kernel(const TreeGlobals* __restrict__ g, int level, int keep,
                 const int rel = p - nstart[k];
                 if (m.x < 0 || rel < keep) {
                     part_idx[m.z + rel] = idx;          // leaf member, or orphan of a split node
+                    slot_node[m.z + rel] = k;
                 } else {
                     const float4 c = center[k];
                     const float4 x = posm[idx];
@@ -391,24 +395,37 @@ entry_digit_kernel(const TreeGlobals* __restrict__ g, int level, int keep,
     }
 }
 
-// single CTA, warp d scans channel d over the tiles
+// single CTA, warp d scans channel d over the tiles; 8 tiles per lane per step (256 per warp step) so
+// that a 16 M-particle level (8192 tiles) is 32 dependent steps, not 256
 __global__ void __launch_bounds__(256)
 tile_scan_kernel(TreeGlobals* __restrict__ g, int level, unsigned* __restrict__ tile_hist) {
     __shared__ unsigned tot[8];
+    constexpr int PER = 8;
     const LevelInfo L = g->lv[level];
     const int n_tiles = (L.n_entries + ENT_TILE - 1) / ENT_TILE;
     const int lane = threadIdx.x & 31, d = threadIdx.x >> 5;
     unsigned carry = 0;
-    for (int base = 0; base < n_tiles; base += 32) {
-        const int t = base + lane;
-        const unsigned v = (t < n_tiles) ? tile_hist[(size_t)t * 8 + d] : 0u;
-        unsigned x = v;
+    for (int base = 0; base < n_tiles; base += 32 * PER) {
+        unsigned v[PER], sum = 0;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int t = base + lane * PER + j;
+            v[j] = (t < n_tiles) ? tile_hist[(size_t)t * 8 + d] : 0u;
+            sum += v[j];
+        }
+        unsigned x = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             unsigned y = __shfl_up_sync(FULL, x, o);
             if (lane >= o) x += y;
         }
-        if (t < n_tiles) tile_hist[(size_t)t * 8 + d] = carry + x - v;
+        unsigned pre = carry + x - sum;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int t = base + lane * PER + j;
+            if (t < n_tiles) tile_hist[(size_t)t * 8 + d] = pre;
+            pre += v[j];
+        }
         carry += __shfl_sync(FULL, x, 31);
     }
     if (lane == 0) { tot[d] = carry; g->totals[d] = carry; }
@@ -520,16 +537,22 @@ entry_scatter_kernel(const TreeGlobals* __restrict__ g, int level, const int4* _
 }
 
 // ------------------------------------------------------- centre of mass ---
-// leaf sources in stored order: (x, y, z, particle index bits) -- or, in the fixed mode, the float4
-// as it is (x, y, z, mass): that walk uses real masses and needs no self test
-__global__ void part_pos_kernel(const int* __restrict__ part_idx, const float4* __restrict__ posm, int n,
-                                float4* __restrict__ part_pos, int fixed) {
+// Stored particles in stored order, (x, y, z, particle index bits) -- or, in the fixed mode, the
+// float4 as it is (x, y, z, mass): that walk uses real masses and needs no self test -- and, for the
+// slots that belong to leaf nodes, a second copy in the walk's per-parent layout (lscan).
+__global__ void stored_pos_kernel(const int* __restrict__ part_idx, const int* __restrict__ slot_node,
+                                  const int4* __restrict__ meta, const int* __restrict__ lscan,
+                                  const float4* __restrict__ posm, int n, float4* __restrict__ part_pos,
+                                  float4* __restrict__ leaf_pos, int fixed) {
     int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     const int idx = part_idx[q];
     float4 p = posm[idx];
     if (!fixed) p.w = __int_as_float(idx);
     part_pos[q] = p;
+    const int k = slot_node[q];
+    const int4 m = meta[k];
+    if (m.x < 0) leaf_pos[lscan[k] + (q - m.z)] = p;
 }
 
 // compute_center_of_mass (:196-243): one rounding per operation, reference order.
@@ -609,19 +632,147 @@ com_kernel(const TreeGlobals* __restrict__ g, int level, int4* __restrict__ meta
     }
 }
 
-// Walk records: centre of mass + node record of node k side by side (one 32-byte sector),
-// written once the build is complete.  The node count is device-side state.
-__global__ void __launch_bounds__(256)
-pack_nodes_kernel(const TreeGlobals* __restrict__ g, int max_depth, const float4* __restrict__ com,
-                  const int4* __restrict__ meta, float4* __restrict__ nodes) {
+// ------------------------------------------------- walk-only structures ---
+// The walk never visits a leaf node.  A target that opens node X interacts with the particles of
+// ALL of X's leaf children (:268-270 makes no distance test for leaves), so those particles are
+// laid out contiguously per parent (leaf nodes in node-id order = grouped by parent, children in
+// order; orphans stored at internal nodes are left out -- they are never sources) and X's record
+// carries the range.  The links of the records skip leaf nodes: `first` = first INTERNAL node in
+// depth-first order inside or after X's children, `skip` = first internal node after X's subtree.
+__device__ __forceinline__ int tree_node_count(const TreeGlobals* g, int max_depth) {
     int nn = 0;
     for (int L = 0; L <= max_depth; ++L)
         if (g->lv[L].node_end > g->lv[L].node_begin) nn = g->lv[L].node_end;
+    return nn;
+}
+__device__ __forceinline__ int leaf_particles(const int4 m) { return m.x < 0 ? m.w : 0; }
+
+// exclusive scan over node ids of the leaf particle counts: tile sums, scan of the sums, apply
+__global__ void __launch_bounds__(256)
+leaf_reduce_kernel(const TreeGlobals* __restrict__ g, int max_depth, const int4* __restrict__ meta,
+                   int* __restrict__ tile_sum) {
+    __shared__ int sh[8];
+    const int nn = tree_node_count(g, max_depth);
+    const int n_tiles = (nn + NODE_TILE - 1) / NODE_TILE;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int v = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = tile * NODE_TILE + j * 256 + threadIdx.x;
+            if (k < nn) v += leaf_particles(meta[k]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < 8; ++w) t += sh[w];
+            tile_sum[tile] = t;
+        }
+    }
+}
+__global__ void __launch_bounds__(1024)
+leaf_scan_kernel(const TreeGlobals* __restrict__ g, int max_depth, int* __restrict__ tile_sum) {
+    __shared__ int wsum[32];
+    __shared__ int carry_s, chunk_s;
+    const int nn = tree_node_count(g, max_depth);
+    const int n_tiles = (nn + NODE_TILE - 1) / NODE_TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = (i < n_tiles) ? tile_sum[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(FULL, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = wsum[lane];
+            int xs = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(FULL, xs, o);
+                if (lane >= o) xs += y;
+            }
+            wsum[lane] = xs - w;
+            if (lane == 31) chunk_s = xs;
+        }
+        __syncthreads();
+        if (i < n_tiles) tile_sum[i] = carry_s + wsum[warp] + (x - v);
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += chunk_s;
+        __syncthreads();
+    }
+}
+// lscan[k] = number of leaf particles in nodes < k (k = 0..nn); one tile of 2048 nodes per CTA pass,
+// thread t owns nodes [8t, 8t+8) of the tile so the in-tile scan is a thread-serial + warp + CTA scan
+__global__ void __launch_bounds__(256)
+leaf_apply_kernel(const TreeGlobals* __restrict__ g, int max_depth, const int4* __restrict__ meta,
+                  const int* __restrict__ tile_sum, int* __restrict__ lscan) {
+    __shared__ int wsum[8];
+    const int nn = tree_node_count(g, max_depth);
+    const int n_tiles = (nn + NODE_TILE - 1) / NODE_TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int v[8], tsum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = tile * NODE_TILE + threadIdx.x * 8 + j;
+            v[j] = (k < nn) ? leaf_particles(meta[k]) : 0;
+            tsum += v[j];
+        }
+        int x = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(FULL, x, o);
+            if (lane >= o) x += y;
+        }
+        __syncthreads();
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        int pre = tile_sum[tile] + (x - tsum);
+        for (int w = 0; w < warp; ++w) pre += wsum[w];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = tile * NODE_TILE + threadIdx.x * 8 + j;
+            if (k < nn) lscan[k] = pre;
+            pre += v[j];
+            if (k == nn - 1) lscan[nn] = pre;
+        }
+    }
+}
+// walk records of the internal nodes (and of a root that is a leaf: first = ROOT_LEAF)
+constexpr int ROOT_LEAF = -2;
+__global__ void __launch_bounds__(256)
+pack_walk_kernel(const TreeGlobals* __restrict__ g, int max_depth, const float4* __restrict__ com,
+                 const int4* __restrict__ meta, const int* __restrict__ lscan,
+                 float4* __restrict__ nodes, int* __restrict__ leaf_off) {
+    const int nn = tree_node_count(g, max_depth);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nn; k += gridDim.x * blockDim.x) {
         const int4 m = meta[k];
+        if (m.x < 0 && k != 0) continue;
+        int first, skip = -1, loff, lcnt;
+        if (m.x < 0) {                               // the whole tree is one leaf
+            first = ROOT_LEAF; loff = 0; lcnt = m.w;
+        } else {
+            first = m.x;                             // children, then whatever follows the subtree
+            while (first >= 0 && meta[first].x < 0) first = meta[first].y;
+            skip = m.y;
+            while (skip >= 0 && meta[skip].x < 0) skip = meta[skip].y;
+            loff = lscan[m.x];
+            lcnt = lscan[m.x + 8] - loff;
+        }
         nodes[2 * k] = com[k];
-        nodes[2 * k + 1] = make_float4(__int_as_float(m.x), __int_as_float(m.y), __int_as_float(m.z),
-                                       __int_as_float(m.w));
+        nodes[2 * k + 1] = make_float4(__int_as_float(first), __int_as_float(skip), __int_as_float(m.w),
+                                       __int_as_float(lcnt));      // m.w of an internal node = cell edge bits
+        leaf_off[k] = loff;
     }
 }
 
@@ -735,8 +886,9 @@ __device__ __forceinline__ bool accept_cell_sq(float size, float d2, float theta
 template <bool COUNT, bool FIXED>
 __global__ void __launch_bounds__(128)
 walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order, int i0, int n_targets,
-                 const float4* __restrict__ nodes, const float4* __restrict__ part_pos, float theta,
-                 float eps, float* __restrict__ acc3, TreeGlobals* __restrict__ g) {
+                 const float4* __restrict__ nodes, const int* __restrict__ leaf_off,
+                 const float4* __restrict__ leaf_pos, float theta, float eps,
+                 float* __restrict__ acc3, TreeGlobals* __restrict__ g) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = t < n_targets;
     const int i = valid ? (order ? order[t] : (i0 + t)) : -1;
@@ -745,46 +897,47 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
     float ax = 0.f, ay = 0.f, az = 0.f;
     const float eps2 = FIXED ? eps * eps : __fmul_rn(0.01f, 0.01f);      // :281-282, :334-335
     const float theta2 = theta > 0.f ? theta * theta : 0.f;              // theta <= 0: nothing is ever accepted
-    unsigned long long c_vis = 0, c_pc = 0, c_pp = 0;
+    unsigned long long c_vis = valid ? 1 : 0, c_pc = 0, c_pp = 0;        // the root is visited by everyone
     constexpr int AWAKE = -2, NEVER = -3;
     int wake = valid ? AWAKE : NEVER;     // node id at which a sleeping lane resumes
+
+    // the particles of a leaf range against this lane's target; `on` = the lane takes part.
+    // Branch-free rows: a lane that is out, or is the particle itself (:321), adds f = 0.
+    auto leaf_range = [&](int q, int cnt, bool on_lane) {
+        auto pair = [&](const float4& s) {
+            const float dx = s.x - p.x, dy = s.y - p.y, dz = s.z - p.z;
+            const float r2 = dx * dx + dy * dy + dz * dz + eps2;
+            const float rinv = rsqrt_fast(r2);
+            const bool on = FIXED ? on_lane : (on_lane && __float_as_int(s.w) != i);
+            const float f = on ? (FIXED ? s.w * rinv * rinv * rinv : rinv * rinv * rinv) : 0.f;   // :253, :340
+            ax += f * dx; ay += f * dy; az += f * dz;
+            if (COUNT && on) ++c_pp;
+        };
+        const int qe = q + cnt;
+        for (; q + 4 <= qe; q += 4) {                    // 4 broadcast loads in flight, then 4 rows
+            const float4 s0 = leaf_pos[q], s1 = leaf_pos[q + 1], s2 = leaf_pos[q + 2], s3 = leaf_pos[q + 3];
+            pair(s0); pair(s1); pair(s2); pair(s3);
+        }
+        for (; q < qe; ++q) pair(leaf_pos[q]);
+    };
+
     int k = 0;
     while (k >= 0) {
         if (wake == k) wake = AWAKE;
         const bool active = (wake == AWAKE);
         const float4 c = nodes[2 * k];                                   // centre of mass, M
-        const float4 mf = nodes[2 * k + 1];                              // first child | skip | part_off | npart or size
-        const int first = __float_as_int(mf.x), skip = __float_as_int(mf.y);
-        if (COUNT && active) ++c_vis;
+        const float4 mf = nodes[2 * k + 1];                              // first | skip | cell edge | leaf-child particles
+        const int first = __float_as_int(mf.x), skip = __float_as_int(mf.y), lcnt = __float_as_int(mf.w);
         if (c.w == 0.0f) { k = skip; continue; }                         // :260
-        if (first < 0) {                                                 // leaf :268-270
-            if (__any_sync(FULL, active)) {
-                // branch-free pair: a lane that is asleep, or is the particle itself (:321), adds f = 0
-                auto pair = [&](const float4& s) {
-                    const float dx = s.x - p.x, dy = s.y - p.y, dz = s.z - p.z;
-                    const float r2 = dx * dx + dy * dy + dz * dz + eps2;
-                    const float rinv = rsqrt_fast(r2);
-                    const bool on = FIXED ? active : (active && __float_as_int(s.w) != i);
-                    const float f = on ? (FIXED ? s.w * rinv * rinv * rinv : rinv * rinv * rinv) : 0.f;   // unit mass (:253, :340)
-                    ax += f * dx; ay += f * dy; az += f * dz;
-                    if (COUNT && on) ++c_pp;
-                };
-                int q = __float_as_int(mf.z);
-                const int qe = q + __float_as_int(mf.w);
-                for (; q + 4 <= qe; q += 4) {            // 4 broadcast loads in flight, then 4 pairs
-                    const float4 s0 = part_pos[q], s1 = part_pos[q + 1], s2 = part_pos[q + 2], s3 = part_pos[q + 3];
-                    pair(s0); pair(s1); pair(s2); pair(s3);
-                }
-                for (; q < qe; ++q) pair(part_pos[q]);
-            }
-            k = skip;
-            continue;
+        if (first == ROOT_LEAF) {                                        // the tree is a single leaf (:268-270)
+            leaf_range(0, lcnt, active);
+            break;
         }
         bool open = false;
         if (active) {
             const float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
             const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            if (accept_cell_sq(mf.w, d2, theta, theta2)) {               // cell edge rides in meta.w; :309
+            if (accept_cell_sq(mf.z, d2, theta, theta2)) {               // :309
                 const float rinv = rsqrt_fast(d2 + eps2);
                 const float f = c.w * rinv * rinv * rinv;                // :280-290
                 ax += f * dx; ay += f * dy; az += f * dz;
@@ -794,7 +947,13 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
                 open = true;
             }
         }
-        k = __any_sync(FULL, open) ? first : skip;                       // :293-297
+        if (__any_sync(FULL, open)) {                                    // :293-297
+            if (COUNT && open) c_vis += 8;                               // its 8 children, leaves included
+            if (lcnt > 0) leaf_range(leaf_off[k], lcnt, open);
+            k = first;
+        } else {
+            k = skip;
+        }
     }
     if (valid) {
         const size_t o = (size_t)(i - i0) * 3;
@@ -875,6 +1034,11 @@ int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_c
     B200_TRY(T->part_idx.reserve(n * sizeof(int)));
     B200_TRY(T->part_pos.reserve(n * sizeof(float4)));
     B200_TRY(T->nodes.reserve(T->max_nodes * 2 * sizeof(float4)));
+    B200_TRY(T->leaf_pos.reserve(n * sizeof(float4)));
+    B200_TRY(T->slot_node.reserve(n * sizeof(int)));
+    B200_TRY(T->leaf_off.reserve(T->max_nodes * sizeof(int)));
+    B200_TRY(T->lscan.reserve((T->max_nodes + 1) * sizeof(int)));
+    B200_TRY(T->leaf_tile_sum.reserve(T->max_node_tiles * sizeof(int)));
     B200_TRY(T->globals.reserve(sizeof(TreeGlobals)));
     B200_TRY(T->tile_hist.reserve(T->max_tiles * 8 * sizeof(unsigned)));
     B200_TRY(T->tile_warp_prefix.reserve(T->max_tiles * 64 * sizeof(unsigned)));
@@ -918,7 +1082,7 @@ int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_c
         entry_digit_kernel<<<egrid, ET_THREADS, 0, st>>>(
             g, L, keep, T->posm, center, meta, nstart, nsr, T->ent_idx[cur].as<int>(),
             T->ent_node[cur].as<int>(), T->digit.as<unsigned char>(), T->part_idx.as<int>(),
-            T->tile_hist.as<unsigned>(), T->tile_warp_prefix.as<unsigned>(), T->split_where.as<int>(),
+            T->slot_node.as<int>(), T->tile_hist.as<unsigned>(), T->tile_warp_prefix.as<unsigned>(), T->split_where.as<int>(),
             T->split_local.as<unsigned>());
         tile_scan_kernel<<<1, 256, 0, st>>>(g, L, T->tile_hist.as<unsigned>());
         make_children_kernel<<<sgrid, 256, 0, st>>>(g, L, T->split_node.as<int>(), T->split_where.as<int>(),
@@ -932,9 +1096,6 @@ int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_c
         B200_CUDA(cudaGetLastError());
         ctx->launches += 7;
     }
-    part_pos_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(T->part_idx.as<int>(), T->posm, (int)n,
-                                                                 T->part_pos.as<float4>(), fixed ? 1 : 0);
-    ctx->launches += 1;
     for (int L = max_depth; L >= 0; --L) {
         const double lvl_nodes = (L < 10) ? (double)(1ull << (3 * L)) : 1e30;
         const size_t nb = (size_t)((lvl_nodes < (double)T->max_nodes) ? lvl_nodes : (double)T->max_nodes);
@@ -942,8 +1103,16 @@ int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_c
         com_kernel<<<cgrid, 256, 0, st>>>(g, L, meta, center, T->part_idx.as<int>(), T->posm, com);
         ctx->launches += 1;
     }
-    pack_nodes_kernel<<<pgrid, 256, 0, st>>>(g, max_depth, com, meta, T->nodes.as<float4>());
-    ctx->launches += 1;
+    // walk-only structures: leaf particles grouped by parent, records with leaf-skipping links
+    leaf_reduce_kernel<<<pgrid, 256, 0, st>>>(g, max_depth, meta, T->leaf_tile_sum.as<int>());
+    leaf_scan_kernel<<<1, 1024, 0, st>>>(g, max_depth, T->leaf_tile_sum.as<int>());
+    leaf_apply_kernel<<<pgrid, 256, 0, st>>>(g, max_depth, meta, T->leaf_tile_sum.as<int>(), T->lscan.as<int>());
+    stored_pos_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        T->part_idx.as<int>(), T->slot_node.as<int>(), meta, T->lscan.as<int>(), T->posm, (int)n,
+        T->part_pos.as<float4>(), T->leaf_pos.as<float4>(), fixed ? 1 : 0);
+    pack_walk_kernel<<<pgrid, 256, 0, st>>>(g, max_depth, com, meta, T->lscan.as<int>(), T->nodes.as<float4>(),
+                                            T->leaf_off.as<int>());
+    ctx->launches += 5;
     B200_CUDA(cudaGetLastError());
     T->built = true;
     return B200_OK;
@@ -992,20 +1161,20 @@ int tree_walk(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* acc
     if (T->fixed) {
         if (T->counting)
             walk_warp_kernel<true, true><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
-                                                               T->nodes.as<float4>(), T->part_pos.as<float4>(), theta,
+                                                               T->nodes.as<float4>(), T->leaf_off.as<int>(), T->leaf_pos.as<float4>(), theta,
                                                                T->eps, (float*)acc3, g);
         else
             walk_warp_kernel<false, true><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
-                                                                T->nodes.as<float4>(), T->part_pos.as<float4>(), theta,
+                                                                T->nodes.as<float4>(), T->leaf_off.as<int>(), T->leaf_pos.as<float4>(), theta,
                                                                 T->eps, (float*)acc3, g);
     } else if (!per_thread) {
         if (T->counting)
             walk_warp_kernel<true, false><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
-                                                                T->nodes.as<float4>(), T->part_pos.as<float4>(), theta,
+                                                                T->nodes.as<float4>(), T->leaf_off.as<int>(), T->leaf_pos.as<float4>(), theta,
                                                                 T->eps, (float*)acc3, g);
         else
             walk_warp_kernel<false, false><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
-                                                                 T->nodes.as<float4>(), T->part_pos.as<float4>(), theta,
+                                                                 T->nodes.as<float4>(), T->leaf_off.as<int>(), T->leaf_pos.as<float4>(), theta,
                                                                  T->eps, (float*)acc3, g);
     } else if (T->counting)
         walk_kernel<true><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
