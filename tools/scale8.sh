@@ -7,10 +7,9 @@ run() { # name, nproc, args...
   echo "$name rc=$?" >> gpurun_out/scale8.log
 }
 : > gpurun_out/scale8.log
-run direct_1m_8gpu 8 --steps 5 --warmup 3
-run direct_1m_4gpu 4 --steps 5 --warmup 3
-run direct_8m_8gpu 8 --steps 2 --warmup 3 --particles 8388608
-run tree_16m_kdk_8gpu 8 --steps 5 --warmup 3 --workload tree --particles 16777216 --kdk
-run tree_16m_kdk_4gpu 4 --steps 3 --warmup 3 --workload tree --particles 16777216 --kdk
-run tree_16m_kdk_2gpu 2 --steps 3 --warmup 3 --workload tree --particles 16777216 --kdk
-nvidia-smi topo -m > gpurun_out/topo8.log 2>&1
+run tree_16m_kdk_8gpu 8 --steps 5 --warmup 3 --workload tree --particles 16777216 --kdk --no-cpu
+run tree_16m_kdk_4gpu 4 --steps 3 --warmup 3 --workload tree --particles 16777216 --kdk --no-cpu
+run tree_16m_kdk_2gpu 2 --steps 3 --warmup 3 --workload tree --particles 16777216 --kdk --no-cpu
+run direct_1m_8gpu 8 --steps 5 --warmup 3 --no-cpu
+run tree_1m_8gpu 8 --steps 5 --warmup 3 --workload tree --no-cpu
+tests/host/_bin/shard_test > gpurun_out/shard_test8.log 2>&1; echo "shard_test rc=$?" >> gpurun_out/scale8.log
