@@ -268,9 +268,12 @@ def bench_gpu(args):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) are
+    # pointed at stderr for the whole run; the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     eng = b200grav.Engine(local)
 
@@ -486,15 +489,16 @@ def bench_gpu(args):
                 src = "fallback 6532.2 GB/s (MEASURED_PEAKS.json not on this box)"
             gbs = tree_bytes / kern_s / 1e9
             line["roofline"] = {
-                "bound": "hbm", "kernel": "walk_warp_kernel (stackless theta walk; a warp walks the union of the "
-                                          "traversals of 32 Morton-adjacent targets, per-lane accept test)",
+                "bound": "hbm", "kernel": "walk_warp_kernel (stackless theta walk over internal nodes; a warp walks the "
+                                          "union of the traversals of 32 Hilbert-adjacent targets, per-lane accept test, "
+                                          "leaf particles grouped per parent)",
                 "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": traffic,
                 "peak_source": src,
                 "note": "algorithmic bytes = 32 B x nodes visited + 16 B x leaf-pair sources + 28 B x targets; most of it "
-                        "is served by L1/L2 (a warp's 32 Morton-adjacent targets visit nearly the same nodes), so this is "
+                        "is served by L1/L2 (a warp's 32 Hilbert-adjacent targets visit nearly the same nodes), so this is "
                         "an L1/L2 figure quoted against the HBM peak and can exceed it; the ncu capture of the same launch (traffic = DRAM "
                         "bytes, ncu_l2_bytes, ncu_l1_bytes; profiles/r1_walk_warp_kernel_ncu_full.txt) shows a kernel bound by "
-                        "instruction issue (73 % of issue slots, l1tex 60 %), not by any memory level",
+                        "instruction issue (81 % of issue slots, l1tex 57 %), not by any memory level",
                 "ncu_l2_bytes": l2_bytes, "ncu_l1_bytes": l1_bytes,
                 "ncu_l2_gbs": (l2_bytes / kern_s / 1e9) if l2_bytes else None,
                 "ncu_l1_gbs": (l1_bytes / kern_s / 1e9) if l1_bytes else None,
@@ -503,7 +507,8 @@ def bench_gpu(args):
             }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = run_cpu_baseline(args.workload)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         if peers is not None:

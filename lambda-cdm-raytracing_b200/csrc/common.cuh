@@ -40,6 +40,9 @@ struct DevBuf {
 
 namespace b200 { struct TreeState; struct ShardState; }   // tree.cu, shard.cu
 
+constexpr int B200_MAX_KERNEL_CFG = 64;
+struct KernelCfg { const void* fn; int blocks_per_sm; };   // per-device launch configuration of a kernel instance
+
 struct b200_ctx {
     int device = 0;
     int sm_count = 0;
@@ -48,6 +51,8 @@ struct b200_ctx {
     bool timing = false;
     float last_ms = 0.f;
     uint64_t launches = 0;
+    KernelCfg kernel_cfg[B200_MAX_KERNEL_CFG];
+    int n_kernel_cfg = 0;
 
     // direct sum scratch
     DevBuf src_tiles;       // tile-SoA sources

@@ -403,9 +403,12 @@ int launch_direct(b200_ctx* ctx, const DirectSources& src, const float4* targets
     auto kern_g = direct_kernel<R, THREADS, MINB, PERIODIC, false, POT>;
     auto kern_u = direct_kernel<R, THREADS, MINB, PERIODIC, true, POT>;
     const size_t smem = STAGES * TILE_BYTES + 64 + (size_t)3 * R * THREADS * sizeof(double);
-    static bool configured = false;     // per template instantiation
-    static int blocks_per_sm = 0;
-    if (!configured) {
+    // shared-memory opt-in and occupancy are per (device, kernel instance): cached in the context,
+    // which belongs to one device and is used by one host thread at a time
+    int blocks_per_sm = 0;
+    for (int k = 0; k < ctx->n_kernel_cfg; ++k)
+        if (ctx->kernel_cfg[k].fn == (const void*)kern_g) blocks_per_sm = ctx->kernel_cfg[k].blocks_per_sm;
+    if (blocks_per_sm == 0) {
         int bu = 0;
         B200_CUDA(cudaFuncSetAttribute(kern_g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         B200_CUDA(cudaFuncSetAttribute(kern_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -413,7 +416,11 @@ int launch_direct(b200_ctx* ctx, const DirectSources& src, const float4* targets
         B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bu, kern_u, THREADS, smem));
         if (bu < blocks_per_sm) blocks_per_sm = bu;      // one grid shape for both instances
         if (blocks_per_sm < 1) return B200_ERR_UNSUPPORTED;
-        configured = true;
+        if (ctx->n_kernel_cfg < B200_MAX_KERNEL_CFG) {
+            ctx->kernel_cfg[ctx->n_kernel_cfg].fn = (const void*)kern_g;
+            ctx->kernel_cfg[ctx->n_kernel_cfg].blocks_per_sm = blocks_per_sm;
+            ++ctx->n_kernel_cfg;
+        }
     }
     const long long T = ((long long)n_targets + BLOCK_I - 1) / BLOCK_I;
     const int NT = src.total_tiles;

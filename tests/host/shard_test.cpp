@@ -81,6 +81,10 @@ int main() {
         {"tree   65536 particles", B200ForceMethod::Tree, 65536, 3, true},
         {"direct 16384 particles, open boundary", B200ForceMethod::DirectOpen, 16384, 5, false},
         {"direct 12345 particles, periodic (ragged)", B200ForceMethod::Direct, 12345, 5, false},
+        // large enough for the 6-targets-per-thread instance (> 48 KB of shared memory: the per-device
+        // opt-in must have happened on every GPU, not only on the first one a process touched)
+        {"direct 262144 particles, open boundary", B200ForceMethod::DirectOpen, 262144, 1, false},
+        {"tree fixed-physics 50000 particles", B200ForceMethod::TreeFixed, 50000, 3, true},
     };
     for (const Case& c : cases) {
         Result single;
