@@ -71,7 +71,7 @@ struct TreeState {
     DevBuf ent_idx[2], ent_node[2], digit;
     DevBuf part_idx, part_pos;
     DevBuf nodes;                 // walk records, 32 B per node: {centre of mass, M} {first, skip, edge, leaf count}
-    DevBuf leaf_pos, leaf_off, lscan, leaf_tile_sum;   // leaf sources grouped by parent (walk-only copies)
+    DevBuf leaf_pos, leaf_off, lscan, pscan, leaf_tile_sum;   // leaf sources grouped by parent, pair-interleaved (walk-only)
     DevBuf slot_node;             // node that stores slot q of part_idx
     DevBuf globals;
     DevBuf tile_hist, tile_warp_prefix, node_tile_sum;
@@ -81,7 +81,7 @@ struct TreeState {
     bool order_valid = false;
     void release() {
         DevBuf* all[] = {&center, &com, &meta, &nstart, &ncount, &nsplit_rank, &ent_idx[0],
-                         &ent_idx[1], &ent_node[0], &ent_node[1], &digit, &part_idx, &part_pos, &nodes, &leaf_pos, &leaf_off, &lscan, &leaf_tile_sum, &slot_node,
+                         &ent_idx[1], &ent_node[0], &ent_node[1], &digit, &part_idx, &part_pos, &nodes, &leaf_pos, &leaf_off, &lscan, &pscan, &leaf_tile_sum, &slot_node,
                          &globals, &tile_hist, &tile_warp_prefix, &node_tile_sum, &split_node,
                          &split_where, &split_local, &split_cstart, &keys, &keys_sorted, &perm,
                          &sort_scratch, &order};
@@ -537,13 +537,23 @@ entry_scatter_kernel(const TreeGlobals* __restrict__ g, int level, const int4* _
 }
 
 // ------------------------------------------------------- centre of mass ---
+__device__ __forceinline__ int tree_node_count(const TreeGlobals* g, int max_depth) {
+    int nn = 0;
+    for (int L = 0; L <= max_depth; ++L)
+        if (g->lv[L].node_end > g->lv[L].node_begin) nn = g->lv[L].node_end;
+    return nn;
+}
+
 // Stored particles in stored order, (x, y, z, particle index bits) -- or, in the fixed mode, the
 // float4 as it is (x, y, z, mass): that walk uses real masses and needs no self test -- and, for the
-// slots that belong to leaf nodes, a second copy in the walk's per-parent layout (lscan).
+// slots that belong to leaf nodes, a second copy in the walk's layout: the leaf particles of one
+// parent are contiguous and PAIR-INTERLEAVED, pair p = {x0 x1 y0 y1} {z0 z1 w0 w1}, so that one
+// packed-FP32 instruction of the walk handles two sources (lscan: rank of a leaf's first particle
+// among all leaf particles; pscan: first pair of a sibling group).
 __global__ void stored_pos_kernel(const int* __restrict__ part_idx, const int* __restrict__ slot_node,
                                   const int4* __restrict__ meta, const int* __restrict__ lscan,
-                                  const float4* __restrict__ posm, int n, float4* __restrict__ part_pos,
-                                  float4* __restrict__ leaf_pos, int fixed) {
+                                  const int* __restrict__ pscan, const float4* __restrict__ posm, int n,
+                                  float4* __restrict__ part_pos, float* __restrict__ leaf_pairs, int fixed) {
     int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     const int idx = part_idx[q];
@@ -552,7 +562,28 @@ __global__ void stored_pos_kernel(const int* __restrict__ part_idx, const int* _
     part_pos[q] = p;
     const int k = slot_node[q];
     const int4 m = meta[k];
-    if (m.x < 0) leaf_pos[lscan[k] + (q - m.z)] = p;
+    if (m.x >= 0) return;                                       // an orphan: never a source
+    int r = lscan[k] + (q - m.z), pair0 = 0;                    // k == 0: the tree is one leaf
+    if (k > 0) { const int grp = (k - 1) >> 3; r -= lscan[1 + 8 * grp]; pair0 = pscan[grp]; }
+    float* dst = leaf_pairs + (size_t)(pair0 + (r >> 1)) * 8 + (r & 1);
+    dst[0] = p.x; dst[2] = p.y; dst[4] = p.z; dst[6] = p.w;
+}
+// the unused half of a group's last pair when its particle count is odd: a source that adds exactly 0
+// (rinv^3 underflows; index -1 / mass 0)
+__global__ void __launch_bounds__(256)
+pair_pad_kernel(const TreeGlobals* __restrict__ g, int max_depth, const int* __restrict__ lscan,
+                const int* __restrict__ pscan, float* __restrict__ leaf_pairs, int fixed) {
+    const int nn = tree_node_count(g, max_depth);
+    const int groups = (nn - 1) / 8;
+    const int items = groups > 0 ? groups : 1;                  // no groups: the root leaf
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < items; j += gridDim.x * blockDim.x) {
+        const int cnt = groups > 0 ? lscan[9 + 8 * j] - lscan[1 + 8 * j] : lscan[1];
+        if ((cnt & 1) == 0) continue;
+        const int pair0 = groups > 0 ? pscan[j] : 0;
+        float* dst = leaf_pairs + (size_t)(pair0 + (cnt >> 1)) * 8 + 1;
+        dst[0] = 1.0e18f; dst[2] = 1.0e18f; dst[4] = 1.0e18f;
+        dst[6] = fixed ? 0.0f : __int_as_float(-1);
+    }
 }
 
 // compute_center_of_mass (:196-243): one rounding per operation, reference order.
@@ -639,27 +670,32 @@ com_kernel(const TreeGlobals* __restrict__ g, int level, int4* __restrict__ meta
 // order; orphans stored at internal nodes are left out -- they are never sources) and X's record
 // carries the range.  The links of the records skip leaf nodes: `first` = first INTERNAL node in
 // depth-first order inside or after X's children, `skip` = first internal node after X's subtree.
-__device__ __forceinline__ int tree_node_count(const TreeGlobals* g, int max_depth) {
-    int nn = 0;
-    for (int L = 0; L <= max_depth; ++L)
-        if (g->lv[L].node_end > g->lv[L].node_begin) nn = g->lv[L].node_end;
-    return nn;
+// The two scans of the build tail share one set of kernels:
+//   MODE 0, item = node k:           particles stored in k if k is a leaf            -> lscan
+//   MODE 1, item = sibling group j   (nodes 1+8j .. 8+8j, the children of one internal node):
+//                                    source PAIRS of the group = ceil(leaf particles / 2) -> pscan
+template <int MODE>
+__device__ __forceinline__ int scan_items(int nn) { return MODE == 0 ? nn : (nn - 1) / 8; }
+template <int MODE>
+__device__ __forceinline__ int scan_value(int k, const int4* __restrict__ meta, const int* __restrict__ lscan) {
+    if (MODE == 0) { const int4 m = meta[k]; return m.x < 0 ? m.w : 0; }
+    return (lscan[9 + 8 * k] - lscan[1 + 8 * k] + 1) >> 1;
 }
-__device__ __forceinline__ int leaf_particles(const int4 m) { return m.x < 0 ? m.w : 0; }
 
 // exclusive scan over node ids of the leaf particle counts: tile sums, scan of the sums, apply
+template <int MODE>
 __global__ void __launch_bounds__(256)
 leaf_reduce_kernel(const TreeGlobals* __restrict__ g, int max_depth, const int4* __restrict__ meta,
-                   int* __restrict__ tile_sum) {
+                   const int* __restrict__ lscan, int* __restrict__ tile_sum) {
     __shared__ int sh[8];
-    const int nn = tree_node_count(g, max_depth);
+    const int nn = scan_items<MODE>(tree_node_count(g, max_depth));
     const int n_tiles = (nn + NODE_TILE - 1) / NODE_TILE;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int v = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int k = tile * NODE_TILE + j * 256 + threadIdx.x;
-            if (k < nn) v += leaf_particles(meta[k]);
+            if (k < nn) v += scan_value<MODE>(k, meta, lscan);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
@@ -673,11 +709,12 @@ leaf_reduce_kernel(const TreeGlobals* __restrict__ g, int max_depth, const int4*
         }
     }
 }
+template <int MODE>
 __global__ void __launch_bounds__(1024)
 leaf_scan_kernel(const TreeGlobals* __restrict__ g, int max_depth, int* __restrict__ tile_sum) {
     __shared__ int wsum[32];
     __shared__ int carry_s, chunk_s;
-    const int nn = tree_node_count(g, max_depth);
+    const int nn = scan_items<MODE>(tree_node_count(g, max_depth));
     const int n_tiles = (nn + NODE_TILE - 1) / NODE_TILE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry_s = 0;
@@ -711,13 +748,15 @@ leaf_scan_kernel(const TreeGlobals* __restrict__ g, int max_depth, int* __restri
         __syncthreads();
     }
 }
-// lscan[k] = number of leaf particles in nodes < k (k = 0..nn); one tile of 2048 nodes per CTA pass,
-// thread t owns nodes [8t, 8t+8) of the tile so the in-tile scan is a thread-serial + warp + CTA scan
+// out[k] = sum of the values of items < k (k = 0..items); one tile of 2048 items per CTA pass,
+// thread t owns items [8t, 8t+8) of the tile so the in-tile scan is a thread-serial + warp + CTA scan
+template <int MODE>
 __global__ void __launch_bounds__(256)
 leaf_apply_kernel(const TreeGlobals* __restrict__ g, int max_depth, const int4* __restrict__ meta,
-                  const int* __restrict__ tile_sum, int* __restrict__ lscan) {
+                  const int* __restrict__ lscan_in, const int* __restrict__ tile_sum, int* __restrict__ lscan) {
     __shared__ int wsum[8];
-    const int nn = tree_node_count(g, max_depth);
+    const int nn = scan_items<MODE>(tree_node_count(g, max_depth));
+    if (nn == 0 && blockIdx.x == 0 && threadIdx.x == 0) lscan[0] = 0;
     const int n_tiles = (nn + NODE_TILE - 1) / NODE_TILE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -725,7 +764,7 @@ leaf_apply_kernel(const TreeGlobals* __restrict__ g, int max_depth, const int4* 
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int k = tile * NODE_TILE + threadIdx.x * 8 + j;
-            v[j] = (k < nn) ? leaf_particles(meta[k]) : 0;
+            v[j] = (k < nn) ? scan_value<MODE>(k, meta, lscan_in) : 0;
             tsum += v[j];
         }
         int x = tsum;
@@ -752,7 +791,7 @@ leaf_apply_kernel(const TreeGlobals* __restrict__ g, int max_depth, const int4* 
 constexpr int ROOT_LEAF = -2;
 __global__ void __launch_bounds__(256)
 pack_walk_kernel(const TreeGlobals* __restrict__ g, int max_depth, const float4* __restrict__ com,
-                 const int4* __restrict__ meta, const int* __restrict__ lscan,
+                 const int4* __restrict__ meta, const int* __restrict__ lscan, const int* __restrict__ pscan,
                  float4* __restrict__ nodes, int* __restrict__ leaf_off) {
     const int nn = tree_node_count(g, max_depth);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nn; k += gridDim.x * blockDim.x) {
@@ -766,8 +805,8 @@ pack_walk_kernel(const TreeGlobals* __restrict__ g, int max_depth, const float4*
             while (first >= 0 && meta[first].x < 0) first = meta[first].y;
             skip = m.y;
             while (skip >= 0 && meta[skip].x < 0) skip = meta[skip].y;
-            loff = lscan[m.x];
-            lcnt = lscan[m.x + 8] - loff;
+            loff = pscan[(m.x - 1) >> 3];                   // first source pair of the children
+            lcnt = lscan[m.x + 8] - lscan[m.x];             // leaf particles among them
         }
         nodes[2 * k] = com[k];
         nodes[2 * k + 1] = make_float4(__int_as_float(first), __int_as_float(skip), __int_as_float(m.w),
@@ -883,42 +922,84 @@ __device__ __forceinline__ bool accept_cell_sq(float size, float d2, float theta
 
 // FIXED: the "fixed physics" walk -- leaf sources carry their real mass in .w and there is no
 // self test (with eps > 0 the self pair adds exactly 0; it is counted), softening = eps.
+__device__ __forceinline__ unsigned long long w_pk(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void w_unpk(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long w_add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long w_mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long w_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 template <bool COUNT, bool FIXED>
 __global__ void __launch_bounds__(128)
 walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order, int i0, int n_targets,
                  const float4* __restrict__ nodes, const int* __restrict__ leaf_off,
-                 const float4* __restrict__ leaf_pos, float theta, float eps,
+                 const ulonglong2* __restrict__ leaf_pairs, float theta, float eps,
                  float* __restrict__ acc3, TreeGlobals* __restrict__ g) {
+    typedef unsigned long long u64;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = t < n_targets;
     const int i = valid ? (order ? order[t] : (i0 + t)) : -1;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) p = posm[i];
-    float ax = 0.f, ay = 0.f, az = 0.f;
+    float ax = 0.f, ay = 0.f, az = 0.f;                                  // cells
+    u64 ax2 = 0ull, ay2 = 0ull, az2 = 0ull;                              // leaf pairs, two sources per lane-op
     const float eps2 = FIXED ? eps * eps : __fmul_rn(0.01f, 0.01f);      // :281-282, :334-335
     const float theta2 = theta > 0.f ? theta * theta : 0.f;              // theta <= 0: nothing is ever accepted
+    const u64 eps2_2 = w_pk(eps2, eps2);
+    const u64 npx = w_pk(-p.x, -p.x), npy = w_pk(-p.y, -p.y), npz = w_pk(-p.z, -p.z);
     unsigned long long c_vis = valid ? 1 : 0, c_pc = 0, c_pp = 0;        // the root is visited by everyone
     constexpr int AWAKE = -2, NEVER = -3;
     int wake = valid ? AWAKE : NEVER;     // node id at which a sleeping lane resumes
 
-    // the particles of a leaf range against this lane's target; `on` = the lane takes part.
-    // Branch-free rows: a lane that is out, or is the particle itself (:321), adds f = 0.
+    // `cnt` leaf particles stored as pairs from pair `q` on, against this lane's target; on_lane = the
+    // lane takes part.  Branch-free packed rows: a lane that is out, or is the particle itself (:321), or a
+    // padding slot, adds f = 0.
     auto leaf_range = [&](int q, int cnt, bool on_lane) {
-        auto pair = [&](const float4& s) {
-            const float dx = s.x - p.x, dy = s.y - p.y, dz = s.z - p.z;
-            const float r2 = dx * dx + dy * dy + dz * dz + eps2;
-            const float rinv = rsqrt_fast(r2);
-            const bool on = FIXED ? on_lane : (on_lane && __float_as_int(s.w) != i);
-            const float f = on ? (FIXED ? s.w * rinv * rinv * rinv : rinv * rinv * rinv) : 0.f;   // :253, :340
-            ax += f * dx; ay += f * dy; az += f * dz;
-            if (COUNT && on) ++c_pp;
+        auto row2 = [&](const ulonglong2& a, const ulonglong2& b) {      // a = {x0 x1 | y0 y1}, b = {z0 z1 | w0 w1}
+            const u64 dx = w_add2(a.x, npx), dy = w_add2(a.y, npy), dz = w_add2(b.x, npz);
+            u64 r2 = w_fma2(dx, dx, eps2_2);
+            r2 = w_fma2(dy, dy, r2);
+            r2 = w_fma2(dz, dz, r2);
+            float r2a, r2b, w0, w1;
+            w_unpk(r2, r2a, r2b);
+            w_unpk(b.y, w0, w1);
+            const u64 rinv = w_pk(rsqrt_fast(r2a), rsqrt_fast(r2b));
+            u64 f = w_mul2(w_mul2(rinv, rinv), rinv);                    // unit mass (:253, :340)
+            if (FIXED) f = w_mul2(f, b.y);
+            const bool on0 = FIXED ? on_lane : (on_lane && __float_as_int(w0) != i);
+            const bool on1 = FIXED ? on_lane : (on_lane && __float_as_int(w1) != i);
+            float f0, f1;
+            w_unpk(f, f0, f1);
+            f = w_pk(on0 ? f0 : 0.f, on1 ? f1 : 0.f);
+            ax2 = w_fma2(f, dx, ax2); ay2 = w_fma2(f, dy, ay2); az2 = w_fma2(f, dz, az2);
+            if (COUNT && !FIXED) c_pp += (on0 && __float_as_int(w0) >= 0) + (on1 && __float_as_int(w1) >= 0);
         };
-        const int qe = q + cnt;
-        for (; q + 4 <= qe; q += 4) {                    // 4 broadcast loads in flight, then 4 rows
-            const float4 s0 = leaf_pos[q], s1 = leaf_pos[q + 1], s2 = leaf_pos[q + 2], s3 = leaf_pos[q + 3];
-            pair(s0); pair(s1); pair(s2); pair(s3);
+        if (COUNT && FIXED && on_lane) c_pp += cnt;
+        const ulonglong2* src = leaf_pairs + 2 * (size_t)q;
+        const int np = (cnt + 1) >> 1;
+        int k2 = 0;
+        for (; k2 + 2 <= np; k2 += 2) {                  // 4 broadcast loads in flight, then 2 packed rows
+            const ulonglong2 a0 = src[2 * k2], b0 = src[2 * k2 + 1], a1 = src[2 * k2 + 2], b1 = src[2 * k2 + 3];
+            row2(a0, b0); row2(a1, b1);
         }
-        for (; q < qe; ++q) pair(leaf_pos[q]);
+        if (k2 < np) row2(src[2 * k2], src[2 * k2 + 1]);
     };
 
     int k = 0;
@@ -956,6 +1037,10 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
         }
     }
     if (valid) {
+        float lo, hi;
+        w_unpk(ax2, lo, hi); ax += lo + hi;
+        w_unpk(ay2, lo, hi); ay += lo + hi;
+        w_unpk(az2, lo, hi); az += lo + hi;
         const size_t o = (size_t)(i - i0) * 3;
         acc3[o + 0] = ax; acc3[o + 1] = ay; acc3[o + 2] = az;
     }
@@ -1034,7 +1119,8 @@ int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_c
     B200_TRY(T->part_idx.reserve(n * sizeof(int)));
     B200_TRY(T->part_pos.reserve(n * sizeof(float4)));
     B200_TRY(T->nodes.reserve(T->max_nodes * 2 * sizeof(float4)));
-    B200_TRY(T->leaf_pos.reserve(n * sizeof(float4)));
+    B200_TRY(T->leaf_pos.reserve((n + T->max_split + 2) * sizeof(float4)));     // pair layout: <= 1 pad slot per parent
+    B200_TRY(T->pscan.reserve((T->max_split + 2) * sizeof(int)));
     B200_TRY(T->slot_node.reserve(n * sizeof(int)));
     B200_TRY(T->leaf_off.reserve(T->max_nodes * sizeof(int)));
     B200_TRY(T->lscan.reserve((T->max_nodes + 1) * sizeof(int)));
@@ -1104,15 +1190,22 @@ int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_c
         ctx->launches += 1;
     }
     // walk-only structures: leaf particles grouped by parent, records with leaf-skipping links
-    leaf_reduce_kernel<<<pgrid, 256, 0, st>>>(g, max_depth, meta, T->leaf_tile_sum.as<int>());
-    leaf_scan_kernel<<<1, 1024, 0, st>>>(g, max_depth, T->leaf_tile_sum.as<int>());
-    leaf_apply_kernel<<<pgrid, 256, 0, st>>>(g, max_depth, meta, T->leaf_tile_sum.as<int>(), T->lscan.as<int>());
+    int* lscan = T->lscan.as<int>();
+    int* pscan = T->pscan.as<int>();
+    int* tsum = T->leaf_tile_sum.as<int>();
+    leaf_reduce_kernel<0><<<pgrid, 256, 0, st>>>(g, max_depth, meta, nullptr, tsum);
+    leaf_scan_kernel<0><<<1, 1024, 0, st>>>(g, max_depth, tsum);
+    leaf_apply_kernel<0><<<pgrid, 256, 0, st>>>(g, max_depth, meta, nullptr, tsum, lscan);
+    leaf_reduce_kernel<1><<<pgrid, 256, 0, st>>>(g, max_depth, meta, lscan, tsum);
+    leaf_scan_kernel<1><<<1, 1024, 0, st>>>(g, max_depth, tsum);
+    leaf_apply_kernel<1><<<pgrid, 256, 0, st>>>(g, max_depth, meta, lscan, tsum, pscan);
     stored_pos_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-        T->part_idx.as<int>(), T->slot_node.as<int>(), meta, T->lscan.as<int>(), T->posm, (int)n,
-        T->part_pos.as<float4>(), T->leaf_pos.as<float4>(), fixed ? 1 : 0);
-    pack_walk_kernel<<<pgrid, 256, 0, st>>>(g, max_depth, com, meta, T->lscan.as<int>(), T->nodes.as<float4>(),
+        T->part_idx.as<int>(), T->slot_node.as<int>(), meta, lscan, pscan, T->posm, (int)n,
+        T->part_pos.as<float4>(), T->leaf_pos.as<float>(), fixed ? 1 : 0);
+    pair_pad_kernel<<<pgrid, 256, 0, st>>>(g, max_depth, lscan, pscan, T->leaf_pos.as<float>(), fixed ? 1 : 0);
+    pack_walk_kernel<<<pgrid, 256, 0, st>>>(g, max_depth, com, meta, lscan, pscan, T->nodes.as<float4>(),
                                             T->leaf_off.as<int>());
-    ctx->launches += 5;
+    ctx->launches += 9;
     B200_CUDA(cudaGetLastError());
     T->built = true;
     return B200_OK;
@@ -1161,20 +1254,20 @@ int tree_walk(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* acc
     if (T->fixed) {
         if (T->counting)
             walk_warp_kernel<true, true><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
-                                                               T->nodes.as<float4>(), T->leaf_off.as<int>(), T->leaf_pos.as<float4>(), theta,
+                                                               T->nodes.as<float4>(), T->leaf_off.as<int>(), T->leaf_pos.as<ulonglong2>(), theta,
                                                                T->eps, (float*)acc3, g);
         else
             walk_warp_kernel<false, true><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
-                                                                T->nodes.as<float4>(), T->leaf_off.as<int>(), T->leaf_pos.as<float4>(), theta,
+                                                                T->nodes.as<float4>(), T->leaf_off.as<int>(), T->leaf_pos.as<ulonglong2>(), theta,
                                                                 T->eps, (float*)acc3, g);
     } else if (!per_thread) {
         if (T->counting)
             walk_warp_kernel<true, false><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
-                                                                T->nodes.as<float4>(), T->leaf_off.as<int>(), T->leaf_pos.as<float4>(), theta,
+                                                                T->nodes.as<float4>(), T->leaf_off.as<int>(), T->leaf_pos.as<ulonglong2>(), theta,
                                                                 T->eps, (float*)acc3, g);
         else
             walk_warp_kernel<false, false><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
-                                                                 T->nodes.as<float4>(), T->leaf_off.as<int>(), T->leaf_pos.as<float4>(), theta,
+                                                                 T->nodes.as<float4>(), T->leaf_off.as<int>(), T->leaf_pos.as<ulonglong2>(), theta,
                                                                  T->eps, (float*)acc3, g);
     } else if (T->counting)
         walk_kernel<true><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,

@@ -44,7 +44,7 @@ class B200Error(RuntimeError):
 
 
 def load_library(path=None):
-    path = path or LIB_PATH
+    path = path or os.environ.get("B200GRAV_LIB") or LIB_PATH      # B200GRAV_LIB: tuning hook (variant builds)
     if not os.path.exists(path):
         raise B200Error(
             f"{path} is missing: build it with `make -C lambda-cdm-raytracing_b200/csrc` "
