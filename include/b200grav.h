@@ -122,6 +122,21 @@ int b200_energy_dev(b200_ctx* ctx, const void* posm4, size_t n_sources, size_t i
                     const void* vel3, float eps, float box, double* kinetic, double* potential,
                     void* stream);
 
+/* Tree-vs-direct error measure of the reference's Barnes-Hut example
+ * (examples/barnes_hut_test.cu:173-189): per particle |a_test - a_ref| / (|a_ref| + 1e-10),
+ * its mean and its maximum over n particles; acc_*: float[3n] (device).  Blocking. */
+int b200_force_error_dev(b200_ctx* ctx, const void* acc_test, const void* acc_ref, size_t n,
+                         double* avg_rel_error, double* max_rel_error, void* stream);
+/* Matter power spectrum of the particles, PowerSpectrumAnalyzer::compute_power_spectrum
+ * (src/analysis/power_spectrum.cu:53-84) on the device: cloud-in-cell assignment on a grid^3
+ * mesh (:86-134; positions taken modulo the box), density contrast (:161-180), forward FFT / grid^3
+ * (cuFFT, bound at run time), shells of width 2 pi / box with half-spectrum multiplicities, x box^3,
+ * optional subtraction of box^3 / grid^3 (:207-285).  Outputs (HOST, grid/2 entries each, any may be
+ * NULL): bin centres k [h/Mpc], P(k) [(Mpc/h)^3], modes per bin.  Blocking. */
+int b200_power_spectrum_dev(b200_ctx* ctx, const void* posm4, size_t n, int grid, float box,
+                            int mass_weighted, int shot_noise_correction, float* k_out, float* p_out,
+                            int* count_out, void* stream);
+
 /* ---- Barnes-Hut (rows T1-T6) ----------------------------------------------
  * Morton keys: replaces compute_morton_codes_kernel + morton3D
  * (src/forces/barnes_hut_tree.cu:33-55, include/forces/barnes_hut_tree.hpp:11-27);

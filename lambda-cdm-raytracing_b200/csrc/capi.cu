@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "diag.cuh"
 #include "direct.cuh"
 #include "ics.cuh"
 #include "leapfrog.cuh"
@@ -157,6 +158,27 @@ int b200_energy_dev(b200_ctx* ctx, const void* posm4, size_t n_sources, size_t i
     *kinetic = h[0];
     *potential = h[1];
     return B200_OK;
+}
+
+int b200_force_error_dev(b200_ctx* ctx, const void* acc_test, const void* acc_ref, size_t n,
+                         double* avg_rel_error, double* max_rel_error, void* stream) {
+    if (!ctx || !avg_rel_error || !max_rel_error) return B200_ERR_INVALID;
+    *avg_rel_error = *max_rel_error = 0.0;
+    if (n == 0) return B200_OK;
+    if (!acc_test || !acc_ref) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return force_error(ctx, acc_test, acc_ref, n, avg_rel_error, max_rel_error, pick_stream(ctx, stream));
+}
+
+int b200_power_spectrum_dev(b200_ctx* ctx, const void* posm4, size_t n, int grid, float box,
+                            int mass_weighted, int shot_noise_correction, float* k_out, float* p_out,
+                            int* count_out, void* stream) {
+    if (!ctx || !posm4 || n == 0 || grid < 4 || (grid & 1) || grid > 2048 || !(box > 0.f)) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    const int s = power_spectrum(ctx, posm4, n, grid, box, mass_weighted, shot_noise_correction, k_out, p_out,
+                                 count_out, pick_stream(ctx, stream));
+    ctx->ic_wk.release(); ctx->ic_psi.release();        // two G^3 arrays: a one-off
+    return s;
 }
 
 size_t b200_tiles_bytes(size_t n) { return direct_tiles_bytes(n); }

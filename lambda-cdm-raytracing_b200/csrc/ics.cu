@@ -21,7 +21,6 @@
 //     psi(x) = inverse FFT, one axis at a time                            (cuFFT C2R)
 // so that <|delta_k|^2> = V P(k) in the reference's convention (:241-244) and
 // div psi = -delta.  cuFFT (a plain library FFT, off the hot path) is bound at run time.
-#include <cufft.h>
 #include <dlfcn.h>
 #include <math.h>
 #include <string.h>
@@ -29,21 +28,13 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "fft.cuh"
 #include "ics.cuh"
 
 namespace b200 {
 
 namespace {
 
-struct CufftApi {
-    void* handle = nullptr;
-    cufftResult (*Plan3d)(cufftHandle*, int, int, int, cufftType) = nullptr;
-    cufftResult (*SetStream)(cufftHandle, cudaStream_t) = nullptr;
-    cufftResult (*ExecR2C)(cufftHandle, cufftReal*, cufftComplex*) = nullptr;
-    cufftResult (*ExecC2R)(cufftHandle, cufftComplex*, cufftReal*) = nullptr;
-    cufftResult (*Destroy)(cufftHandle) = nullptr;
-    bool ok = false;
-};
 CufftApi g_fft;
 std::once_flag g_fft_once;
 
@@ -65,15 +56,6 @@ void load_cufft() {
 #undef B200_SYM
     g_fft.ok = true;
 }
-const CufftApi* cufft() {
-    std::call_once(g_fft_once, load_cufft);
-    return g_fft.ok ? &g_fft : nullptr;
-}
-#define B200_FFT(call)                                           \
-    do {                                                         \
-        cufftResult r__ = (call);                                \
-        if (r__ != CUFFT_SUCCESS) return 3000 + (int)r__;        \
-    } while (0)
 
 // ---- host scalars (double) ---------------------------------------------------
 double transfer_bbks(double k, double gamma) {                  // initial_conditions.cpp:83-96
@@ -201,6 +183,11 @@ __global__ void ic_particles_kernel(const float* __restrict__ px, const float* _
 }
 
 }  // namespace
+
+const CufftApi* cufft() {
+    std::call_once(g_fft_once, load_cufft);
+    return g_fft.ok ? &g_fft : nullptr;
+}
 
 int zeldovich_ics(b200_ctx* ctx, const b200_ic_params* p, size_t n_particles, void* posm4, void* vel3,
                   double* stats_out, cudaStream_t st) {

@@ -26,7 +26,7 @@ EXPORTS = [
     "b200_device_alloc", "b200_device_free", "b200_memcpy_h2d", "b200_memcpy_d2h", "b200_unpack_pos3_dev", "b200_ipc_export", "b200_ipc_open", "b200_ipc_close",
     "b200_shard_range", "b200_shard_unique_id", "b200_shard_init", "b200_shard_finalize", "b200_shard_info",
     "b200_allgather_sources_dev", "b200_allreduce_sum_f64", "b200_direct_potential_dev", "b200_energy_dev",
-    "b200_ic_params_default", "b200_zeldovich_ics_dev", "b200_tree_build_fixed_dev", "b200_tree_forces_fixed_host",
+    "b200_ic_params_default", "b200_zeldovich_ics_dev", "b200_force_error_dev", "b200_power_spectrum_dev", "b200_tree_build_fixed_dev", "b200_tree_forces_fixed_host",
     "b200_fp32_peak_probe", "b200_last_kernel_ms", "b200_set_timing", "b200_launch_count",
 ]
 
@@ -104,6 +104,8 @@ def load_library(path=None):
     L.b200_ic_params_default.argtypes = [C.POINTER(ICParams)]
     L.b200_ic_params_default.restype = None
     L.b200_zeldovich_ics_dev.argtypes = [vp, C.POINTER(ICParams), sz, vp, vp, C.POINTER(f64), vp]
+    L.b200_force_error_dev.argtypes = [vp, vp, vp, sz, C.POINTER(f64), C.POINTER(f64), vp]
+    L.b200_power_spectrum_dev.argtypes = [vp, vp, sz, i32, f32, i32, i32, vp, vp, vp, vp]
     L.b200_fp32_peak_probe.argtypes = [vp, i32, i32, C.POINTER(f64), C.POINTER(f32)]
     L.b200_last_kernel_ms.argtypes = [vp, C.POINTER(f32)]
     L.b200_set_timing.argtypes = [vp, i32]
@@ -324,6 +326,24 @@ class Engine:
         st = (C.c_double * 4)()
         self._check(self.L.b200_zeldovich_ics_dev(self._h, C.byref(p), n, _ptr(posm), _ptr(vel), st, _stream(stream)))
         return tuple(st)
+
+    # ---- diagnostics ----
+    def force_error_dev(self, acc_test, acc_ref, n=None, stream=None):
+        """(mean, max) of |a_test - a_ref| / (|a_ref| + 1e-10) over the particles."""
+        n = acc_ref.shape[0] if n is None else n
+        a, m = C.c_double(), C.c_double()
+        self._check(self.L.b200_force_error_dev(self._h, _ptr(acc_test), _ptr(acc_ref), n, C.byref(a), C.byref(m),
+                                                _stream(stream)))
+        return a.value, m.value
+
+    def power_spectrum_dev(self, posm, grid, box, mass_weighted=True, shot_noise_correction=True, n=None, stream=None):
+        """(k, P(k), modes per bin) of the particles: CIC mesh of grid^3, bins of width 2 pi / box."""
+        n = posm.shape[0] if n is None else n
+        nb = grid // 2
+        k, p, c = np.empty(nb, np.float32), np.empty(nb, np.float32), np.empty(nb, np.int32)
+        self._check(self.L.b200_power_spectrum_dev(self._h, _ptr(posm), n, grid, box, int(mass_weighted),
+                                                   int(shot_noise_correction), _ptr(k), _ptr(p), _ptr(c), _stream(stream)))
+        return k, p, c
 
     # ---- energy diagnostic ----
     def direct_potential_dev(self, posm, phi, i0=0, n_targets=None, eps=0.01, box=0.0, stream=None):
