@@ -28,6 +28,7 @@
 // canonical numbering the CPU oracle exports, which is what makes the
 // bit-exact topology test a plain array compare.
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -79,7 +80,36 @@ struct TreeState {
     DevBuf keys, keys_sorted, perm, sort_scratch, order;
     size_t order_i0 = 0, order_n = 0;
     bool order_valid = false;
+    // The build is a fixed sequence of ~200 launches with no host decision in it: captured once into
+    // a CUDA graph and replayed while (inputs pointer, sizes, parameters, scratch buffers) stay the same.
+    cudaGraphExec_t graph_exec = nullptr;
+    size_t graph_key = 0;
+    int graph_launches = 0;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    size_t fingerprint() const {
+        size_t h = 1469598103934665603ull;
+        auto mix = [&h](size_t v) { h = (h ^ v) * 1099511628211ull; };
+        mix((size_t)posm); mix(n); mix((size_t)cap); mix((size_t)max_depth); mix(fixed ? 1 : 0);
+        unsigned bb, eb;
+        memcpy(&bb, &box, 4); memcpy(&eb, &eps, 4);
+        mix(bb); mix(eb);
+        const DevBuf* all[] = {&center, &com, &meta, &nstart, &ncount, &nsplit_rank, &ent_idx[0], &ent_idx[1],
+                               &ent_node[0], &ent_node[1], &digit, &part_idx, &part_pos, &nodes, &leaf_pos,
+                               &leaf_off, &lscan, &pscan, &leaf_tile_sum, &slot_node, &globals, &tile_hist,
+                               &tile_warp_prefix, &node_tile_sum, &split_node, &split_where, &split_local,
+                               &split_cstart};
+        for (const DevBuf* b : all) mix((size_t)b->p);
+        return h;
+    }
+    void drop_graph() {
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        graph_exec = nullptr; graph_key = 0;
+    }
     void release() {
+        drop_graph();
+        if (ev_in) cudaEventDestroy(ev_in);
+        if (ev_out) cudaEventDestroy(ev_out);
+        ev_in = ev_out = nullptr;
         DevBuf* all[] = {&center, &com, &meta, &nstart, &ncount, &nsplit_rank, &ent_idx[0],
                          &ent_idx[1], &ent_node[0], &ent_node[1], &digit, &part_idx, &part_pos, &nodes, &leaf_pos, &leaf_off, &lscan, &pscan, &leaf_tile_sum, &slot_node,
                          &globals, &tile_hist, &tile_warp_prefix, &node_tile_sum, &split_node,
@@ -1084,6 +1114,8 @@ void tree_destroy(b200_ctx* ctx) {
     }
 }
 
+static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st);
+
 int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_cap, int max_depth,
                bool fixed, float eps, cudaStream_t st) {
     if (!posm4 || n == 0) return B200_ERR_INVALID;
@@ -1134,6 +1166,61 @@ int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_c
     B200_TRY(T->split_local.reserve(T->max_split * 8 * sizeof(unsigned)));
     B200_TRY(T->split_cstart.reserve(T->max_split * 8 * sizeof(unsigned)));
 
+    // graph replay (B200_NO_GRAPH=1: plain launches).  The graph runs on the context's own stream,
+    // ordered after / before the caller's stream by events; a caller that is itself capturing gets
+    // the plain launches on its stream instead (they become part of its graph).
+    cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+    if (st != nullptr && cudaStreamIsCapturing(st, &cap_status) != cudaSuccess) { cudaGetLastError(); cap_status = cudaStreamCaptureStatusNone; }
+    if (getenv("B200_NO_GRAPH") == nullptr && cap_status == cudaStreamCaptureStatusNone && ctx->stream != nullptr) {
+        const size_t key = T->fingerprint();
+        if (T->graph_exec == nullptr || T->graph_key != key) {
+            T->drop_graph();
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const uint64_t before = ctx->launches;
+                const int rc = tree_enqueue(ctx, T, ctx->stream);
+                const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+                T->graph_launches = (int)(ctx->launches - before);
+                ctx->launches = before;
+                if (rc == B200_OK && ce == cudaSuccess && graph != nullptr &&
+                    cudaGraphInstantiate(&T->graph_exec, graph, 0) == cudaSuccess)
+                    T->graph_key = key;
+                else
+                    T->graph_exec = nullptr;
+                if (graph) cudaGraphDestroy(graph);
+            }
+            cudaGetLastError();
+        }
+        if (T->graph_exec != nullptr) {
+            if (!T->ev_in) {
+                B200_CUDA(cudaEventCreateWithFlags(&T->ev_in, cudaEventDisableTiming));
+                B200_CUDA(cudaEventCreateWithFlags(&T->ev_out, cudaEventDisableTiming));
+            }
+            if (st != ctx->stream) {
+                B200_CUDA(cudaEventRecord(T->ev_in, st));
+                B200_CUDA(cudaStreamWaitEvent(ctx->stream, T->ev_in, 0));
+            }
+            B200_CUDA(cudaGraphLaunch(T->graph_exec, ctx->stream));
+            if (st != ctx->stream) {
+                B200_CUDA(cudaEventRecord(T->ev_out, ctx->stream));
+                B200_CUDA(cudaStreamWaitEvent(st, T->ev_out, 0));
+            }
+            ctx->launches += (uint64_t)T->graph_launches;
+            T->built = true;
+            return B200_OK;
+        }
+    }
+    B200_TRY(tree_enqueue(ctx, T, st));
+    T->built = true;
+    return B200_OK;
+}
+
+// The launch sequence of one build (kernels only: no allocation, no host synchronisation).
+static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st) {
+    const size_t n = T->n;
+    const float box = T->box;
+    const int leaf_cap = T->cap, max_depth = T->max_depth;
+    const bool fixed = T->fixed;
     TreeGlobals* g = T->globals.as<TreeGlobals>();
     float4* center = T->center.as<float4>();
     float4* com = T->com.as<float4>();
@@ -1207,7 +1294,6 @@ int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_c
                                             T->leaf_off.as<int>());
     ctx->launches += 9;
     B200_CUDA(cudaGetLastError());
-    T->built = true;
     return B200_OK;
 }
 
