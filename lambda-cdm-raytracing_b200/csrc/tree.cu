@@ -425,45 +425,61 @@ entry_digit_kernel(const TreeGlobals* __restrict__ g, int level, int keep,
     }
 }
 
-// single CTA, warp d scans channel d over the tiles; 8 tiles per lane per step (256 per warp step) so
-// that a 16 M-particle level (8192 tiles) is 32 dependent steps, not 256
-__global__ void __launch_bounds__(256)
+// 8 CTAs, CTA d scans channel (octant digit) d over the tiles: 1024 threads x 8 tiles per step, so a
+// 16 M-particle level (8192 tiles) is one step of thread-serial + warp + CTA scan.  The next level's
+// entry count is the sum of the 8 channel totals (reset by node_scan_kernel, added here).
+__global__ void __launch_bounds__(1024)
 tile_scan_kernel(TreeGlobals* __restrict__ g, int level, unsigned* __restrict__ tile_hist) {
-    __shared__ unsigned tot[8];
+    __shared__ unsigned wsum[32];
+    __shared__ unsigned carry_s, chunk_s;
     constexpr int PER = 8;
     const LevelInfo L = g->lv[level];
     const int n_tiles = (L.n_entries + ENT_TILE - 1) / ENT_TILE;
-    const int lane = threadIdx.x & 31, d = threadIdx.x >> 5;
-    unsigned carry = 0;
-    for (int base = 0; base < n_tiles; base += 32 * PER) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, d = blockIdx.x;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024 * PER) {
         unsigned v[PER], sum = 0;
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
-            const int t = base + lane * PER + j;
+            const int t = base + threadIdx.x * PER + j;
             v[j] = (t < n_tiles) ? tile_hist[(size_t)t * 8 + d] : 0u;
             sum += v[j];
         }
         unsigned x = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            unsigned y = __shfl_up_sync(FULL, x, o);
+            const unsigned y = __shfl_up_sync(FULL, x, o);
             if (lane >= o) x += y;
         }
-        unsigned pre = carry + x - sum;
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned w = wsum[lane];
+            unsigned xs = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned y = __shfl_up_sync(FULL, xs, o);
+                if (lane >= o) xs += y;
+            }
+            wsum[lane] = xs - w;
+            if (lane == 31) chunk_s = xs;
+        }
+        __syncthreads();
+        unsigned pre = carry_s + wsum[warp] + (x - sum);
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
-            const int t = base + lane * PER + j;
+            const int t = base + threadIdx.x * PER + j;
             if (t < n_tiles) tile_hist[(size_t)t * 8 + d] = pre;
             pre += v[j];
         }
-        carry += __shfl_sync(FULL, x, 31);
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += chunk_s;
+        __syncthreads();
     }
-    if (lane == 0) { tot[d] = carry; g->totals[d] = carry; }
-    __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned s = 0;
-        for (int k = 0; k < 8; ++k) s += tot[k];
-        g->lv[level + 1].n_entries = (int)s;
+        g->totals[d] = carry_s;
+        atomicAdd(&g->lv[level + 1].n_entries, (int)carry_s);
     }
 }
 
@@ -1257,7 +1273,7 @@ static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st) {
             T->ent_node[cur].as<int>(), T->digit.as<unsigned char>(), T->part_idx.as<int>(),
             T->slot_node.as<int>(), T->tile_hist.as<unsigned>(), T->tile_warp_prefix.as<unsigned>(), T->split_where.as<int>(),
             T->split_local.as<unsigned>());
-        tile_scan_kernel<<<1, 256, 0, st>>>(g, L, T->tile_hist.as<unsigned>());
+        tile_scan_kernel<<<8, 1024, 0, st>>>(g, L, T->tile_hist.as<unsigned>());
         make_children_kernel<<<sgrid, 256, 0, st>>>(g, L, T->split_node.as<int>(), T->split_where.as<int>(),
                                                     T->split_local.as<unsigned>(), T->tile_hist.as<unsigned>(),
                                                     T->tile_warp_prefix.as<unsigned>(),
