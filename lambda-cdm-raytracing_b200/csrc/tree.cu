@@ -844,13 +844,15 @@ pack_walk_kernel(const TreeGlobals* __restrict__ g, int max_depth, const float4*
         const int4 m = meta[k];
         if (m.x < 0 && k != 0) continue;
         int first, skip = -1, loff, lcnt;
+        // the walk visits internal nodes that carry mass; everything else is stepped over here, once
+        auto stepped_over = [&](int j) { return meta[j].x < 0 || com[j].w == 0.0f; };     // leaf, or :260
         if (m.x < 0) {                               // the whole tree is one leaf
             first = ROOT_LEAF; loff = 0; lcnt = m.w;
         } else {
             first = m.x;                             // children, then whatever follows the subtree
-            while (first >= 0 && meta[first].x < 0) first = meta[first].y;
+            while (first >= 0 && stepped_over(first)) first = meta[first].y;
             skip = m.y;
-            while (skip >= 0 && meta[skip].x < 0) skip = meta[skip].y;
+            while (skip >= 0 && stepped_over(skip)) skip = meta[skip].y;
             loff = pscan[(m.x - 1) >> 3];                   // first source pair of the children
             lcnt = lscan[m.x + 8] - lscan[m.x];             // leaf particles among them
         }
@@ -1048,18 +1050,21 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
         if (k2 < np) row2(src[2 * k2], src[2 * k2 + 1]);
     };
 
+    // the root: massless -> nothing to do (:260); a leaf -> one pair loop (:268-270).  Every node the
+    // links lead to after that is internal and carries mass (pack_walk_kernel).
     int k = 0;
+    {
+        const float4 c = nodes[0];
+        const float4 mf = nodes[1];
+        if (c.w == 0.0f) k = -1;
+        else if (__float_as_int(mf.x) == ROOT_LEAF) { leaf_range(0, __float_as_int(mf.w), valid); k = -1; }
+    }
     while (k >= 0) {
         if (wake == k) wake = AWAKE;
         const bool active = (wake == AWAKE);
         const float4 c = nodes[2 * k];                                   // centre of mass, M
         const float4 mf = nodes[2 * k + 1];                              // first | skip | cell edge | leaf-child particles
         const int first = __float_as_int(mf.x), skip = __float_as_int(mf.y), lcnt = __float_as_int(mf.w);
-        if (c.w == 0.0f) { k = skip; continue; }                         // :260
-        if (first == ROOT_LEAF) {                                        // the tree is a single leaf (:268-270)
-            leaf_range(0, lcnt, active);
-            break;
-        }
         bool open = false;
         if (active) {
             const float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
