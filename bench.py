@@ -40,10 +40,23 @@ EPS = 0.01
 
 
 # --------------------------------------------------------------------------- inputs
-def make_particles(n, seed=42):
-    """Uniform in [-50,50)^3, unit masses (what every reference generator emits)."""
+def make_particles(n, seed=42, order="random"):
+    """Uniform in [-50,50)^3, unit masses (what every reference generator emits).  order="morton":
+    the same particles stored in Morton (Z-curve) order, the way a production run keeps them, so that a
+    contiguous index range -- one rank's shard -- is a compact region of space."""
     rng = np.random.default_rng(seed)
     pos = rng.uniform(-50.0, 50.0, size=(n, 3)).astype(np.float32)
+    if order == "morton":
+        q = np.clip(((pos + 50.0) * (1024.0 / 100.0)).astype(np.int64), 0, 1023)
+
+        def spread(v):
+            v = (v | (v << 16)) & 0x030000FF
+            v = (v | (v << 8)) & 0x0300F00F
+            v = (v | (v << 4)) & 0x030C30C3
+            v = (v | (v << 2)) & 0x09249249
+            return v
+        key = (spread(q[:, 0]) << 2) | (spread(q[:, 1]) << 1) | spread(q[:, 2])
+        pos = np.ascontiguousarray(pos[np.argsort(key, kind="stable")])
     return pos, np.ones(n, np.float32)
 
 
@@ -231,6 +244,9 @@ def zeldovich_grid(n):
 
 def workload_config(args):
     cfg = _workload_config(args)
+    if getattr(args, "order", "random") == "morton" and getattr(args, "ic", "uniform") == "uniform":
+        cfg["workload"] = cfg["workload"].replace("uniform [-50,50)^3", "uniform [-50,50)^3 stored in Morton order")
+        cfg["order"] = "morton"
     if getattr(args, "ic", "uniform") == "zeldovich":
         cfg["workload"] = cfg["workload"].replace(
             "uniform [-50,50)^3",
@@ -292,7 +308,7 @@ def bench_gpu(args):
         posm_host = posm.cpu().numpy()
         pos, mass = np.ascontiguousarray(posm_host[:, :3]), np.ascontiguousarray(posm_host[:, 3])
     else:
-        pos, mass = make_particles(n)
+        pos, mass = make_particles(n, order=args.order)
         posm_host = np.ascontiguousarray(np.concatenate([pos, mass[:, None]], 1), np.float32)
         posm = torch.from_numpy(posm_host).to(dev)             # full source set, resident in HBM
     shard = posm[lo:hi].clone() if world > 1 else posm     # this rank's particles (all-gather input)
@@ -529,6 +545,8 @@ def main():
                     help="synthetic inputs: uniform random (default) or Zel'dovich initial conditions generated on "
                          "the device")
     ap.add_argument("--z-initial", type=float, default=49.0, help="redshift of the Zel'dovich ICs")
+    ap.add_argument("--order", default="random", choices=["random", "morton"],
+                    help="index order of the uniform particles: as drawn (default) or sorted along a Morton curve")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--sources", default="allgather", choices=["allgather", "peer"],
                     help="N>1 direct sum: NCCL all-gather of the shards (default) or peer-mapped source tiles "
