@@ -5,6 +5,7 @@
 #include <random>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "b200grav.h"
 
@@ -74,6 +75,62 @@ void B200LambdaCDMSimulation::initialize_particles(uint32_t seed) {
         for (int k = 0; k < 3; ++k) vel[3 * i + k] = nrm(rng);
     }
     set_particles(pos.data(), vel.data(), nullptr);
+}
+
+void B200LambdaCDMSimulation::set_initial_conditions_from_power_spectrum(uint32_t seed, double z_initial) {
+    const size_t n = num_particles_;
+    if (n == 0) return;
+    b200_ic_params p;
+    b200_ic_params_default(&p);
+    int grid = 4;
+    while ((size_t)grid * grid * grid < n) grid *= 2;
+    p.grid = grid;
+    p.box = box_size_;
+    p.z_initial = z_initial;
+    p.seed = seed;
+    p.omega_m = params_.omega_m; p.omega_lambda = params_.omega_lambda; p.omega_k = params_.omega_k;
+    p.h = params_.h; p.sigma_8 = params_.sigma_8; p.n_s = params_.n_s;
+    const bool tree = method_ == B200ForceMethod::Tree || method_ == B200ForceMethod::TreeFixed;
+    p.origin_shift = tree ? 0.5f * box_size_ : 0.0f;
+    // all N velocities land in the staging buffer; this rank keeps its own range
+    void* d_vel_all = nullptr;
+    check(b200_device_alloc(ctx_, n * 12 + 16, &d_vel_all), "alloc IC velocities");
+    const int rc = b200_zeldovich_ics_dev(ctx_, &p, n, d_posm_, d_vel_all, nullptr, stream_);
+    if (rc == B200_OK && n_local_) {
+        std::vector<float> v(3 * n_local_);
+        const int r2 = b200_memcpy_d2h(ctx_, v.data(), (char*)d_vel_all + i0_ * 12, n_local_ * 12, stream_);
+        if (r2 == B200_OK) b200_memcpy_h2d(ctx_, d_vel_, v.data(), n_local_ * 12, stream_);
+        b200_ctx_sync(ctx_, stream_);
+    }
+    b200_device_free(ctx_, d_vel_all);
+    check(rc, "Zel'dovich initial conditions");
+    scale_factor_ = 1.0 / (1.0 + z_initial);
+    have_forces_ = false;
+    current_step_ = 0;
+}
+
+void B200LambdaCDMSimulation::copy_particles_to_host(std::vector<Particle>& particles) const {
+    particles.resize(n_local_);
+    if (!n_local_) return;
+    std::vector<float> posm(4 * n_local_), vel(3 * n_local_);
+    check(b200_memcpy_d2h(ctx_, posm.data(), (const char*)d_posm_ + i0_ * 16, n_local_ * 16, stream_), "download particles");
+    check(b200_memcpy_d2h(ctx_, vel.data(), d_vel_, n_local_ * 12, stream_), "download velocities");
+    for (size_t i = 0; i < n_local_; ++i) {
+        Particle& q = particles[i];
+        q.position.x = posm[4 * i]; q.position.y = posm[4 * i + 1]; q.position.z = posm[4 * i + 2];
+        q.velocity.x = vel[3 * i]; q.velocity.y = vel[3 * i + 1]; q.velocity.z = vel[3 * i + 2];
+        q.mass = posm[4 * i + 3];
+        q.id = (uint64_t)(i0_ + i);
+    }
+}
+
+void B200LambdaCDMSimulation::power_spectrum(int grid, std::vector<float>& k, std::vector<float>& pk,
+                                             std::vector<int>& modes, bool shot_noise_correction) const {
+    const size_t nb = grid > 0 ? (size_t)grid / 2 : 0;
+    k.assign(nb, 0.0f); pk.assign(nb, 0.0f); modes.assign(nb, 0);
+    check(b200_power_spectrum_dev(ctx_, d_posm_, num_particles_, grid, box_size_, /*mass_weighted=*/1,
+                                  shot_noise_correction ? 1 : 0, k.data(), pk.data(), modes.data(), stream_),
+          "power spectrum");
 }
 
 void B200LambdaCDMSimulation::set_force_method(B200ForceMethod m, float theta, int leaf_capacity, int max_depth) {

@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "physics/cosmology_model.hpp"
+#include "physics/lambda_cdm.hpp"        // physics::Particle
 
 struct b200_ctx;
 
@@ -73,6 +74,12 @@ public:
     // 128-byte id rank 0 obtained from b200_shard_unique_id().  Collective (blocks until all
     // `world` ranks have called it).
     void enable_sharding(const unsigned char* nccl_unique_id, int rank, int world);
+    // lambda_cdm.hpp:42 -- declared by the reference, defined nowhere in it.  Here: Zel'dovich particles
+    // generated on the device (b200_zeldovich_ics_dev: the reference generator's spectrum, growth and
+    // velocity conventions, with the inverse FFT its displacement step lacks), grid = the smallest power
+    // of two with grid^3 >= N, positions in [0, box) -- or origin-centred for the tree methods, whose root
+    // cube is centred on the origin.  Every rank of a sharded run generates the same particles.
+    void set_initial_conditions_from_power_spectrum(uint32_t seed = 12345, double z_initial = 49.0);
     void set_softening(float softening) { softening_ = softening; have_forces_ = false; }
     void set_force_method(B200ForceMethod m, float theta = 0.5f, int leaf_capacity = 8, int max_depth = 20);
 
@@ -90,6 +97,11 @@ public:
     void copy_positions_to_host(float* positions) const;       // float[3N]
     void copy_velocities_to_host(float* velocities) const;     // float[3*local count]
     void copy_forces_to_host(float* accelerations) const;      // float[3*local count]
+    void copy_particles_to_host(std::vector<Particle>& particles) const;   // lambda_cdm.hpp:58; the local range
+    // analysis::PowerSpectrumAnalyzer::compute_power_spectrum (src/analysis/power_spectrum.cu:53-84) on the
+    // device-resident particles: grid/2 bins of width 2 pi / box
+    void power_spectrum(int grid, std::vector<float>& k, std::vector<float>& pk, std::vector<int>& modes,
+                        bool shot_noise_correction = true) const;
     size_t get_local_offset() const { return i0_; }            // first particle this rank integrates
     size_t get_local_count() const { return n_local_; }        // == N unless sharded
     int get_rank() const { return rank_; }

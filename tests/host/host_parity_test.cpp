@@ -195,6 +195,42 @@ int main() {
     }
 
     std::cout.rdbuf(quiet.rdbuf());
+    {   // device-generated initial conditions + the particle / power-spectrum accessors of the simulation class
+        const size_t m_n = 32768;                                   // 32^3: every grid point
+        physics::B200LambdaCDMSimulation sim(m_n, 100.0f);
+        sim.set_force_method(physics::B200ForceMethod::TreeFixed);
+        sim.set_initial_conditions_from_power_spectrum(12345, 49.0);
+        std::vector<physics::Particle> parts;
+        sim.copy_particles_to_host(parts);
+        std::vector<float> x(3 * m_n);
+        sim.copy_positions_to_host(x.data());
+        bool same = parts.size() == m_n, inside = true;
+        double disp2 = 0.0;
+        for (size_t i = 0; i < m_n && same; ++i) {
+            same = parts[i].position.x == x[3 * i] && parts[i].position.z == x[3 * i + 2] && parts[i].mass == 1.0f &&
+                   parts[i].id == i;
+            inside = inside && x[3 * i] >= -50.0f && x[3 * i] < 50.0f;
+            const size_t ix = i / (32 * 32);
+            const double q = (ix + 0.5) * (100.0 / 32) - 50.0;     // cell centre, origin-centred
+            double d = x[3 * i] - q;
+            d -= 100.0 * std::round(d / 100.0);
+            disp2 += d * d;
+        }
+        const double rms_x = std::sqrt(disp2 / m_n);
+        std::vector<float> kk, pk;
+        std::vector<int> modes;
+        sim.power_spectrum(32, kk, pk, modes, false);
+        CHECK(same && inside && rms_x > 0.02 && rms_x < 0.4 && std::fabs(sim.get_redshift() - 49.0) < 1e-9 &&
+                  pk.size() == 16 && modes[1] == 26 && pk[1] > 0.0f,
+              "set_initial_conditions_from_power_spectrum: %zu particles, rms x-displacement %.3f Mpc/h, P(k_1) %.3g",
+              parts.size(), rms_x, pk.size() > 1 ? pk[1] : 0.0f);
+        sim.step(1e-4);
+        sim.compute_energy();
+        CHECK(std::isfinite(sim.get_total_energy()) && sim.get_potential_energy() < 0.0 && sim.get_kinetic_energy() > 0.0,
+              "step + compute_energy on the generated particles: KE %.4g PE %.4g", sim.get_kinetic_energy(),
+              sim.get_potential_energy());
+    }
+
     direct->finalize(); direct->finalize();                                        // idempotent
     tree->finalize(); cpu_tree->finalize();
     std::cout.rdbuf(old);
