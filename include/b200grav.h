@@ -177,6 +177,13 @@ int b200_tree_forces_host(b200_ctx* ctx, const float* pos3, const float* mass,
  * sum: 1.3e-3 relative L2 at theta = 0.5, 7e-5 at theta = 0.2 (uniform, leaf_cap 8). */
 int b200_tree_build_fixed_dev(b200_ctx* ctx, const void* posm4, size_t n, int leaf_cap,
                               int max_depth, float eps, void* stream);
+/* Fixed-physics walks only: box > 0 takes every separation (cell and particle) to its nearest periodic
+ * image, d -= box * round(d / box) -- the minimum image of the reference's GPU kernels
+ * (src/physics/lambda_cdm_kernels.cu:39-41, src/forces/barnes_hut_tree.cu:247-254); a cell that reaches across
+ * the half-box distance from the target is always opened, so the result converges to the minimum-image direct
+ * sum as theta -> 0; no Ewald sum.  0 = open
+ * boundary (default).  The reference-faithful tree is never periodic (the CPU TreeForceComputer is not). */
+int b200_tree_set_periodic(b200_ctx* ctx, float box);
 int b200_tree_forces_fixed_host(b200_ctx* ctx, const float* pos3, const float* mass /* NULL = 1 */,
                                 float* acc3, size_t n, float theta, int leaf_cap, int max_depth,
                                 float eps);

@@ -344,6 +344,11 @@ int b200_tree_export(b200_ctx* ctx, int32_t* level, float* center, float* size, 
     return tree_export(ctx, level, center, size, first_child, arrivals, part_off, part_idx, mass, com);
 }
 
+int b200_tree_set_periodic(b200_ctx* ctx, float box) {
+    if (!ctx) return B200_ERR_INVALID;
+    return tree_set_periodic(ctx, box);
+}
+
 int b200_tree_set_counting(b200_ctx* ctx, int enabled) {
     if (!ctx) return B200_ERR_INVALID;
     return tree_set_counting(ctx, enabled);

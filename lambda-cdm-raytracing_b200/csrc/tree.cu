@@ -68,6 +68,7 @@ struct TreeState {
     bool counting = false;
     bool fixed = false;          // "fixed physics" tree: no orphans, data-fitted root, real leaf masses
     float eps = 0.01f;           // softening of the walk (0.01f literal in the faithful mode)
+    float periodic_box = 0.f;    // fixed mode only: > 0 = minimum-image separations in the walk
     DevBuf center, com, meta, nstart, ncount, nsplit_rank;
     DevBuf ent_idx[2], ent_node[2], digit;
     DevBuf part_idx, part_pos;
@@ -80,6 +81,7 @@ struct TreeState {
     DevBuf keys, keys_sorted, perm, sort_scratch, order;
     size_t order_i0 = 0, order_n = 0;
     bool order_valid = false;
+    int order_age = 0;            // builds since the target order was computed
     // The build is a fixed sequence of ~200 launches with no host decision in it: captured once into
     // a CUDA graph and replayed while (inputs pointer, sizes, parameters, scratch buffers) stay the same.
     cudaGraphExec_t graph_exec = nullptr;
@@ -994,11 +996,17 @@ __device__ __forceinline__ unsigned long long w_fma2(unsigned long long a, unsig
     return r;
 }
 
-template <bool COUNT, bool FIXED>
+// PERIODIC (fixed mode only): separations are taken to the nearest periodic image, d -= box*round(d/box)
+// (the minimum image of compute_forces_direct, src/physics/lambda_cdm_kernels.cu:39-41, which is also what
+// the reference's GPU tree kernel applies to its cells, src/forces/barnes_hut_tree.cu:247-254) -- for the
+// accept test and the monopole with roundf, for the pair rows with the packed magic-number rounding.
+// A cell that reaches across the half-box distance from the target (|d| + edge > box/2 on any axis) is
+// always opened: its particles need not share the image of its centre of mass.
+template <bool COUNT, bool FIXED, bool PERIODIC = false>
 __global__ void __launch_bounds__(128)
 walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order, int i0, int n_targets,
                  const float4* __restrict__ nodes, const int* __restrict__ leaf_off,
-                 const ulonglong2* __restrict__ leaf_pairs, float theta, float eps,
+                 const ulonglong2* __restrict__ leaf_pairs, float theta, float eps, float box,
                  float* __restrict__ acc3, TreeGlobals* __restrict__ g) {
     typedef unsigned long long u64;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1012,6 +1020,14 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
     const float theta2 = theta > 0.f ? theta * theta : 0.f;              // theta <= 0: nothing is ever accepted
     const u64 eps2_2 = w_pk(eps2, eps2);
     const u64 npx = w_pk(-p.x, -p.x), npy = w_pk(-p.y, -p.y), npz = w_pk(-p.z, -p.z);
+    [[maybe_unused]] u64 inv_box2, magic2, nmagic2, nbox2;
+    if constexpr (PERIODIC) {
+        const float ib = 1.0f / box;
+        inv_box2 = w_pk(ib, ib);
+        magic2 = w_pk(12582912.0f, 12582912.0f);             // 1.5 * 2^23: round to nearest integer
+        nmagic2 = w_pk(-12582912.0f, -12582912.0f);
+        nbox2 = w_pk(-box, -box);
+    }
     unsigned long long c_vis = valid ? 1 : 0, c_pc = 0, c_pp = 0;        // the root is visited by everyone
     constexpr int AWAKE = -2, NEVER = -3;
     int wake = valid ? AWAKE : NEVER;     // node id at which a sleeping lane resumes
@@ -1021,7 +1037,12 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
     // padding slot, adds f = 0.
     auto leaf_range = [&](int q, int cnt, bool on_lane) {
         auto row2 = [&](const ulonglong2& a, const ulonglong2& b) {      // a = {x0 x1 | y0 y1}, b = {z0 z1 | w0 w1}
-            const u64 dx = w_add2(a.x, npx), dy = w_add2(a.y, npy), dz = w_add2(b.x, npz);
+            u64 dx = w_add2(a.x, npx), dy = w_add2(a.y, npy), dz = w_add2(b.x, npz);
+            if constexpr (PERIODIC) {
+                dx = w_fma2(w_add2(w_add2(w_mul2(dx, inv_box2), magic2), nmagic2), nbox2, dx);
+                dy = w_fma2(w_add2(w_add2(w_mul2(dy, inv_box2), magic2), nmagic2), nbox2, dy);
+                dz = w_fma2(w_add2(w_add2(w_mul2(dz, inv_box2), magic2), nmagic2), nbox2, dz);
+            }
             u64 r2 = w_fma2(dx, dx, eps2_2);
             r2 = w_fma2(dy, dy, r2);
             r2 = w_fma2(dz, dz, r2);
@@ -1067,9 +1088,19 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
         const int first = __float_as_int(mf.x), skip = __float_as_int(mf.y), lcnt = __float_as_int(mf.w);
         bool open = false;
         if (active) {
-            const float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
+            float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
+            if constexpr (PERIODIC) {
+                dx = __fsub_rn(dx, __fmul_rn(box, roundf(__fdiv_rn(dx, box))));
+                dy = __fsub_rn(dy, __fmul_rn(box, roundf(__fdiv_rn(dy, box))));
+                dz = __fsub_rn(dz, __fmul_rn(box, roundf(__fdiv_rn(dz, box))));
+            }
             const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            if (accept_cell_sq(mf.z, d2, theta, theta2)) {               // :309
+            bool wraps = false;      // periodic: a cell reaching across the half-box distance is never a monopole
+            if constexpr (PERIODIC) {
+                const float hb = __fmul_rn(box, 0.5f);
+                wraps = __fadd_rn(fabsf(dx), mf.z) > hb || __fadd_rn(fabsf(dy), mf.z) > hb || __fadd_rn(fabsf(dz), mf.z) > hb;
+            }
+            if (!wraps && accept_cell_sq(mf.z, d2, theta, theta2)) {     // :309
                 const float rinv = rsqrt_fast(d2 + eps2);
                 const float f = c.w * rinv * rinv * rinv;                // :280-290
                 ax += f * dx; ay += f * dy; az += f * dz;
@@ -1145,7 +1176,9 @@ int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_c
     if (n >= (1ull << 30)) return B200_ERR_UNSUPPORTED;
     TreeState* T = state(ctx);
     T->built = false;
-    T->order_valid = false;
+    // The warp grouping of the targets is a performance heuristic (any permutation of the range gives the
+    // same forces): particles move little per step, so an order is kept for up to 8 builds.
+    if (++T->order_age >= 8) T->order_valid = false;
     T->n = n; T->box = box; T->cap = leaf_cap; T->max_depth = max_depth;
     T->fixed = fixed;
     T->eps = fixed ? eps : 0.01f;
@@ -1340,7 +1373,7 @@ static int tree_target_order(b200_ctx* ctx, TreeState* T, size_t i0, size_t n_ta
         ctx->launches += 1;
     }
     B200_CUDA(cudaGetLastError());
-    T->order_valid = true; T->order_i0 = i0; T->order_n = n_targets;
+    T->order_valid = true; T->order_i0 = i0; T->order_n = n_targets; T->order_age = 0;
     return B200_OK;
 }
 
@@ -1358,24 +1391,18 @@ int tree_walk(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* acc
     }
     if (ctx->timing) B200_CUDA(cudaEventRecord(ctx->ev0, st));
     const bool per_thread = !T->fixed && getenv("B200_WALK_PER_THREAD") != nullptr;     // tuning hook
+    // one launch macro for the warp walk's instances: <COUNT, FIXED, PERIODIC>
+#define B200_WALK(COUNT_, FIXED_, PERIODIC_)                                                                     \
+    walk_warp_kernel<COUNT_, FIXED_, PERIODIC_><<<grid, 128, 0, st>>>(                                           \
+        T->posm, T->order.as<int>(), (int)i0, (int)n_targets, T->nodes.as<float4>(), T->leaf_off.as<int>(),      \
+        T->leaf_pos.as<ulonglong2>(), theta, T->eps, T->periodic_box, (float*)acc3, g)
     if (T->fixed) {
-        if (T->counting)
-            walk_warp_kernel<true, true><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
-                                                               T->nodes.as<float4>(), T->leaf_off.as<int>(), T->leaf_pos.as<ulonglong2>(), theta,
-                                                               T->eps, (float*)acc3, g);
-        else
-            walk_warp_kernel<false, true><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
-                                                                T->nodes.as<float4>(), T->leaf_off.as<int>(), T->leaf_pos.as<ulonglong2>(), theta,
-                                                                T->eps, (float*)acc3, g);
+        const bool periodic = T->periodic_box > 0.f;
+        if (T->counting) { if (periodic) B200_WALK(true, true, true); else B200_WALK(true, true, false); }
+        else             { if (periodic) B200_WALK(false, true, true); else B200_WALK(false, true, false); }
     } else if (!per_thread) {
-        if (T->counting)
-            walk_warp_kernel<true, false><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
-                                                                T->nodes.as<float4>(), T->leaf_off.as<int>(), T->leaf_pos.as<ulonglong2>(), theta,
-                                                                T->eps, (float*)acc3, g);
-        else
-            walk_warp_kernel<false, false><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
-                                                                 T->nodes.as<float4>(), T->leaf_off.as<int>(), T->leaf_pos.as<ulonglong2>(), theta,
-                                                                 T->eps, (float*)acc3, g);
+        if (T->counting) B200_WALK(true, false, false); else B200_WALK(false, false, false);
+#undef B200_WALK
     } else if (T->counting)
         walk_kernel<true><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
                                                 T->com.as<float4>(), T->center.as<float4>(), T->meta.as<int4>(),
@@ -1387,6 +1414,12 @@ int tree_walk(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* acc
     if (ctx->timing) B200_CUDA(cudaEventRecord(ctx->ev1, st));
     B200_CUDA(cudaGetLastError());
     ctx->launches += 1;
+    return B200_OK;
+}
+
+int tree_set_periodic(b200_ctx* ctx, float box) {
+    if (box < 0.f) return B200_ERR_INVALID;
+    state(ctx)->periodic_box = box;
     return B200_OK;
 }
 

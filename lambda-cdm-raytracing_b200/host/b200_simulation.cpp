@@ -90,8 +90,8 @@ void B200LambdaCDMSimulation::set_initial_conditions_from_power_spectrum(uint32_
     p.seed = seed;
     p.omega_m = params_.omega_m; p.omega_lambda = params_.omega_lambda; p.omega_k = params_.omega_k;
     p.h = params_.h; p.sigma_8 = params_.sigma_8; p.n_s = params_.n_s;
-    const bool tree = method_ == B200ForceMethod::Tree || method_ == B200ForceMethod::TreeFixed;
-    p.origin_shift = tree ? 0.5f * box_size_ : 0.0f;
+    const bool centred = method_ == B200ForceMethod::Tree || method_ == B200ForceMethod::TreeFixed;
+    p.origin_shift = centred ? 0.5f * box_size_ : 0.0f;
     // all N velocities land in the staging buffer; this rank keeps its own range
     void* d_vel_all = nullptr;
     check(b200_device_alloc(ctx_, n * 12 + 16, &d_vel_all), "alloc IC velocities");
@@ -142,12 +142,15 @@ void B200LambdaCDMSimulation::compute_forces() {
     const size_t n = num_particles_;
     if (n == 0) return;
     // every rank sees all sources (replicated positions), and evaluates its own targets only
-    if (method_ == B200ForceMethod::Tree || method_ == B200ForceMethod::TreeFixed) {
+    if (method_ == B200ForceMethod::Tree || method_ == B200ForceMethod::TreeFixed ||
+        method_ == B200ForceMethod::TreeFixedPeriodic) {
         if (method_ == B200ForceMethod::Tree)
             check(b200_tree_build_dev(ctx_, d_posm_, n, box_size_, leaf_capacity_, max_depth_, stream_), "tree build");
         else
             check(b200_tree_build_fixed_dev(ctx_, d_posm_, n, leaf_capacity_, max_depth_, softening_, stream_),
                   "tree build (fixed physics)");
+        check(b200_tree_set_periodic(ctx_, method_ == B200ForceMethod::TreeFixedPeriodic ? box_size_ : 0.0f),
+              "tree periodic box");
         check(b200_tree_walk_dev(ctx_, i0_, n_local_, theta_, d_acc_, stream_), "tree walk");
     } else {
         const float box = (method_ == B200ForceMethod::Direct) ? box_size_ : 0.0f;   // K1/K2 are periodic
@@ -160,7 +163,8 @@ void B200LambdaCDMSimulation::compute_forces() {
 void B200LambdaCDMSimulation::compute_energy() {
     // launch_energy_computation (lambda_cdm_kernels.cu:492-516): periodic minimum image whenever the
     // force method is (Direct); open boundary for DirectOpen and Tree.
-    const float box = (method_ == B200ForceMethod::Direct) ? box_size_ : 0.0f;
+    const float box = (method_ == B200ForceMethod::Direct || method_ == B200ForceMethod::TreeFixedPeriodic)
+                          ? box_size_ : 0.0f;
     double e[2] = {0.0, 0.0};
     check(b200_energy_dev(ctx_, d_posm_, num_particles_, i0_, n_local_, d_vel_, softening_, box, &e[0], &e[1], stream_),
           "energy");
@@ -177,7 +181,8 @@ void B200LambdaCDMSimulation::step(double dt) {
     const size_t n = num_particles_;
     if (n == 0) { ++current_step_; return; }
     if (!have_forces_) compute_forces();
-    const float wrap = (method_ == B200ForceMethod::Direct) ? box_size_ : 0.0f;     // only K1/K2 are periodic
+    const float wrap = (method_ == B200ForceMethod::Direct || method_ == B200ForceMethod::TreeFixedPeriodic)
+                           ? box_size_ : 0.0f;                                   // the periodic methods wrap into [0, box)
     // lambda_cdm_impl.cu:167-213: kick(dt/2, a) -> drift(dt) -> a update -> forces -> kick(dt/2, a_new)
     void* my_posm = (char*)d_posm_ + i0_ * 16;
     check(b200_leapfrog_dev(ctx_, my_posm, d_vel_, d_acc_, n_local_, 1, (float)(dt * 0.5), scale_factor_, (float)dt, wrap,

@@ -33,7 +33,10 @@ struct b200_ctx;
 
 namespace physics {
 
-enum class B200ForceMethod { Direct, DirectOpen, Tree, TreeFixed };   // TreeFixed: b200_tree_build_fixed_dev
+// Direct: minimum image + wrap (the reference's K1/K2); DirectOpen: open boundary; Tree: the CPU
+// TreeForceComputer's tree, open boundary; TreeFixed: b200_tree_build_fixed_dev, open boundary;
+// TreeFixedPeriodic: the same with minimum-image walks (b200_tree_set_periodic) and wrapped drifts.
+enum class B200ForceMethod { Direct, DirectOpen, Tree, TreeFixed, TreeFixedPeriodic };
 
 class B200LambdaCDMSimulation {
     b200_ctx* ctx_ = nullptr;

@@ -637,6 +637,16 @@ void orc_tree_forces(const orc_tree* t, const float* pos3, float theta,
 void orc_tree_forces_fixed(const orc_tree* t, const float* pos3, const float* mass, float theta,
                            float eps, size_t i0, size_t n_targets, float* out3,
                            uint64_t* counters) {
+    orc_tree_forces_fixed_periodic(t, pos3, mass, theta, eps, 0.0f, i0, n_targets, out3, counters);
+}
+
+/* ... with box > 0: every separation (cell and particle) taken to its nearest periodic image,
+ * d -= box * roundf(d / box), the minimum image of compute_forces_direct
+ * (src/physics/lambda_cdm_kernels.cu:39-41) that the reference's GPU tree kernel also applies to its
+ * cells (src/forces/barnes_hut_tree.cu:247-254).  No Ewald sum. */
+void orc_tree_forces_fixed_periodic(const orc_tree* t, const float* pos3, const float* mass, float theta,
+                                    float eps, float box, size_t i0, size_t n_targets, float* out3,
+                                    uint64_t* counters) {
     uint64_t c_vis = 0, c_pc = 0, c_pp = 0;
     const float eps2 = eps * eps;
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : c_vis, c_pc, c_pp)
@@ -657,6 +667,11 @@ void orc_tree_forces_fixed(const orc_tree* t, const float* pos3, const float* ma
                     float dx = pos3[3 * j + 0] - px;
                     float dy = pos3[3 * j + 1] - py;
                     float dz = pos3[3 * j + 2] - pz;
+                    if (box > 0.0f) {
+                        dx = dx - box * roundf(dx / box);
+                        dy = dy - box * roundf(dy / box);
+                        dz = dz - box * roundf(dz / box);
+                    }
                     float r2 = dx * dx + dy * dy + dz * dz + eps2;
                     float r = sqrtf(r2);
                     float f = (mass ? mass[j] : 1.0f) / (r2 * r);
@@ -668,8 +683,20 @@ void orc_tree_forces_fixed(const orc_tree* t, const float* pos3, const float* ma
             float dx = t->com[3 * k + 0] - px;
             float dy = t->com[3 * k + 1] - py;
             float dz = t->com[3 * k + 2] - pz;
+            if (box > 0.0f) {
+                dx = dx - box * roundf(dx / box);
+                dy = dy - box * roundf(dy / box);
+                dz = dz - box * roundf(dz / box);
+            }
             float d2 = dx * dx + dy * dy + dz * dz;
-            if ((t->size[k] / sqrtf(d2)) < theta) {
+            /* periodic: a cell whose particles may wrap differently from its centre of mass (it reaches
+             * across the half-box distance from the target) cannot be a monopole: it is opened */
+            int wraps = 0;
+            if (box > 0.0f) {
+                const float hb = box * 0.5f, sz = t->size[k];
+                wraps = (fabsf(dx) + sz > hb) || (fabsf(dy) + sz > hb) || (fabsf(dz) + sz > hb);
+            }
+            if (!wraps && (t->size[k] / sqrtf(d2)) < theta) {
                 float r2 = d2 + eps2;
                 float f = t->mass[k] / (r2 * sqrtf(r2));
                 fx += f * dx; fy += f * dy; fz += f * dz;

@@ -99,6 +99,8 @@ class Oracle:
         L.orc_tree_build_fixed.restype = C.POINTER(_Tree)
         L.orc_tree_forces_fixed.argtypes = [C.POINTER(_Tree), _f32p, _f32p, C.c_float, C.c_float, sz, sz, _f32p,
                                             C.c_void_p]
+        L.orc_tree_forces_fixed_periodic.argtypes = [C.POINTER(_Tree), _f32p, _f32p, C.c_float, C.c_float, C.c_float,
+                                                     sz, sz, _f32p, C.c_void_p]
         L.orc_tree_free.argtypes = [C.POINTER(_Tree)]
         L.orc_tree_equal.argtypes = [C.POINTER(_Tree)] * 2; L.orc_tree_equal.restype = C.c_int
         L.orc_tree_forces.argtypes = [C.POINTER(_Tree), _f32p, C.c_float, sz, sz, _f32p, C.c_void_p]
@@ -175,14 +177,16 @@ class Oracle:
         mass = np.ascontiguousarray(mass, np.float32)
         return Tree(self.lib, self.lib.orc_tree_build_fixed(pos, mass, pos.shape[0], leaf_cap, max_depth))
 
-    def tree_forces_fixed(self, tree, pos, mass, theta=0.5, eps=0.01, i0=0, n_targets=None, counters=False):
+    def tree_forces_fixed(self, tree, pos, mass, theta=0.5, eps=0.01, i0=0, n_targets=None, counters=False, box=0.0):
+        """box > 0: minimum-image separations (periodic box)."""
         pos = np.ascontiguousarray(pos, np.float32)
         mass = np.ascontiguousarray(mass, np.float32)
         n = pos.shape[0]
         nt = n - i0 if n_targets is None else n_targets
         out = np.empty((nt, 3), np.float32)
         cnt = np.zeros(3, np.uint64)
-        self.lib.orc_tree_forces_fixed(tree._ptr, pos, mass, theta, eps, i0, nt, out, cnt.ctypes.data_as(C.c_void_p))
+        self.lib.orc_tree_forces_fixed_periodic(tree._ptr, pos, mass, theta, eps, box, i0, nt, out,
+                                                cnt.ctypes.data_as(C.c_void_p))
         return (out, cnt) if counters else out
 
     def tree_equal(self, a, b):

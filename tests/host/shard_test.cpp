@@ -85,6 +85,7 @@ int main() {
         // opt-in must have happened on every GPU, not only on the first one a process touched)
         {"direct 262144 particles, open boundary", B200ForceMethod::DirectOpen, 262144, 1, false},
         {"tree fixed-physics 50000 particles", B200ForceMethod::TreeFixed, 50000, 3, true},
+        {"tree fixed-physics periodic 30001 particles", B200ForceMethod::TreeFixedPeriodic, 30001, 3, true},
     };
     for (const Case& c : cases) {
         Result single;
