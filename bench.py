@@ -64,7 +64,7 @@ def make_particles(n, seed=42, order="random"):
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons while the timed region runs."""
 
-    def __init__(self, index=0, period=0.1):
+    def __init__(self, index=0, period=0.02):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
