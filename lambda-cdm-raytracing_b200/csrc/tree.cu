@@ -866,7 +866,8 @@ pack_walk_kernel(const TreeGlobals* __restrict__ g, int max_depth, const float4*
 }
 
 // ------------------------------------------------------------------ walk ---
-// One thread per target, targets taken in Morton order so the 32 lanes of a
+// Legacy kernel (B200_WALK_PER_THREAD=1; kept as an independent cross-check of the warp walk).
+// One thread per target, targets taken in space-filling-curve order so the 32 lanes of a
 // warp walk nearly the same nodes.  Stackless: every node carries the id of the
 // node that follows its subtree in depth-first order (meta.y), so "skip" is one
 // load and "open" is meta.x.  Accept test: IEEE sqrt/divide, no contraction, so
@@ -954,7 +955,7 @@ __device__ __forceinline__ bool accept_cell(float size, float d2, float theta) {
     return __fdiv_rn(size, __fsqrt_rn(d2)) < theta;
 }
 
-// Warp-cooperative walk: a warp owns 32 Morton-adjacent targets and walks the
+// Warp-cooperative walk: a warp owns 32 targets that are neighbours on a Hilbert curve and walks the
 // UNION of their traversals in lockstep (node id is warp-uniform, so node and leaf
 // data are broadcast loads and control flow never diverges).  Every lane still
 // applies ITS OWN accept test: a lane that accepts a cell adds the monopole and
@@ -1351,7 +1352,7 @@ static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st) {
     return B200_OK;
 }
 
-// Morton order of the targets [i0, i0+n): stable sort of their 30-bit keys.
+// Hilbert order of the targets [i0, i0+n): stable sort of their 30-bit keys; kept across builds (order_age).
 static int tree_target_order(b200_ctx* ctx, TreeState* T, size_t i0, size_t n_targets, cudaStream_t st) {
     if (T->order_valid && T->order_i0 == i0 && T->order_n == n_targets) return B200_OK;
     B200_TRY(T->keys.reserve(n_targets * sizeof(uint32_t)));

@@ -82,3 +82,23 @@ def test_shard_ranges_cover():
             r = [b200grav.shard_range(n, k, w) for k in range(w)]
             assert r[0][0] == 0 and r[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
+
+
+def test_bench_input_helpers():
+    """Host-side helpers of bench.py: Zel'dovich grid choice and Morton storage order."""
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.zeldovich_grid(1 << 20) == 128 and bench.zeldovich_grid(1 << 24) == 256
+    assert bench.zeldovich_grid(64) == 4 and bench.zeldovich_grid(65) == 8
+    import numpy as np
+    p, m = bench.make_particles(20000, order="morton")
+    q, _ = bench.make_particles(20000)
+    assert np.array_equal(np.sort(p.view([("x", "f4"), ("y", "f4"), ("z", "f4")]).ravel(), order=("x", "y", "z")),
+                          np.sort(q.view([("x", "f4"), ("y", "f4"), ("z", "f4")]).ravel(), order=("x", "y", "z")))
+    # neighbours in storage order are neighbours in space
+    assert np.abs(np.diff(p, axis=0)).mean() < 0.2 * np.abs(np.diff(q, axis=0)).mean()
+    assert np.all(m == 1.0)
