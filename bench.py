@@ -17,6 +17,10 @@ positions with NCCL and every rank evaluates its N/G targets against all sources
            timed region).  This is the number to hold against --impl reference.
 `roofline`: dominant kernel (direct_kernel) against the FP32 FMA peak measured
            in this run by an FFMA probe (MEASURED_PEAKS.json has no FP32 figure).
+`tree_summary`: (default direct run on 1 GPU) a short Barnes-Hut measurement on the same particles --
+           ms per build + walk step, interactions/s, particle-steps/s; `--workload tree` gives the full
+           line (roofline with ncu traffic, e2e, CPU reference tree), `--ic zeldovich` / `--order morton`
+           other inputs, `--kdk` full leapfrog steps.
 `cpu_baseline` / --impl reference: the reference's own CPU direct sum
            (oracle/_ref = /root/reference sources compiled in place; falls back
            to the restated port) on all host cores, bounded sample.
@@ -521,6 +525,10 @@ def bench_gpu(args):
                 "walk_counters_nodes_cells_pairs": tree_counts, "kernel_ms": 1e3 * kern_s,
                 "interactions_per_s_walk_only": per_launch / kern_s,
             }
+        if world == 1 and args.workload == "direct" and not args.kdk and not args.no_tree_summary:
+            # the second kernel family of the hot path, same particles, a few steps: so that the default
+            # run's one line also says where the Barnes-Hut path (BASELINE configs[2]) stands
+            line["tree_summary"] = tree_summary(eng, posm, n, flush)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = run_cpu_baseline(args.workload)
         sys.stdout.flush()
@@ -531,6 +539,41 @@ def bench_gpu(args):
             peers.close()
         dist.destroy_process_group()
     eng.close()
+
+
+def tree_summary(eng, posm, n, flush, steps=5):
+    """Barnes-Hut theta = 0.5, leaf 8, max_depth 20 on the device-resident particles: build + walk per step,
+    CUDA events around each step, L2 flushed between steps.  The full line is `--workload tree`."""
+    import torch
+    acc = torch.empty((n, 3), dtype=torch.float32, device=posm.device)
+    for _ in range(3):
+        eng.tree_build_dev(posm, n, 100.0, 8, 20)
+        eng.tree_walk_dev(acc, 0, n, theta=0.5)
+    torch.cuda.synchronize()
+    eng.set_timing(True)
+    ms, walk_ms = [], []
+    for _ in range(steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.tree_build_dev(posm, n, 100.0, 8, 20)
+        eng.tree_walk_dev(acc, 0, n, theta=0.5)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+        walk_ms.append(eng.last_kernel_ms())
+    eng.set_timing(False)
+    eng.tree_set_counting(True)
+    eng.tree_walk_dev(acc, 0, n, theta=0.5)
+    torch.cuda.synchronize()
+    cnt = eng.tree_counters()
+    eng.tree_set_counting(False)
+    step_s = float(np.mean(ms)) * 1e-3
+    return {"workload": f"TreeForceComputer theta=0.5 leaf=8 max_depth=20, {n} particles, build + walk per step",
+            "ms_per_step": 1e3 * step_s, "walk_kernel_ms": float(np.mean(walk_ms)),
+            "interactions_per_s": float(cnt[1] + cnt[2]) / step_s, "particle_steps_per_s": n / step_s,
+            "walk_counters_nodes_cells_pairs": [int(x) for x in cnt], "steps": steps}
 
 
 def main():
@@ -548,6 +591,8 @@ def main():
     ap.add_argument("--order", default="random", choices=["random", "morton"],
                     help="index order of the uniform particles: as drawn (default) or sorted along a Morton curve")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-tree-summary", action="store_true",
+                    help="default (direct, 1 GPU) run: skip the short Barnes-Hut measurement added as `tree_summary`")
     ap.add_argument("--sources", default="allgather", choices=["allgather", "peer"],
                     help="N>1 direct sum: NCCL all-gather of the shards (default) or peer-mapped source tiles "
                          "pulled over NVLink by the force kernel itself")
