@@ -274,7 +274,7 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
             }
         };
 
-#pragma unroll 2
+#pragma unroll 1      // one LDS.128 group per iteration: ptxas schedules the 2 x R interaction pairs best when left alone
         for (int j4 = 0; j4 < TILE_J / 4; ++j4) {
             const ulonglong2 X = sx[j4], Y = sy[j4], Z = sz[j4];
             ulonglong2 M = make_ulonglong2(0ull, 0ull);
@@ -482,11 +482,11 @@ int direct_forces(b200_ctx* ctx, const DirectSources& src, const void* targets4,
     }
     const float4* tg = (const float4*)targets4;
     float* out = (float*)acc3;
-    // Register blocking: 6 targets/thread (one 256-thread CTA per SM, 228 registers) whenever
+    // Register blocking: 8 targets/thread (one 256-thread CTA per SM, 2048 targets per block) whenever
     // the flattened (target block x source tile) space gives every CTA several units of work
     // and the last, partly filled target block wastes little; 2 targets/thread below that.
-    const long long units6 = (((long long)n_targets + 1535) / 1536) * (long long)src.total_tiles;
-    const bool small = n_targets < 4 * 1536 || units6 < 4ll * ctx->sm_count;
+    const long long units8 = (((long long)n_targets + 2047) / 2048) * (long long)src.total_tiles;
+    const bool small = n_targets < 4 * 2048 || units8 < 4ll * ctx->sm_count;
     if (const char* v = getenv("B200_DIRECT_VARIANT")) {      // tuning hook: "R,THREADS,MINB"
         int r = 0, th = 0, mb = 0;
         if (sscanf(v, "%d,%d,%d", &r, &th, &mb) == 3 && box == 0.f) {
@@ -509,7 +509,7 @@ int direct_forces(b200_ctx* ctx, const DirectSources& src, const void* targets4,
                      : launch_direct<4, 256, 1, true>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
     }
     return small ? launch_direct<2, 256, 2, false>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st)
-                 : launch_direct<6, 256, 1, false>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
+                 : launch_direct<8, 256, 1, false>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
 }
 
 // Per-target potential phi_i = sum_{j != i} m_j / sqrt(|d|^2 + eps^2) (positive, G = 1).
