@@ -184,6 +184,16 @@ int b200_tree_build_fixed_dev(b200_ctx* ctx, const void* posm4, size_t n, int le
  * sum as theta -> 0; no Ewald sum.  0 = open
  * boundary (default).  The reference-faithful tree is never periodic (the CPU TreeForceComputer is not). */
 int b200_tree_set_periodic(b200_ctx* ctx, float box);
+/* Energy diagnostic from the fixed-physics tree (after b200_tree_build_fixed_dev): the walk accumulating
+ * phi_i = sum m / sqrt(|d|^2 + eps^2) -- M / r for an accepted cell -- so that compute_energy
+ * (src/physics/lambda_cdm_kernels.cu:338-408) costs O(N log N) in a tree run instead of O(N^2).
+ * phi: float[n_targets] (device), positive, i == i excluded.  theta <= 1/sqrt(3) (a target must not
+ * accept a cell that contains itself), else B200_ERR_UNSUPPORTED; B200_ERR_UNSUPPORTED for the
+ * reference-faithful tree (unit-mass leaves, orphans).  _energy_: kinetic = sum 1/2 m v^2, potential =
+ * -1/2 sum m_i phi_i over the target range, two HOST doubles, blocking. */
+int b200_tree_potential_dev(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* phi, void* stream);
+int b200_tree_energy_dev(b200_ctx* ctx, size_t i0, size_t n_targets, const void* vel3, float theta,
+                         double* kinetic, double* potential, void* stream);
 int b200_tree_forces_fixed_host(b200_ctx* ctx, const float* pos3, const float* mass /* NULL = 1 */,
                                 float* acc3, size_t n, float theta, int leaf_cap, int max_depth,
                                 float eps);

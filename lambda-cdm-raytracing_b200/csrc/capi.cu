@@ -344,6 +344,33 @@ int b200_tree_export(b200_ctx* ctx, int32_t* level, float* center, float* size, 
     return tree_export(ctx, level, center, size, first_child, arrivals, part_off, part_idx, mass, com);
 }
 
+int b200_tree_potential_dev(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* phi, void* stream) {
+    if (!ctx) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return tree_potential(ctx, i0, n_targets, theta, phi, pick_stream(ctx, stream));
+}
+
+int b200_tree_energy_dev(b200_ctx* ctx, size_t i0, size_t n_targets, const void* vel3, float theta,
+                         double* kinetic, double* potential, void* stream) {
+    if (!ctx || !kinetic || !potential) return B200_ERR_INVALID;
+    *kinetic = *potential = 0.0;
+    if (n_targets == 0) return B200_OK;
+    if (!vel3) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick_stream(ctx, stream);
+    B200_TRY(ctx->energy_phi.reserve(n_targets * sizeof(float)));
+    B200_TRY(ctx->energy_out.reserve(2 * sizeof(double)));
+    B200_TRY(tree_potential(ctx, i0, n_targets, theta, ctx->energy_phi.p, st));
+    B200_TRY(energy_reduce(ctx, (const float4*)tree_posm(ctx) + i0, vel3, ctx->energy_phi.p, n_targets,
+                           ctx->energy_out.as<double>(), st));
+    double h[2];
+    B200_CUDA(cudaMemcpyAsync(h, ctx->energy_out.p, sizeof h, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    *kinetic = h[0];
+    *potential = h[1];
+    return B200_OK;
+}
+
 int b200_tree_set_periodic(b200_ctx* ctx, float box) {
     if (!ctx) return B200_ERR_INVALID;
     return tree_set_periodic(ctx, box);

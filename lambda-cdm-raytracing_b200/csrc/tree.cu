@@ -1003,7 +1003,11 @@ __device__ __forceinline__ unsigned long long w_fma2(unsigned long long a, unsig
 // accept test and the monopole with roundf, for the pair rows with the packed magic-number rounding.
 // A cell that reaches across the half-box distance from the target (|d| + edge > box/2 on any axis) is
 // always opened: its particles need not share the image of its centre of mass.
-template <bool COUNT, bool FIXED, bool PERIODIC = false>
+// POT (fixed mode, no counters): the same walk accumulating the potential phi_i = sum m / sqrt(|d|^2 + eps^2)
+// -- monopole M / r for an accepted cell -- instead of the acceleration; one float per target comes out.
+// The pair loop has no self test, so the i == i term m_i / eps is subtracted at the end; that is exact as
+// long as a target never accepts a cell that contains itself, i.e. theta <= 1/sqrt(3) (checked by the host).
+template <bool COUNT, bool FIXED, bool PERIODIC = false, bool POT = false>
 __global__ void __launch_bounds__(128)
 walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order, int i0, int n_targets,
                  const float4* __restrict__ nodes, const int* __restrict__ leaf_off,
@@ -1051,6 +1055,12 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
             w_unpk(r2, r2a, r2b);
             w_unpk(b.y, w0, w1);
             const u64 rinv = w_pk(rsqrt_fast(r2a), rsqrt_fast(r2b));
+            if constexpr (POT) {
+                float f0, f1;
+                w_unpk(w_mul2(rinv, b.y), f0, f1);
+                ax2 = w_add2(ax2, w_pk(on_lane ? f0 : 0.f, on_lane ? f1 : 0.f));
+                return;
+            }
             u64 f = w_mul2(w_mul2(rinv, rinv), rinv);                    // unit mass (:253, :340)
             if (FIXED) f = w_mul2(f, b.y);
             const bool on0 = FIXED ? on_lane : (on_lane && __float_as_int(w0) != i);
@@ -1103,8 +1113,12 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
             }
             if (!wraps && accept_cell_sq(mf.z, d2, theta, theta2)) {     // :309
                 const float rinv = rsqrt_fast(d2 + eps2);
-                const float f = c.w * rinv * rinv * rinv;                // :280-290
-                ax += f * dx; ay += f * dy; az += f * dz;
+                if constexpr (POT) {
+                    ax += c.w * rinv;
+                } else {
+                    const float f = c.w * rinv * rinv * rinv;            // :280-290
+                    ax += f * dx; ay += f * dy; az += f * dz;
+                }
                 if (COUNT) ++c_pc;
                 wake = skip;                                             // sleep through this subtree
             } else {
@@ -1122,10 +1136,14 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
     if (valid) {
         float lo, hi;
         w_unpk(ax2, lo, hi); ax += lo + hi;
-        w_unpk(ay2, lo, hi); ay += lo + hi;
-        w_unpk(az2, lo, hi); az += lo + hi;
-        const size_t o = (size_t)(i - i0) * 3;
-        acc3[o + 0] = ax; acc3[o + 1] = ay; acc3[o + 2] = az;
+        if constexpr (POT) {
+            acc3[i - i0] = ax - p.w * rsqrt_fast(eps2);                  // minus the i == i term of the pair loop
+        } else {
+            w_unpk(ay2, lo, hi); ay += lo + hi;
+            w_unpk(az2, lo, hi); az += lo + hi;
+            const size_t o = (size_t)(i - i0) * 3;
+            acc3[o + 0] = ax; acc3[o + 1] = ay; acc3[o + 2] = az;
+        }
     }
     if (COUNT) {
 #pragma unroll
@@ -1417,6 +1435,32 @@ int tree_walk(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* acc
     ctx->launches += 1;
     return B200_OK;
 }
+
+// Potential of the targets [i0, i0 + n) from the fixed-physics tree (phi: float[n_targets], positive).
+int tree_potential(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* phi, cudaStream_t st) {
+    TreeState* T = ctx->tree;
+    if (!T || !T->built) return B200_ERR_STATE;
+    if (!T->fixed) return B200_ERR_UNSUPPORTED;            // the reference's tree has unit-mass leaves and orphans
+    if (!(theta <= 0.57735f)) return B200_ERR_UNSUPPORTED;  // a target must never accept a cell containing itself
+    if (n_targets == 0) return B200_OK;
+    if (!phi || i0 + n_targets > T->n) return B200_ERR_INVALID;
+    B200_TRY(tree_target_order(ctx, T, i0, n_targets, st));
+    TreeGlobals* g = T->globals.as<TreeGlobals>();
+    const unsigned grid = (unsigned)((n_targets + 127) / 128);
+    if (T->periodic_box > 0.f)
+        walk_warp_kernel<false, true, true, true><<<grid, 128, 0, st>>>(
+            T->posm, T->order.as<int>(), (int)i0, (int)n_targets, T->nodes.as<float4>(), T->leaf_off.as<int>(),
+            T->leaf_pos.as<ulonglong2>(), theta, T->eps, T->periodic_box, (float*)phi, g);
+    else
+        walk_warp_kernel<false, true, false, true><<<grid, 128, 0, st>>>(
+            T->posm, T->order.as<int>(), (int)i0, (int)n_targets, T->nodes.as<float4>(), T->leaf_off.as<int>(),
+            T->leaf_pos.as<ulonglong2>(), theta, T->eps, T->periodic_box, (float*)phi, g);
+    B200_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return B200_OK;
+}
+
+const void* tree_posm(b200_ctx* ctx) { return ctx->tree ? (const void*)ctx->tree->posm : nullptr; }
 
 int tree_set_periodic(b200_ctx* ctx, float box) {
     if (box < 0.f) return B200_ERR_INVALID;

@@ -161,13 +161,24 @@ void B200LambdaCDMSimulation::compute_forces() {
 }
 
 void B200LambdaCDMSimulation::compute_energy() {
-    // launch_energy_computation (lambda_cdm_kernels.cu:492-516): periodic minimum image whenever the
-    // force method is (Direct); open boundary for DirectOpen and Tree.
-    const float box = (method_ == B200ForceMethod::Direct || method_ == B200ForceMethod::TreeFixedPeriodic)
-                          ? box_size_ : 0.0f;
+    // launch_energy_computation (lambda_cdm_kernels.cu:492-516).  Potential energy by the same method as the
+    // forces: the fixed-physics tree walks its potential (O(N log N); theta capped at 1/sqrt(3), where a
+    // particle can no longer accept a cell that contains it), every other method takes the O(N^2) pair sum of
+    // the direct-sum kernel -- minimum image whenever the force method is periodic.
     double e[2] = {0.0, 0.0};
-    check(b200_energy_dev(ctx_, d_posm_, num_particles_, i0_, n_local_, d_vel_, softening_, box, &e[0], &e[1], stream_),
-          "energy");
+    const bool tree_fixed = method_ == B200ForceMethod::TreeFixed || method_ == B200ForceMethod::TreeFixedPeriodic;
+    if (tree_fixed && num_particles_ > 0) {
+        check(b200_tree_build_fixed_dev(ctx_, d_posm_, num_particles_, leaf_capacity_, max_depth_, softening_, stream_),
+              "tree build (fixed physics)");
+        check(b200_tree_set_periodic(ctx_, method_ == B200ForceMethod::TreeFixedPeriodic ? box_size_ : 0.0f),
+              "tree periodic box");
+        check(b200_tree_energy_dev(ctx_, i0_, n_local_, d_vel_, theta_ < 0.577f ? theta_ : 0.577f, &e[0], &e[1], stream_),
+              "tree energy");
+    } else {
+        const float box = (method_ == B200ForceMethod::Direct) ? box_size_ : 0.0f;
+        check(b200_energy_dev(ctx_, d_posm_, num_particles_, i0_, n_local_, d_vel_, softening_, box, &e[0], &e[1], stream_),
+              "energy");
+    }
     if (world_ > 1) check(b200_allreduce_sum_f64(ctx_, e, 2), "energy all-reduce");
     kinetic_energy_ = e[0];
     potential_energy_ = e[1];

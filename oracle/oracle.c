@@ -712,6 +712,59 @@ void orc_tree_forces_fixed_periodic(const orc_tree* t, const float* pos3, const 
     if (counters) { counters[0] = c_vis; counters[1] = c_pc; counters[2] = c_pp; }
 }
 
+/* Potential from the fixed-physics tree: the walk of orc_tree_forces_fixed_periodic accumulating
+ * phi_i = sum m / sqrt(|d|^2 + eps^2) (M / r for an accepted cell), j == i skipped. */
+void orc_tree_potential_fixed(const orc_tree* t, const float* pos3, const float* mass, float theta,
+                              float eps, float box, size_t i0, size_t n_targets, float* phi) {
+    const float eps2 = eps * eps;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long long tt = 0; tt < (long long)n_targets; ++tt) {
+        size_t i = i0 + (size_t)tt;
+        float px = pos3[3 * i + 0], py = pos3[3 * i + 1], pz = pos3[3 * i + 2];
+        double acc = 0.0;
+        int32_t stack[8 * 64];
+        int sp = 0;
+        stack[sp++] = 0;
+        while (sp > 0) {
+            size_t k = (size_t)stack[--sp];
+            if (t->mass[k] == 0.0f) continue;
+            if (t->first_child[k] < 0) {
+                for (int64_t q = t->part_off[k]; q < t->part_off[k + 1]; ++q) {
+                    size_t j = (size_t)t->part_idx[q];
+                    if (j == i) continue;
+                    float dx = pos3[3 * j + 0] - px, dy = pos3[3 * j + 1] - py, dz = pos3[3 * j + 2] - pz;
+                    if (box > 0.0f) {
+                        dx = dx - box * roundf(dx / box);
+                        dy = dy - box * roundf(dy / box);
+                        dz = dz - box * roundf(dz / box);
+                    }
+                    float r2 = dx * dx + dy * dy + dz * dz + eps2;
+                    acc += (double)((mass ? mass[j] : 1.0f) / sqrtf(r2));
+                }
+                continue;
+            }
+            float dx = t->com[3 * k + 0] - px, dy = t->com[3 * k + 1] - py, dz = t->com[3 * k + 2] - pz;
+            if (box > 0.0f) {
+                dx = dx - box * roundf(dx / box);
+                dy = dy - box * roundf(dy / box);
+                dz = dz - box * roundf(dz / box);
+            }
+            float d2 = dx * dx + dy * dy + dz * dz;
+            int wraps = 0;
+            if (box > 0.0f) {
+                const float hb = box * 0.5f, sz = t->size[k];
+                wraps = (fabsf(dx) + sz > hb) || (fabsf(dy) + sz > hb) || (fabsf(dz) + sz > hb);
+            }
+            if (!wraps && (t->size[k] / sqrtf(d2)) < theta) {
+                acc += (double)(t->mass[k] / sqrtf(d2 + eps2));
+            } else {
+                for (int ch = 7; ch >= 0; --ch) stack[sp++] = t->first_child[k] + ch;
+            }
+        }
+        phi[tt] = (float)acc;
+    }
+}
+
 /* --------------------------------------------------------------- L1-L3 --- */
 /* include/physics/cosmology_model.hpp:49-61 */
 double orc_hubble_a(double a, double omega_m, double omega_k,

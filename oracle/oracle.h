@@ -96,6 +96,8 @@ void orc_tree_forces_fixed(const orc_tree* t, const float* pos3, const float* ma
 void orc_tree_forces_fixed_periodic(const orc_tree* t, const float* pos3, const float* mass, float theta,
                                     float eps, float box, size_t i0, size_t n_targets, float* out3,
                                     uint64_t* counters);
+void orc_tree_potential_fixed(const orc_tree* t, const float* pos3, const float* mass, float theta,
+                              float eps, float box, size_t i0, size_t n_targets, float* phi);
 void orc_tree_free(orc_tree* t);
 /* 1 if the two canonical tables are identical (topology, stored particles,
  * centres, sizes, mass, com bit patterns), else 0. */

@@ -101,6 +101,8 @@ class Oracle:
                                             C.c_void_p]
         L.orc_tree_forces_fixed_periodic.argtypes = [C.POINTER(_Tree), _f32p, _f32p, C.c_float, C.c_float, C.c_float,
                                                      sz, sz, _f32p, C.c_void_p]
+        L.orc_tree_potential_fixed.argtypes = [C.POINTER(_Tree), _f32p, _f32p, C.c_float, C.c_float, C.c_float, sz, sz,
+                                               _f32p]
         L.orc_tree_free.argtypes = [C.POINTER(_Tree)]
         L.orc_tree_equal.argtypes = [C.POINTER(_Tree)] * 2; L.orc_tree_equal.restype = C.c_int
         L.orc_tree_forces.argtypes = [C.POINTER(_Tree), _f32p, C.c_float, sz, sz, _f32p, C.c_void_p]
@@ -188,6 +190,15 @@ class Oracle:
         self.lib.orc_tree_forces_fixed_periodic(tree._ptr, pos, mass, theta, eps, box, i0, nt, out,
                                                 cnt.ctypes.data_as(C.c_void_p))
         return (out, cnt) if counters else out
+
+    def tree_potential_fixed(self, tree, pos, mass, theta=0.5, eps=0.01, box=0.0, i0=0, n_targets=None):
+        pos = np.ascontiguousarray(pos, np.float32)
+        mass = np.ascontiguousarray(mass, np.float32)
+        n = pos.shape[0]
+        nt = n - i0 if n_targets is None else n_targets
+        phi = np.empty(nt, np.float32)
+        self.lib.orc_tree_potential_fixed(tree._ptr, pos, mass, theta, eps, box, i0, nt, phi)
+        return phi
 
     def tree_equal(self, a, b):
         return bool(self.lib.orc_tree_equal(a._ptr, b._ptr))

@@ -133,3 +133,49 @@ def test_fixed_tree_periodic_walk(engine, oracle):
     finally:
         engine.tree_set_periodic(0.0)
         engine.tree_set_counting(False)
+
+
+@pytest.mark.parametrize("box", [0.0, 100.0])
+def test_fixed_tree_potential_and_energy(engine, oracle, box):
+    """Tree potential (the walk accumulating m / r): against the oracle's walk, against the direct-sum
+    potential, and as the energy diagnostic of a tree run."""
+    n = 30000
+    pos = uniform_np(n, seed=51, lo=0.0, hi=100.0) if box > 0 else clustered_np(n, seed=51)
+    mass = masses_np(n, seed=52)
+    rng = np.random.default_rng(53)
+    vel = rng.normal(0, 50, (n, 3)).astype(np.float32)
+    posm = _posm(pos, mass)
+    engine.tree_build_fixed_dev(posm, n, 8, 20, eps=0.05)
+    phi = torch.empty(n, dtype=torch.float32, device="cuda")
+    t = oracle.tree_build_fixed(pos, mass, 8, 20)
+    try:
+        engine.tree_set_periodic(box)
+        engine.tree_potential_dev(phi, 0, n, theta=0.5)
+        torch.cuda.synchronize()
+        got = phi.cpu().numpy()
+        want = oracle.tree_potential_fixed(t, pos, mass, 0.5, 0.05, box)
+        assert np.max(np.abs(got - want) / want) < 2e-5
+        phi_d = torch.empty(n, dtype=torch.float32, device="cuda")
+        engine.direct_potential_dev(posm, phi_d, eps=0.05, box=box)
+        torch.cuda.synchronize()
+        d = phi_d.cpu().numpy()
+        assert np.sqrt(((got - d) ** 2).sum() / (d ** 2).sum()) < 2e-3          # monopole error at theta 0.5
+        ke, pe = engine.tree_energy_dev(torch.from_numpy(vel).cuda(), 0, n, theta=0.5)
+        ke_d, pe_d = engine.energy_dev(posm, torch.from_numpy(vel).cuda(), eps=0.05, box=box)
+        assert abs(ke - ke_d) <= 1e-12 * ke_d and abs(pe / pe_d - 1.0) < 1e-3
+        # target shards add up
+        k2 = p2 = 0.0
+        for lo, hi in ((0, 10000), (10000, n)):
+            a, b = engine.tree_energy_dev(torch.from_numpy(vel[lo:hi].copy()).cuda(), lo, hi - lo, theta=0.5)
+            k2 += a
+            p2 += b
+        assert abs(k2 - ke) <= 1e-12 * ke and abs(p2 - pe) <= 1e-9 * abs(pe)
+        import b200grav
+        with pytest.raises(b200grav.B200Error):
+            engine.tree_potential_dev(phi, 0, n, theta=0.7)                     # a target could accept its own cell
+    finally:
+        engine.tree_set_periodic(0.0)
+    engine.tree_build_dev(posm, n, 100.0, 8, 20)
+    import b200grav
+    with pytest.raises(b200grav.B200Error):
+        engine.tree_potential_dev(phi, 0, n, theta=0.5)                         # reference-faithful tree: unsupported
