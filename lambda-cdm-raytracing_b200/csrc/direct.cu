@@ -247,9 +247,9 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
                 u64 dy = add2(Y, nyi[r]);
                 u64 dz = add2(Z, nzi[r]);
                 if constexpr (PERIODIC) {
-                    u64 qx = add2(add2(mul2(dx, inv_box2), magic2), nmagic2);
-                    u64 qy = add2(add2(mul2(dy, inv_box2), magic2), nmagic2);
-                    u64 qz = add2(add2(mul2(dz, inv_box2), magic2), nmagic2);
+                    u64 qx = add2(fma2(dx, inv_box2, magic2), nmagic2);      // rint(d / box): 3 lane-ops per component
+                    u64 qy = add2(fma2(dy, inv_box2, magic2), nmagic2);
+                    u64 qz = add2(fma2(dz, inv_box2, magic2), nmagic2);
                     dx = fma2(qx, nbox2, dx);
                     dy = fma2(qy, nbox2, dy);
                     dz = fma2(qz, nbox2, dz);
@@ -489,6 +489,14 @@ int direct_forces(b200_ctx* ctx, const DirectSources& src, const void* targets4,
     const bool small = n_targets < 4 * 2048 || units8 < 4ll * ctx->sm_count;
     if (const char* v = getenv("B200_DIRECT_VARIANT")) {      // tuning hook: "R,THREADS,MINB"
         int r = 0, th = 0, mb = 0;
+        if (sscanf(v, "%d,%d,%d", &r, &th, &mb) == 3 && box > 0.f) {
+#define B200_PVARIANT(RR, TH, MB) \
+    if (r == RR && th == TH && mb == MB) \
+        return launch_direct<RR, TH, MB, true>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
+            B200_PVARIANT(4, 256, 1) B200_PVARIANT(5, 256, 1) B200_PVARIANT(6, 256, 1) B200_PVARIANT(8, 256, 1)
+#undef B200_PVARIANT
+            return B200_ERR_UNSUPPORTED;
+        }
         if (sscanf(v, "%d,%d,%d", &r, &th, &mb) == 3 && box == 0.f) {
 #define B200_VARIANT(RR, TH, MB) \
     if (r == RR && th == TH && mb == MB) \

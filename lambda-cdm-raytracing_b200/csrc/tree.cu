@@ -1044,9 +1044,9 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
         auto row2 = [&](const ulonglong2& a, const ulonglong2& b) {      // a = {x0 x1 | y0 y1}, b = {z0 z1 | w0 w1}
             u64 dx = w_add2(a.x, npx), dy = w_add2(a.y, npy), dz = w_add2(b.x, npz);
             if constexpr (PERIODIC) {
-                dx = w_fma2(w_add2(w_add2(w_mul2(dx, inv_box2), magic2), nmagic2), nbox2, dx);
-                dy = w_fma2(w_add2(w_add2(w_mul2(dy, inv_box2), magic2), nmagic2), nbox2, dy);
-                dz = w_fma2(w_add2(w_add2(w_mul2(dz, inv_box2), magic2), nmagic2), nbox2, dz);
+                dx = w_fma2(w_add2(w_fma2(dx, inv_box2, magic2), nmagic2), nbox2, dx);
+                dy = w_fma2(w_add2(w_fma2(dy, inv_box2, magic2), nmagic2), nbox2, dy);
+                dz = w_fma2(w_add2(w_fma2(dz, inv_box2, magic2), nmagic2), nbox2, dz);
             }
             u64 r2 = w_fma2(dx, dx, eps2_2);
             r2 = w_fma2(dy, dy, r2);

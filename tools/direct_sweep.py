@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--variants", default="default;2,256,2;4,256,1;4,256,2;5,256,1;6,256,1;7,256,1;8,256,1;4,384,1;4,512,1;3,512,1;6,128,2;8,128,2")
     ap.add_argument("--masses", default="unit", choices=["unit", "random"])
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--box", type=float, default=0.0, help="> 0: the periodic (minimum-image) instance")
     args = ap.parse_args()
     eng = b200grav.Engine(0)
     rng = np.random.default_rng(0)
@@ -38,7 +39,7 @@ def main():
             os.environ["B200_DIRECT_VARIANT"] = v
         best = 1e30
         for _ in range(args.reps):
-            eng.direct_forces_dev(posm, acc, 0, n, eps=0.01)
+            eng.direct_forces_dev(posm, acc, 0, n, eps=0.01, box=args.box)
             torch.cuda.synchronize()
             best = min(best, eng.last_kernel_ms())
         a = acc.cpu().numpy()
