@@ -33,3 +33,16 @@ def test_host_sharded_simulation_matches_single_gpu():
     assert "FAIL" not in r.stdout
     if "SKIP" in r.stdout:
         pytest.skip(r.stdout.strip())
+
+
+@pytest.mark.parametrize("args", [("20000", "20", "direct", "random"), ("32768", "20", "tree-fixed", "zeldovich"),
+                                  ("20000", "10", "tree", "random"), ("20000", "10", "tree-periodic", "random")])
+def test_example_program(args):
+    """The reference's cuda_nbody_test flow (examples/cuda_nbody_test.cpp) on the B200 simulation class."""
+    exe = os.path.join(ROOT, "lambda-cdm-raytracing_b200", "examples", "_bin", "nbody_b200")
+    if not os.path.exists(exe):
+        pytest.skip("examples/_bin/nbody_b200 not built (needs the reference headers at build time)")
+    r = subprocess.run([exe, *args], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:], r.stderr[-1000:])
+    assert r.returncode == 0, r.stderr[-1000:]
+    assert "particle-updates/second" in r.stdout and "nan" not in r.stdout.lower()
