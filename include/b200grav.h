@@ -174,7 +174,10 @@ int b200_tree_forces_host(b200_ctx* ctx, const float* pos3, const float* mass,
  * leaf pairs use the sources' masses, the root cube is fitted to the data (centre = bounding-box
  * midpoint, edge = largest extent * 1.00001), eps is a parameter.  Same kernels, same walk
  * (b200_tree_walk_dev / _stats / _export / _counters apply).  Checked against the FP64 direct
- * sum: 1.3e-3 relative L2 at theta = 0.5, 7e-5 at theta = 0.2 (uniform, leaf_cap 8). */
+ * sum: 1.3e-3 relative L2 at theta = 0.5, 7e-5 at theta = 0.2 (uniform, leaf_cap 8).
+ * The node table of this mode holds N/2 internal nodes (typical trees need N/25); a pathological input
+ * that needs more (many tight knots of leaf_cap + 1 particles) fails loudly: the walk fills its output
+ * with NaN, b200_tree_stats / _export / b200_tree_forces_fixed_host return B200_ERR_NOMEM. */
 int b200_tree_build_fixed_dev(b200_ctx* ctx, const void* posm4, size_t n, int leaf_cap,
                               int max_depth, float eps, void* stream);
 /* Fixed-physics walks only: box > 0 takes every separation (cell and particle) to its nearest periodic

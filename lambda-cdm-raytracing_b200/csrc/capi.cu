@@ -300,7 +300,9 @@ int b200_tree_forces_fixed_host(b200_ctx* ctx, const float* pos3, const float* m
     B200_TRY(tree_walk(ctx, 0, n, theta, ctx->h_acc3.p, st));
     B200_CUDA(cudaMemcpyAsync(acc3, ctx->h_acc3.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
-    return B200_OK;
+    int overflow = 0;
+    B200_TRY(tree_overflowed(ctx, &overflow));
+    return overflow ? B200_ERR_NOMEM : B200_OK;      // the walk has filled acc3 with NaN
 }
 
 int b200_tree_walk_dev(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* acc3,

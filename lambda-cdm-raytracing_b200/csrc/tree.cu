@@ -1082,6 +1082,16 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
         if (k2 < np) row2(src[2 * k2], src[2 * k2 + 1]);
     };
 
+    // a build that ran out of node slots (possible only in the fixed mode, whose node count has no a-priori
+    // bound short of 2.3 N) left an incomplete tree: fail loudly rather than return a plausible force
+    if (g->error) {
+        if (valid) {
+            const float nan = __int_as_float(0x7fc00000);
+            if (POT) acc3[i - i0] = nan;
+            else { const size_t o = (size_t)(i - i0) * 3; acc3[o] = acc3[o + 1] = acc3[o + 2] = nan; }
+        }
+        return;
+    }
     // the root: massless -> nothing to do (:260); a leaf -> one pair loop (:268-270).  Every node the
     // links lead to after that is internal and carries mass (pack_walk_kernel).
     int k = 0;
@@ -1477,6 +1487,16 @@ static int fetch_globals(b200_ctx* ctx, TreeState* T, TreeGlobals* h) {
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
     B200_CUDA(cudaDeviceSynchronize());
     B200_CUDA(cudaMemcpy(h, T->globals.p, sizeof(TreeGlobals), cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+// 1 if the last build overflowed its node table (synchronises)
+int tree_overflowed(b200_ctx* ctx, int* flag) {
+    TreeState* T = ctx->tree;
+    if (!T || !T->built) return B200_ERR_STATE;
+    TreeGlobals h;
+    B200_TRY(fetch_globals(ctx, T, &h));
+    *flag = h.error ? 1 : 0;
     return B200_OK;
 }
 

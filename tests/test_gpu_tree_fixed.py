@@ -179,3 +179,28 @@ def test_fixed_tree_potential_and_energy(engine, oracle, box):
     import b200grav
     with pytest.raises(b200grav.B200Error):
         engine.tree_potential_dev(phi, 0, n, theta=0.5)                         # reference-faithful tree: unsupported
+
+
+def test_fixed_tree_overflow_fails_loudly(engine):
+    """The fixed tree's node count has no useful a-priori bound (tight groups of leaf_cap + 1 particles make
+    20-level chains); the table holds N/2 internal nodes.  A build that runs out must not yield a plausible
+    force: the walk writes NaN and the host entry point reports B200_ERR_NOMEM."""
+    import b200grav
+    rng = np.random.default_rng(61)
+    groups = rng.uniform(-40, 40, (12, 3))
+    pos = np.repeat(groups, 9, axis=0) + rng.uniform(-2e-5, 2e-5, (108, 3))        # 12 knots of 9 particles
+    pos = pos.astype(np.float32)
+    mass = np.ones(len(pos), np.float32)
+    with pytest.raises(b200grav.B200Error, match="allocation"):
+        engine.tree_forces_fixed_host(pos, mass, theta=0.5, leaf_cap=8, max_depth=20, eps=0.01)
+    posm = _posm(pos, mass)
+    engine.tree_build_fixed_dev(posm, len(pos), 8, 20, eps=0.01)
+    acc = torch.zeros((len(pos), 3), dtype=torch.float32, device="cuda")
+    engine.tree_walk_dev(acc, 0, len(pos), theta=0.5)
+    torch.cuda.synchronize()
+    assert torch.isnan(acc).all()
+    with pytest.raises(b200grav.B200Error):
+        engine.tree_stats()
+    # the same particles with room to spare (leaf capacity 16: no chains) are fine
+    out = engine.tree_forces_fixed_host(pos, mass, theta=0.5, leaf_cap=16, max_depth=20, eps=0.01)
+    assert np.isfinite(out).all()
