@@ -159,6 +159,12 @@ int b200_tree_build_dev(b200_ctx* ctx, const void* posm4, size_t n, float box,
  * of the array the tree was built from. acc3: float[3*n_targets]. */
 int b200_tree_walk_dev(b200_ctx* ctx, size_t i0, size_t n_targets, float theta,
                        void* acc3, void* stream);
+/* The two phases the reference class exposes separately (include/forces/tree_force_computer.hpp:78-80,
+ * build_tree / compute_tree_forces) on host arrays; the particles stay on the device in between.
+ * b200_tree_walk_host walks all n particles of the last b200_tree_build_host. */
+int b200_tree_build_host(b200_ctx* ctx, const float* pos3, const float* mass, size_t n, float box,
+                         int leaf_cap, int max_depth);
+int b200_tree_walk_host(b200_ctx* ctx, float* acc3, size_t n, float theta);
 /* IForceComputer::compute_forces for "TreeForceComputer" on host arrays. */
 int b200_tree_forces_host(b200_ctx* ctx, const float* pos3, const float* mass,
                           float* acc3, size_t n, float theta, int leaf_cap,

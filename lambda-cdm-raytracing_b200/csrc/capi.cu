@@ -312,25 +312,44 @@ int b200_tree_walk_dev(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, 
     return tree_walk(ctx, i0, n_targets, theta, acc3, pick_stream(ctx, stream));
 }
 
-int b200_tree_forces_host(b200_ctx* ctx, const float* pos3, const float* mass, float* acc3, size_t n,
-                          float theta, int leaf_cap, int max_depth, float box) {
+// The two phases of compute_forces as the reference class exposes them (tree_force_computer.hpp:78-80:
+// build_tree / compute_tree_forces): the particles stay on the device between the calls.
+int b200_tree_build_host(b200_ctx* ctx, const float* pos3, const float* mass, size_t n, float box,
+                         int leaf_cap, int max_depth) {
     if (!ctx) return B200_ERR_INVALID;
-    if (n == 0) return B200_OK;            // tree_force_computer.cpp:83
-    if (!pos3 || !mass || !acc3) return B200_ERR_INVALID;
+    if (n == 0) return B200_OK;
+    if (!pos3 || !mass) return B200_ERR_INVALID;
     B200_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     B200_TRY(ctx->h_pos3.reserve(n * 3 * sizeof(float)));
     B200_TRY(ctx->h_mass.reserve(n * sizeof(float)));
     B200_TRY(ctx->h_posm4.reserve(n * 4 * sizeof(float)));
-    B200_TRY(ctx->h_acc3.reserve(n * 3 * sizeof(float)));
     B200_CUDA(cudaMemcpyAsync(ctx->h_pos3.p, pos3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaMemcpyAsync(ctx->h_mass.p, mass, n * sizeof(float), cudaMemcpyHostToDevice, st));
     B200_TRY(pack_posm(ctx, ctx->h_pos3.p, ctx->h_mass.p, n, ctx->h_posm4.p, st));
-    B200_TRY(tree_build(ctx, ctx->h_posm4.p, n, box, leaf_cap, max_depth, false, 0.01f, st));
+    return tree_build(ctx, ctx->h_posm4.p, n, box, leaf_cap, max_depth, false, 0.01f, st);
+}
+
+int b200_tree_walk_host(b200_ctx* ctx, float* acc3, size_t n, float theta) {
+    if (!ctx) return B200_ERR_INVALID;
+    if (n == 0) return B200_OK;
+    if (!acc3) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    B200_TRY(ctx->h_acc3.reserve(n * 3 * sizeof(float)));
     B200_TRY(tree_walk(ctx, 0, n, theta, ctx->h_acc3.p, st));
     B200_CUDA(cudaMemcpyAsync(acc3, ctx->h_acc3.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     return B200_OK;
+}
+
+int b200_tree_forces_host(b200_ctx* ctx, const float* pos3, const float* mass, float* acc3, size_t n,
+                          float theta, int leaf_cap, int max_depth, float box) {
+    if (!ctx) return B200_ERR_INVALID;
+    if (n == 0) return B200_OK;            // tree_force_computer.cpp:83
+    if (!pos3 || !mass || !acc3) return B200_ERR_INVALID;
+    B200_TRY(b200_tree_build_host(ctx, pos3, mass, n, box, leaf_cap, max_depth));
+    return b200_tree_walk_host(ctx, acc3, n, theta);
 }
 
 int b200_tree_stats(b200_ctx* ctx, size_t* n_nodes, size_t* n_leaves, size_t* depth, size_t* n_stored) {

@@ -4,6 +4,7 @@
 
 #include <iostream>
 #include <stdexcept>
+#include <vector>
 
 #include "b200grav.h"
 #include "core/simulation_context.hpp"
@@ -92,6 +93,33 @@ void B200TreeForceComputer::compute_forces(const float* positions, const float* 
         fail("TreeForceComputer::compute_forces", rc);
     }
     force_evaluations_ += num_particles;
+    tree_traversals_ += num_particles;
+}
+
+void B200TreeForceComputer::build_tree(const float* positions, const float* masses, size_t num_particles) {
+    if (num_particles == 0) return;
+    require_ctx();
+    const int rc = b200_tree_build_host(ctx_, positions, masses, num_particles, box_size_, (int)leaf_capacity_, max_depth_);
+    if (rc != B200_OK) fail("TreeForceComputer::build_tree", rc);
+}
+
+void B200TreeForceComputer::compute_tree_forces(const float*, float* forces, size_t num_particles) const {
+    if (num_particles == 0) return;
+    require_ctx();
+    const int rc = b200_tree_walk_host(ctx_, forces, num_particles, theta_);
+    if (rc != B200_OK) fail("TreeForceComputer::compute_tree_forces", rc);
+}
+
+void B200TreeForceComputer::count_interactions(size_t num_particles, unsigned long long counts[3]) const {
+    require_ctx();
+    std::vector<float> scratch(3 * num_particles);
+    uint64_t c[3] = {0, 0, 0};
+    int rc = b200_tree_set_counting(ctx_, 1);
+    if (rc == B200_OK) rc = b200_tree_walk_host(ctx_, scratch.data(), num_particles, theta_);
+    if (rc == B200_OK) rc = b200_tree_counters(ctx_, c);
+    b200_tree_set_counting(ctx_, 0);
+    if (rc != B200_OK) fail("TreeForceComputer::count_interactions", rc);
+    for (int k = 0; k < 3; ++k) counts[k] = c[k];
 }
 
 size_t B200TreeForceComputer::get_node_count() const {

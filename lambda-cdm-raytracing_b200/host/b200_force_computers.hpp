@@ -82,6 +82,7 @@ class B200TreeForceComputer : public B200ComputerBase {
     size_t leaf_capacity_ = 8;
     int max_depth_ = 20;
     float box_size_ = 100.0f;
+    mutable size_t tree_traversals_ = 0;
     bool fixed_physics_ = false;                // see set_fixed_physics
     float softening_ = 0.01f;                   // fixed-physics mode only (the reference hard-codes 0.01)
 public:
@@ -91,6 +92,10 @@ public:
     std::string get_type() const override { return "TreeForceComputer"; }
     void compute_forces(const float* positions, const float* masses, float* forces,
                         size_t num_particles, const std::any& params = {}) override;
+    // tree_force_computer.hpp:78-80: the two phases of compute_forces (the tree stays on the device in between;
+    // `positions` of compute_tree_forces must be the array build_tree saw, as in the reference's own call :125)
+    void build_tree(const float* positions, const float* masses, size_t num_particles);
+    void compute_tree_forces(const float* positions, float* forces, size_t num_particles) const;
     // tree_force_computer.hpp:83-93
     void set_opening_angle(float theta) { theta_ = theta; }
     void set_leaf_capacity(size_t capacity) { leaf_capacity_ = capacity; }
@@ -107,6 +112,16 @@ public:
     void set_fixed_physics(bool on) { fixed_physics_ = on; }
     bool get_fixed_physics() const { return fixed_physics_; }
     void set_softening(float eps) { softening_ = eps; }
+    // tree_force_computer.hpp:96-98 (the reference adds N to both per compute_forces call, :126-127)
+    size_t get_tree_traversals() const { return tree_traversals_; }
+    void reset_statistics() const { force_evaluations_ = 0; tree_traversals_ = 0; }
+    float get_tree_efficiency() const {            // tree_force_computer.cpp:420-423
+        const size_t n2 = get_max_particles() * get_max_particles();
+        return n2 > 0 ? static_cast<float>(force_evaluations_) / n2 : 0.0f;
+    }
+    // What the reference's counters do not say: nodes visited, cell and pair interactions of one more walk
+    // over the current tree (valid after a compute_forces / build_tree call).
+    void count_interactions(size_t num_particles, unsigned long long counts[3]) const;
     // tree_force_computer.hpp:100-103 (valid after a compute_forces call)
     size_t get_tree_depth() const;
     size_t get_node_count() const;

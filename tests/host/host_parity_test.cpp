@@ -85,6 +85,23 @@ int main() {
               bt->get_tree_depth() == ct->get_tree_depth(),
           "tree statistics equal: %zu nodes, %zu leaves, depth %zu", bt->get_node_count(), bt->get_leaf_count(), bt->get_tree_depth());
 
+    {   // the two phases the reference class exposes, and its statistics getters (tree_force_computer.hpp:78-103)
+        std::vector<float> f2(3 * n), f1(3 * n);
+        tree->compute_forces(pos.data(), mass.data(), f1.data(), n);
+        bt->reset_statistics();
+        bt->build_tree(pos.data(), mass.data(), n);
+        bt->compute_tree_forces(pos.data(), f2.data(), n);
+        bool same = true;
+        for (size_t i = 0; i < 3 * n && same; ++i) same = f1[i] == f2[i];
+        unsigned long long cnt[3];
+        bt->count_interactions(n, cnt);
+        tree->compute_forces(pos.data(), mass.data(), f1.data(), n);
+        CHECK(same && bt->get_tree_traversals() == n && bt->get_force_evaluations() == n && cnt[0] > n && cnt[1] > 0 &&
+                  cnt[2] > 0 && bt->get_tree_efficiency() > 0.0f,
+              "build_tree + compute_tree_forces == compute_forces bitwise; %.0f node visits, %.0f cell and %.0f pair "
+              "interactions per particle", (double)cnt[0] / n, (double)cnt[1] / n, (double)cnt[2] / n);
+    }
+
     {   // ForceComputeParameters through std::any
         ForceComputeParameters p;
         p.softening_length = 0.5f;
