@@ -264,6 +264,18 @@ int b200_sort_pairs_dev(b200_ctx* ctx, const void* keys_in_u32, size_t n, void* 
                       (int32_t*)perm_out_i32, 32, ctx->sort_scratch.p, pick_stream(ctx, stream));
 }
 
+int b200_spatial_order_dev(b200_ctx* ctx, const void* posm4, size_t n, float box, void* perm_i32, void* stream) {
+    if (!ctx || (n && (!posm4 || !perm_i32)) || !(box > 0.f)) return B200_ERR_INVALID;
+    if (n == 0) return B200_OK;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick_stream(ctx, stream);
+    B200_TRY(ctx->h_mass.reserve(2 * n * sizeof(uint32_t)));           // keys in / keys out
+    B200_TRY(ctx->sort_scratch.reserve(sort_scratch_bytes(n)));
+    uint32_t* keys = ctx->h_mass.as<uint32_t>();
+    B200_TRY(hilbert_keys(ctx, posm4, n, box, nullptr, keys, st));
+    return sort_pairs(ctx, keys, n, keys + n, (int32_t*)perm_i32, 30, ctx->sort_scratch.p, st);
+}
+
 int b200_tree_build_dev(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_cap,
                         int max_depth, void* stream) {
     if (!ctx) return B200_ERR_INVALID;

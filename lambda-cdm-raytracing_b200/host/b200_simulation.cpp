@@ -63,6 +63,32 @@ void B200LambdaCDMSimulation::set_particles(const float* pos3, const float* vel3
     current_step_ = 0;
 }
 
+void B200LambdaCDMSimulation::set_particles_spatially_ordered(const float* pos3, const float* vel3, const float* mass) {
+    const size_t n = num_particles_;
+    order_.assign(n, 0);
+    if (n == 0) return;
+    // keys need positions relative to a cube centred on the origin
+    const bool centred = method_ == B200ForceMethod::Tree || method_ == B200ForceMethod::TreeFixed;
+    const float shift = centred ? 0.0f : 0.5f * box_size_;
+    std::vector<float> p(3 * n);
+    for (size_t i = 0; i < 3 * n; ++i) p[i] = pos3[i] - shift;
+    void* d_perm = nullptr;
+    check(b200_device_alloc(ctx_, n * 4, &d_perm), "alloc order");
+    int rc = b200_memcpy_h2d(ctx_, d_tmp3_, p.data(), n * 12, stream_);
+    if (rc == B200_OK) rc = b200_pack_posm_dev(ctx_, d_tmp3_, nullptr, n, d_posm_, stream_);
+    if (rc == B200_OK) rc = b200_spatial_order_dev(ctx_, d_posm_, n, box_size_, d_perm, stream_);
+    if (rc == B200_OK) rc = b200_memcpy_d2h(ctx_, order_.data(), d_perm, n * 4, stream_);
+    b200_device_free(ctx_, d_perm);
+    check(rc, "spatial order");
+    std::vector<float> ps(3 * n), vs(3 * n), ms(mass ? n : 0);
+    for (size_t k = 0; k < n; ++k) {
+        const size_t i = (size_t)order_[k];
+        for (int c = 0; c < 3; ++c) { ps[3 * k + c] = pos3[3 * i + c]; vs[3 * k + c] = vel3[3 * i + c]; }
+        if (mass) ms[k] = mass[i];
+    }
+    set_particles(ps.data(), vs.data(), mass ? ms.data() : nullptr);
+}
+
 void B200LambdaCDMSimulation::initialize_particles(uint32_t seed) {
     // generate_initial_conditions (lambda_cdm_impl.cu:26-49): uniform positions in the box, Gaussian
     // velocities with dispersion 100*sqrt(omega_m) (:153), unit masses -- seeded here.

@@ -53,6 +53,7 @@ class B200LambdaCDMSimulation {
     int leaf_capacity_ = 8, max_depth_ = 20;
     bool have_forces_ = false;
     double kinetic_energy_ = 0.0, potential_energy_ = 0.0;
+    std::vector<int> order_;                // set_particles_spatially_ordered
     int rank_ = 0, world_ = 1;              // enable_sharding()
     size_t i0_ = 0, n_local_ = 0;           // this rank's particle range
     void* d_posm_ = nullptr;                // float4[N]
@@ -73,6 +74,12 @@ public:
     void initialize_particles(uint32_t seed = 12345);          // uniform [0,box), v ~ N(0, 100*sqrt(omega_m)), m = 1
     // host arrays of all N particles (every rank passes the same data), mass may be null
     void set_particles(const float* pos3, const float* vel3, const float* mass);
+    // Same, but the particles are first put in space-filling-curve order (b200_spatial_order_dev; the cube is
+    // centred on the origin for the tree methods and on box/2 otherwise): contiguous index ranges -- the shards
+    // of a multi-GPU run -- become compact regions.  get_particle_order()[k] is the caller's index of stored
+    // particle k.
+    void set_particles_spatially_ordered(const float* pos3, const float* vel3, const float* mass);
+    const std::vector<int>& get_particle_order() const { return order_; }
     // Multi-GPU: call once, before set_particles/initialize_particles, on every rank with the
     // 128-byte id rank 0 obtained from b200_shard_unique_id().  Collective (blocks until all
     // `world` ranks have called it).

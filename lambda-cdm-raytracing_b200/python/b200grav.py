@@ -26,7 +26,7 @@ EXPORTS = [
     "b200_device_alloc", "b200_device_free", "b200_memcpy_h2d", "b200_memcpy_d2h", "b200_unpack_pos3_dev", "b200_ipc_export", "b200_ipc_open", "b200_ipc_close",
     "b200_shard_range", "b200_shard_unique_id", "b200_shard_init", "b200_shard_finalize", "b200_shard_info",
     "b200_allgather_sources_dev", "b200_allreduce_sum_f64", "b200_direct_potential_dev", "b200_energy_dev",
-    "b200_ic_params_default", "b200_zeldovich_ics_dev", "b200_force_error_dev", "b200_power_spectrum_dev", "b200_tree_build_fixed_dev", "b200_tree_forces_fixed_host", "b200_tree_set_periodic", "b200_tree_build_host", "b200_tree_walk_host", "b200_tree_potential_dev", "b200_tree_energy_dev",
+    "b200_ic_params_default", "b200_zeldovich_ics_dev", "b200_force_error_dev", "b200_power_spectrum_dev", "b200_tree_build_fixed_dev", "b200_tree_forces_fixed_host", "b200_tree_set_periodic", "b200_spatial_order_dev", "b200_tree_build_host", "b200_tree_walk_host", "b200_tree_potential_dev", "b200_tree_energy_dev",
     "b200_fp32_peak_probe", "b200_last_kernel_ms", "b200_set_timing", "b200_launch_count",
 ]
 
@@ -72,6 +72,7 @@ def load_library(path=None):
     L.b200_tree_build_fixed_dev.argtypes = [vp, vp, sz, i32, i32, f32, vp]
     L.b200_tree_forces_fixed_host.argtypes = [vp, vp, vp, vp, sz, f32, i32, i32, f32]
     L.b200_tree_set_periodic.argtypes = [vp, f32]
+    L.b200_spatial_order_dev.argtypes = [vp, vp, sz, f32, vp, vp]
     L.b200_tree_build_host.argtypes = [vp, vp, vp, sz, f32, i32, i32]
     L.b200_tree_walk_host.argtypes = [vp, vp, sz, f32]
     L.b200_tree_potential_dev.argtypes = [vp, sz, sz, f32, vp, vp]
@@ -240,6 +241,10 @@ class Engine:
         self._check(self.L.b200_tree_energy_dev(self._h, i0, n_targets, _ptr(vel), theta, C.byref(ke), C.byref(pe),
                                                 _stream(stream)))
         return ke.value, pe.value
+
+    def spatial_order_dev(self, posm, n, box, perm, stream=None):
+        """perm[k] = index of the k-th particle along a Hilbert curve over [-box/2, box/2)^3."""
+        self._check(self.L.b200_spatial_order_dev(self._h, _ptr(posm), n, box, _ptr(perm), _stream(stream)))
 
     def tree_set_periodic(self, box):
         """Fixed-physics walks: minimum-image separations in a periodic box (0 = open boundary)."""

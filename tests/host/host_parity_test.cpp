@@ -212,6 +212,36 @@ int main() {
     }
 
     std::cout.rdbuf(quiet.rdbuf());
+    {   // particles stored in space-filling-curve order: same physics, indices mapped back
+        const size_t m_n = 20000;
+        std::vector<float> v0(3 * m_n, 0.0f);
+        physics::B200LambdaCDMSimulation a(m_n, 100.0f), b(m_n, 100.0f);
+        a.set_force_method(physics::B200ForceMethod::TreeFixed);
+        b.set_force_method(physics::B200ForceMethod::TreeFixed);
+        a.set_particles(pos.data(), v0.data(), mass.data());
+        b.set_particles_spatially_ordered(pos.data(), v0.data(), mass.data());
+        for (int s = 0; s < 3; ++s) { a.step(1e-4); b.step(1e-4); }
+        std::vector<float> xa(3 * m_n), xb(3 * m_n), xb_back(3 * m_n);
+        a.copy_positions_to_host(xa.data());
+        b.copy_positions_to_host(xb.data());
+        const std::vector<int>& ord = b.get_particle_order();
+        std::vector<char> seen(m_n, 0);
+        bool perm_ok = ord.size() == m_n;
+        double jump = 0.0;
+        for (size_t k = 0; k < m_n && perm_ok; ++k) {
+            perm_ok = ord[k] >= 0 && (size_t)ord[k] < m_n && !seen[ord[k]];
+            if (perm_ok) seen[ord[k]] = 1;
+            for (int c = 0; c < 3; ++c) xb_back[3 * (size_t)ord[k] + c] = xb[3 * k + c];
+            if (k) jump += std::fabs(xb[3 * k] - xb[3 * k - 3]) + std::fabs(xb[3 * k + 1] - xb[3 * k - 2]) +
+                           std::fabs(xb[3 * k + 2] - xb[3 * k - 1]);
+        }
+        double dmax = 0.0;
+        for (size_t i = 0; i < 3 * m_n; ++i) dmax = std::fmax(dmax, std::fabs((double)xa[i] - xb_back[i]));
+        CHECK(perm_ok && dmax < 1e-4 && jump / m_n < 12.0,
+              "spatially ordered storage: same trajectories (max |dx| %.2e), neighbours in storage %.1f apart (L1)",
+              dmax, jump / m_n);
+    }
+
     {   // device-generated initial conditions + the particle / power-spectrum accessors of the simulation class
         const size_t m_n = 32768;                                   // 32^3: every grid point
         physics::B200LambdaCDMSimulation sim(m_n, 100.0f);

@@ -183,3 +183,21 @@ def test_tree_zeldovich_c3(engine, oracle):
     keys = torch.empty(n, dtype=torch.int32, device="cuda")
     engine.morton_keys_dev(_posm(zp, zm), n, 100.0, keys)
     assert np.array_equal(keys.cpu().numpy().view(np.uint32), oracle.morton_keys(zp, 100.0))
+
+
+def test_spatial_order_is_a_local_permutation(engine):
+    """b200_spatial_order_dev: a permutation of the particles along a Hilbert curve -- consecutive particles
+    are close in space (every step of a Hilbert curve moves to a face-adjacent lattice cell)."""
+    import torch
+    n = 200000
+    pos = uniform_mt(n, seed=77)
+    posm = torch.from_numpy(np.concatenate([pos, np.ones((n, 1), np.float32)], 1)).cuda()
+    perm = torch.empty(n, dtype=torch.int32, device="cuda")
+    engine.spatial_order_dev(posm, n, 100.0, perm)
+    torch.cuda.synchronize()
+    p = perm.cpu().numpy()
+    assert np.array_equal(np.sort(p), np.arange(n))
+    step = np.abs(np.diff(pos[p], axis=0)).sum(1)
+    rand = np.abs(np.diff(pos, axis=0)).sum(1)
+    assert step.mean() < 0.04 * rand.mean()                  # ~2 vs ~100 (L1 distance between neighbours)
+    assert np.percentile(step, 99.9) < 15.0                  # no long jumps: a Morton curve would have 50-unit ones
