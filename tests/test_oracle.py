@@ -152,3 +152,42 @@ def test_energy_known_answer(oracle):
     pos2 = np.array([[0.1, 5, 5], [99.9, 5, 5]], np.float32)
     _, pe2 = oracle.energy(pos2, vel, m, 0.01, box=100.0)
     assert abs(pe2 + 3.0 / np.sqrt(0.04 + 1e-4)) < 1e-3      # 99.9f - 0.1f carries FP32 rounding
+
+
+def test_fixed_tree_oracle_properties(oracle):
+    """The fixed-physics restatement (not the reference's tree): no orphans, leaves within capacity above the
+    depth limit, data-fitted root, and a walk that converges to the FP64 direct sum as theta shrinks."""
+    from inputs import clustered_np, masses_np, rel_l2
+    n = 6000
+    pos, mass = clustered_np(n, seed=3), masses_np(n, seed=4)
+    t = oracle.tree_build_fixed(pos, mass, 8, 20)
+    counts = np.diff(t.part_off)
+    leaf = t.first_child < 0
+    assert counts[~leaf].sum() == 0 and counts[leaf].sum() == n           # internal nodes store nothing
+    assert np.array_equal(np.sort(t.part_idx), np.arange(n))              # every particle exactly once
+    assert np.all(counts[leaf & (t.level < 20)] <= 8)
+    lo, hi = pos.min(0), pos.max(0)
+    assert np.allclose(t.center[0], (lo + hi) * 0.5) and abs(t.size[0] / (hi - lo).max() - 1.00001) < 1e-6
+    assert abs(t.mass[0] - mass.sum()) < 1e-3 * mass.sum()
+    ref = oracle.direct_f64(pos, mass, eps=0.01)
+    errs = [rel_l2(oracle.tree_forces_fixed(t, pos, mass, th, 0.01), ref) for th in (0.6, 0.4, 0.2)]
+    assert errs[0] > errs[1] > errs[2] and errs[2] < 2e-4, errs
+    # the reference's tree semantics on the same particles are far from the direct sum (SURVEY 0.4)
+    assert rel_l2(oracle.tree_forces(oracle.tree_build(pos, mass), pos, 0.5), ref) > 0.1
+
+
+def test_fixed_tree_periodic_oracle_converges(oracle):
+    from inputs import masses_np, rel_l2, uniform_np
+    n, box = 3000, 100.0
+    pos, mass = uniform_np(n, seed=5, lo=0.0, hi=box), masses_np(n, seed=6)
+    t = oracle.tree_build_fixed(pos, mass, 8, 20)
+    ref = oracle.direct_periodic_f32(pos, mass, 0.05, box)
+    e5 = rel_l2(oracle.tree_forces_fixed(t, pos, mass, 0.5, 0.05, box=box), ref)
+    e2 = rel_l2(oracle.tree_forces_fixed(t, pos, mass, 0.2, 0.05, box=box), ref)
+    assert e5 < 2e-2 and e2 < 0.3 * e5, (e5, e2)
+    phi = oracle.tree_potential_fixed(t, pos, mass, 0.3, 0.05, box)
+    d = pos[None, :50].astype(np.float64) - pos[:, None].astype(np.float64)
+    d -= box * np.round(d / box)
+    r = np.sqrt((d ** 2).sum(-1) + 0.05 ** 2)
+    want = (mass[:, None] / r).sum(0) - mass[:50] / 0.05
+    assert np.max(np.abs(phi[:50] - want) / want) < 2e-3
