@@ -269,6 +269,11 @@ typedef struct b200_ic_params {
     float particle_mass;      /* written to posm4.w (<= 0 means 1) */
     float origin_shift;       /* subtracted from every coordinate after the wrap: box/2 gives the
                                  origin-centred convention of the CPU tree's root cube */
+    int use_2lpt;             /* InitialConditionsParams::use_2lpt (initial_conditions.hpp:38): add the second-order
+                                 displacement, x = q + D1 psi1 + D2 psi2 with lap phi2 = sum_{a<b}(phi1,aa phi1,bb -
+                                 phi1,ab^2), psi2 = grad phi2, D2 = -3/7 D1^2 Omega_m^-1/143, v = a H (f1 D1 psi1 +
+                                 f2 D2 psi2), f2 = 2 Omega_m^6/11 -- computed in real space with 10 more FFTs, not by
+                                 the reference's 26-neighbour mode sum (initial_conditions.cpp:639-722) */
 } b200_ic_params;
 void b200_ic_params_default(b200_ic_params* p);   /* the reference's defaults: 256, 100, z 49, seed 12345, ... */
 /* n_particles <= G^3: particle p is grid point p * max(1, G^3 / n_particles).

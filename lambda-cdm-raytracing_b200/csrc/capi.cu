@@ -497,6 +497,7 @@ void b200_ic_params_default(b200_ic_params* p) {
     p->n_s = 0.965;
     p->particle_mass = 1.0f;
     p->origin_shift = 0.0f;
+    p->use_2lpt = 0;             // InitialConditionsParams::use_2lpt default (initial_conditions.hpp:38)
 }
 
 int b200_zeldovich_ics_dev(b200_ctx* ctx, const b200_ic_params* params, size_t n_particles, void* posm4,

@@ -144,8 +144,73 @@ __global__ void ic_psi_kernel(const float2* __restrict__ wk, float2* __restrict_
     }
 }
 
+// ---- second order (2LPT) ---------------------------------------------------------
+// phi1,ab(k) = k_a k_b delta_k / k^2  (phi1 = inverse Laplacian of delta, psi1 = -grad phi1).  For a != b the
+// Nyquist planes of a and b are dropped (k_a k_b is not odd there), as for psi.
+__global__ void ic_d2_kernel(const float2* __restrict__ wk, float2* __restrict__ out, int G, int a, int b,
+                             double dk, double gamma, double n_s, double norm) {
+    const int H = G / 2 + 1;
+    const long long total = (long long)G * G * H;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int kz = (int)(t % H);
+        const int jy = (int)((t / H) % G);
+        const int ix = (int)(t / ((long long)H * G));
+        const int n3[3] = {ix <= G / 2 ? ix : ix - G, jy <= G / 2 ? jy : jy - G, kz};
+        const long long n2 = (long long)n3[0] * n3[0] + (long long)n3[1] * n3[1] + (long long)n3[2] * n3[2];
+        const bool nyq = a != b && (2 * (n3[a] < 0 ? -n3[a] : n3[a]) == G || 2 * (n3[b] < 0 ? -n3[b] : n3[b]) == G);
+        float2 o = make_float2(0.f, 0.f);
+        if (n2 > 0 && !nyq) {
+            const double k = dk * sqrt((double)n2);
+            const double q = k / gamma;
+            const double tr = log(1.0 + 2.34 * q) / (2.34 * q) *
+                              pow(1.0 + 3.89 * q + (16.1 * q) * (16.1 * q) + (5.46 * q) * (5.46 * q) * (5.46 * q) +
+                                      (6.71 * q) * (6.71 * q) * (6.71 * q) * (6.71 * q), -0.25);
+            const double amp = sqrt(pow(k, n_s) * tr * tr * norm) * (double)n3[a] * (double)n3[b] / (double)n2;
+            const float2 v = wk[t];
+            o.x = (float)(amp * (double)v.x);
+            o.y = (float)(amp * (double)v.y);
+        }
+        out[t] = o;
+    }
+}
+// S = sum_{a<b} (phi,aa phi,bb - phi,ab^2): the diagonal part, then one off-diagonal term at a time
+__global__ void ic_s_diag_kernel(const float* __restrict__ xx, const float* __restrict__ yy,
+                                 const float* __restrict__ zz, float* __restrict__ S, long long cells) {
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (long long)gridDim.x * blockDim.x)
+        S[c] = xx[c] * yy[c] + xx[c] * zz[c] + yy[c] * zz[c];
+}
+__global__ void ic_s_offdiag_kernel(const float* __restrict__ ab, float* __restrict__ S, long long cells) {
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (long long)gridDim.x * blockDim.x)
+        S[c] -= ab[c] * ab[c];
+}
+// psi2_k = grad of phi2, phi2 = inverse Laplacian of S: -i k_a S_k / k^2, with the 1/G^3 of the forward transform
+__global__ void ic_psi2_kernel(const float2* __restrict__ sk, float2* __restrict__ out, int G, int axis, double dk) {
+    const int H = G / 2 + 1;
+    const long long total = (long long)G * G * H;
+    const double inv_cells = 1.0 / ((double)G * G * G);
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int kz = (int)(t % H);
+        const int jy = (int)((t / H) % G);
+        const int ix = (int)(t / ((long long)H * G));
+        const int n3[3] = {ix <= G / 2 ? ix : ix - G, jy <= G / 2 ? jy : jy - G, kz};
+        const long long n2 = (long long)n3[0] * n3[0] + (long long)n3[1] * n3[1] + (long long)n3[2] * n3[2];
+        const int na = n3[axis];
+        float2 o = make_float2(0.f, 0.f);
+        if (n2 > 0 && 2 * (na < 0 ? -na : na) != G) {
+            const double c = inv_cells * (double)na / (dk * (double)n2);      // k_a / k^2 / G^3
+            const float2 v = sk[t];
+            o.x = (float)(c * (double)v.y);                                   // -i (x + iy) = y - ix
+            o.y = (float)(-c * (double)v.x);
+        }
+        out[t] = o;
+    }
+}
+
 __global__ void ic_particles_kernel(const float* __restrict__ px, const float* __restrict__ py,
-                                    const float* __restrict__ pz, int G, long long n_particles,
+                                    const float* __restrict__ pz, const float* __restrict__ p2 /* 3 planes or null */,
+                                    float growth2, float vfac2, int G, long long n_particles,
                                     long long skip, float dx, float box, float growth, float vfac,
                                     float shift, float mass, float4* __restrict__ posm,
                                     float* __restrict__ vel3, double* __restrict__ stats /* sum psi^2, max |psi| bits */) {
@@ -155,7 +220,14 @@ __global__ void ic_particles_kernel(const float* __restrict__ px, const float* _
          p += (long long)gridDim.x * blockDim.x) {
         const long long c = p * skip;                      // grid_to_particles :371-380
         const int k = (int)(c % G), j = (int)((c / G) % G), i = (int)(c / ((long long)G * G));
-        const float dxs = growth * px[c], dys = growth * py[c], dzs = growth * pz[c];
+        float dxs = growth * px[c], dys = growth * py[c], dzs = growth * pz[c];
+        float vx = vfac * dxs, vy = vfac * dys, vz = vfac * dzs;                  // :350-354
+        if (p2) {                                  // x = q + D1 psi1 + D2 psi2, v = a H (f1 D1 psi1 + f2 D2 psi2)
+            const long long cells = (long long)G * G * G;
+            const float ex = growth2 * p2[c], ey = growth2 * p2[cells + c], ez = growth2 * p2[2 * cells + c];
+            dxs += ex; dys += ey; dzs += ez;
+            vx += vfac2 * ex; vy += vfac2 * ey; vz += vfac2 * ez;
+        }
         float x = (i + 0.5f) * dx + dxs, y = (j + 0.5f) * dx + dys, z = (k + 0.5f) * dx + dzs;
         while (x < 0.0f) x += box;                         // :287-292
         while (x >= box) x -= box;
@@ -164,9 +236,9 @@ __global__ void ic_particles_kernel(const float* __restrict__ px, const float* _
         while (z < 0.0f) z += box;
         while (z >= box) z -= box;
         posm[p] = make_float4(x - shift, y - shift, z - shift, mass);
-        vel3[3 * p + 0] = vfac * dxs;                      // :350-354
-        vel3[3 * p + 1] = vfac * dys;
-        vel3[3 * p + 2] = vfac * dzs;
+        vel3[3 * p + 0] = vx;
+        vel3[3 * p + 1] = vy;
+        vel3[3 * p + 2] = vz;
         const float d2 = dxs * dxs + dys * dys + dzs * dzs;
         s2 += (double)d2;
         mx = fmaxf(mx, d2);
@@ -214,7 +286,9 @@ int zeldovich_ics(b200_ctx* ctx, const b200_ic_params* p, size_t n_particles, vo
     const size_t cplx_bytes = (size_t)G * G * (G / 2 + 1) * sizeof(float2);
     B200_TRY(ctx->ic_wk.reserve(cplx_bytes));
     B200_TRY(ctx->ic_tmp.reserve(cplx_bytes));          // psi_k, transformed in place to psi(x)
-    B200_TRY(ctx->ic_psi.reserve(3 * real_bytes));
+    const bool lpt2 = p->use_2lpt != 0;
+    // planes: psi1 x,y,z [0..2]; 2LPT: psi2 x,y,z [3..5], phi,xx phi,yy phi,zz [6..8], one off-diagonal [9], S [10]
+    B200_TRY(ctx->ic_psi.reserve((lpt2 ? 11 : 3) * real_bytes));
     B200_TRY(ctx->ic_stats.reserve(2 * sizeof(double)));
     B200_CUDA(cudaMemsetAsync(ctx->ic_stats.p, 0, 2 * sizeof(double), st));
 
@@ -241,11 +315,48 @@ int zeldovich_ics(b200_ctx* ctx, const b200_ic_params* p, size_t n_particles, vo
             e = fft->ExecC2R(c2r, (cufftComplex*)ctx->ic_tmp.p, ctx->ic_psi.as<float>() + (size_t)axis * cells);
             if (e != CUFFT_SUCCESS) status = 3000 + (int)e;
         }
+        if (status == B200_OK && lpt2) {
+            // second order: phi1,ab to real space, S = sum_{a<b} (phi,aa phi,bb - phi,ab^2), psi2 = grad lap^-1 S
+            float* planes = ctx->ic_psi.as<float>();
+            float2* wk = ctx->ic_wk.as<float2>();
+            float2* tmp = ctx->ic_tmp.as<float2>();
+            const double nrm = pnorm / (V * (double)cells);
+            for (int a = 0; a < 3 && status == B200_OK; ++a) {
+                ic_d2_kernel<<<grid, 256, 0, st>>>(wk, tmp, G, a, a, dk, gamma, p->n_s, nrm);
+                e = fft->ExecC2R(c2r, (cufftComplex*)tmp, planes + (size_t)(6 + a) * cells);
+                if (e != CUFFT_SUCCESS) status = 3000 + (int)e;
+            }
+            float* S = planes + (size_t)10 * cells;
+            if (status == B200_OK)
+                ic_s_diag_kernel<<<grid, 256, 0, st>>>(planes + 6 * cells, planes + 7 * cells, planes + 8 * cells, S, cells);
+            const int pairs[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+            for (int q = 0; q < 3 && status == B200_OK; ++q) {
+                ic_d2_kernel<<<grid, 256, 0, st>>>(wk, tmp, G, pairs[q][0], pairs[q][1], dk, gamma, p->n_s, nrm);
+                e = fft->ExecC2R(c2r, (cufftComplex*)tmp, planes + (size_t)9 * cells);
+                if (e != CUFFT_SUCCESS) { status = 3000 + (int)e; break; }
+                ic_s_offdiag_kernel<<<grid, 256, 0, st>>>(planes + (size_t)9 * cells, S, cells);
+            }
+            if (status == B200_OK) {            // W_k is no longer needed: its buffer takes S_k
+                e = fft->ExecR2C(r2c, S, (cufftComplex*)wk);
+                if (e != CUFFT_SUCCESS) status = 3000 + (int)e;
+            }
+            for (int axis = 0; axis < 3 && status == B200_OK; ++axis) {
+                ic_psi2_kernel<<<grid, 256, 0, st>>>(wk, tmp, G, axis, dk);
+                e = fft->ExecC2R(c2r, (cufftComplex*)tmp, planes + (size_t)(3 + axis) * cells);
+                if (e != CUFFT_SUCCESS) status = 3000 + (int)e;
+            }
+            ctx->launches += 13;
+        }
     } while (0);
     if (status == B200_OK) {
         const long long skip = cells / (long long)n_particles > 1 ? cells / (long long)n_particles : 1;
         const float* psi = ctx->ic_psi.as<float>();
-        ic_particles_kernel<<<grid, 256, 0, st>>>(psi, psi + cells, psi + 2 * cells, G, (long long)n_particles, skip,
+        // second-order growth: D2 = -3/7 D1^2 Omega_m(a)^(-1/143), f2 = 2 Omega_m(a)^(6/11) (Bouchet et al. 1995)
+        const double om_a = omega_m_a(*p, a);
+        const double D2 = -3.0 / 7.0 * D * D * pow(om_a, -1.0 / 143.0);
+        const double vfac2 = a * hubble_a(*p, a) * 2.0 * pow(om_a, 6.0 / 11.0);
+        ic_particles_kernel<<<grid, 256, 0, st>>>(psi, psi + cells, psi + 2 * cells, lpt2 ? psi + 3 * cells : nullptr,
+                                                  (float)D2, (float)vfac2, G, (long long)n_particles, skip,
                                                   p->box / (float)G, p->box, (float)D, (float)vfac, p->origin_shift,
                                                   p->particle_mass > 0.f ? p->particle_mass : 1.0f, (float4*)posm4,
                                                   (float*)vel3, ctx->ic_stats.as<double>());

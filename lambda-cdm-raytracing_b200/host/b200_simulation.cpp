@@ -103,7 +103,8 @@ void B200LambdaCDMSimulation::initialize_particles(uint32_t seed) {
     set_particles(pos.data(), vel.data(), nullptr);
 }
 
-void B200LambdaCDMSimulation::set_initial_conditions_from_power_spectrum(uint32_t seed, double z_initial) {
+void B200LambdaCDMSimulation::set_initial_conditions_from_power_spectrum(uint32_t seed, double z_initial,
+                                                                         bool use_2lpt) {
     const size_t n = num_particles_;
     if (n == 0) return;
     b200_ic_params p;
@@ -114,6 +115,7 @@ void B200LambdaCDMSimulation::set_initial_conditions_from_power_spectrum(uint32_
     p.box = box_size_;
     p.z_initial = z_initial;
     p.seed = seed;
+    p.use_2lpt = use_2lpt ? 1 : 0;
     p.omega_m = params_.omega_m; p.omega_lambda = params_.omega_lambda; p.omega_k = params_.omega_k;
     p.h = params_.h; p.sigma_8 = params_.sigma_8; p.n_s = params_.n_s;
     const bool centred = method_ == B200ForceMethod::Tree || method_ == B200ForceMethod::TreeFixed;

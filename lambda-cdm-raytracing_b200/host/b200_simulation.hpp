@@ -89,7 +89,8 @@ public:
     // velocity conventions, with the inverse FFT its displacement step lacks), grid = the smallest power
     // of two with grid^3 >= N, positions in [0, box) -- or origin-centred for the tree methods, whose root
     // cube is centred on the origin.  Every rank of a sharded run generates the same particles.
-    void set_initial_conditions_from_power_spectrum(uint32_t seed = 12345, double z_initial = 49.0);
+    void set_initial_conditions_from_power_spectrum(uint32_t seed = 12345, double z_initial = 49.0,
+                                                    bool use_2lpt = false);   // InitialConditionsParams::use_2lpt
     void set_softening(float softening) { softening_ = softening; have_forces_ = false; }
     void set_force_method(B200ForceMethod m, float theta = 0.5f, int leaf_capacity = 8, int max_depth = 20);
 

@@ -36,7 +36,7 @@ class ICParams(C.Structure):
     _fields_ = [("grid", C.c_int), ("box", C.c_float), ("z_initial", C.c_double), ("seed", C.c_uint32),
                 ("omega_m", C.c_double), ("omega_lambda", C.c_double), ("omega_k", C.c_double), ("h", C.c_double),
                 ("sigma_8", C.c_double), ("n_s", C.c_double), ("particle_mass", C.c_float),
-                ("origin_shift", C.c_float)]
+                ("origin_shift", C.c_float), ("use_2lpt", C.c_int)]
 
 
 class B200Error(RuntimeError):

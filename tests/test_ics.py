@@ -90,3 +90,70 @@ def test_zeldovich_particles_layout():
     assert np.allclose(vel, (pos - (np.stack(np.unravel_index(np.arange(512) * 8, (16, 16, 16)), 1) + 0.5)
                              .astype(np.float32) * np.float32(6.25) + 50.0) * np.float32(vfac), atol=2e-2)
     assert 0.05 < rms < 0.5
+
+
+def _delta_k_of(field, box):
+    """delta_k in the generator's convention, delta(x) = (1/V) sum_k delta_k e^{ikx}."""
+    G = field.shape[0]
+    return np.fft.rfftn(field) * box ** 3 / G ** 3
+
+
+def test_second_order_source_analytic():
+    """lap phi = delta.  One plane wave has no second-order term; two crossed waves
+    delta = A cos(k1 x) + B cos(k2 y) give phi,xx = A cos, phi,yy = B cos, S = A B cos(k1 x) cos(k2 y)."""
+    G, box = 32, 100.0
+    x = (np.arange(G) * box / G)
+    k1, k2 = 2 * np.pi / box * 2, 2 * np.pi / box * 3
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    one = 0.3 * np.cos(k1 * X + 0.4)
+    assert np.abs(ics_np.second_order_source(_delta_k_of(one, box), G, box)).max() < 1e-14
+    two = 0.3 * np.cos(k1 * X) + 0.2 * np.cos(k2 * Y)
+    S = ics_np.second_order_source(_delta_k_of(two, box), G, box)
+    assert np.abs(S - 0.06 * np.cos(k1 * X) * np.cos(k2 * Y)).max() < 1e-14
+    # oblique waves exercise the off-diagonal terms: delta = A cos(k.x) + B cos(q.x),
+    # S = A B cos cos (1 - (k.q)^2 / (k^2 q^2))
+    kv = 2 * np.pi / box * np.array([1, 2, 0]); qv = 2 * np.pi / box * np.array([2, -1, 3])
+    pk, pq = kv[0] * X + kv[1] * Y + kv[2] * Z, qv[0] * X + qv[1] * Y + qv[2] * Z
+    obl = 0.3 * np.cos(pk) + 0.2 * np.cos(pq)
+    mu2 = (kv @ qv) ** 2 / ((kv @ kv) * (qv @ qv))
+    kq = 2 * np.pi / box * np.array([3, 1, 0])
+    obl2 = 0.3 * np.cos(pk) + 0.2 * np.cos(kq[0] * X + kq[1] * Y)
+    for f, q in ((obl, qv), (obl2, kq)):
+        mu2 = (kv @ q) ** 2 / ((kv @ kv) * (q @ q))
+        S = ics_np.second_order_source(_delta_k_of(f, box), G, box)
+        expect = 0.06 * np.cos(pk) * np.cos(q[0] * X + q[1] * Y + q[2] * Z) * (1.0 - mu2)
+        assert np.abs(S - expect).max() < 1e-13, mu2
+
+
+def test_second_order_displacement_is_gradient_of_inverse_laplacian():
+    G, box = 32, 100.0
+    x = (np.arange(G) * box / G)
+    k1, k2 = 2 * np.pi / box * 2, 2 * np.pi / box * 3
+    X, Y, _ = np.meshgrid(x, x, x, indexing="ij")
+    S = np.cos(k1 * X) * np.cos(k2 * Y)                       # phi2 = -S / (k1^2 + k2^2)
+    psi2 = ics_np.second_order_displacement(S, box)
+    kk = k1 * k1 + k2 * k2
+    assert np.abs(psi2[0] - k1 * np.sin(k1 * X) * np.cos(k2 * Y) / kk).max() < 1e-12
+    assert np.abs(psi2[1] - k2 * np.cos(k1 * X) * np.sin(k2 * Y) / kk).max() < 1e-12
+    assert np.abs(psi2[2]).max() < 1e-12
+
+
+def test_2lpt_correction_is_second_order():
+    """D2 psi2 scales as D1^2: small against the first order at z = 49, four times larger (relative) at twice the
+    growth; the velocity factor uses f2 = 2 Omega_m^(6/11)."""
+    z1 = ics_np.zeldovich(16, z_init=49.0, seed=3)
+    l1 = ics_np.zeldovich(16, z_init=49.0, seed=3, use_2lpt=True)
+    z2 = ics_np.zeldovich(16, z_init=24.0, seed=3)
+    l2 = ics_np.zeldovich(16, z_init=24.0, seed=3, use_2lpt=True)
+
+    def wrapped(a, b):
+        d = np.abs(a.astype(np.float64) - b)
+        return np.minimum(d, 100.0 - d)
+    c1 = np.sqrt((wrapped(l1[0], z1[0]) ** 2).sum(1).mean())
+    c2 = np.sqrt((wrapped(l2[0], z2[0]) ** 2).sum(1).mean())
+    assert 0 < c1 < 0.05 * z1[2][0]
+    ratio = (c2 / c1) / (ics_np.growth(1 / 25.0) / ics_np.growth(1 / 50.0)) ** 2
+    assert abs(ratio - 1.0) < 0.02, ratio
+    D2, vf2 = ics_np.growth2(1 / 50.0)
+    assert abs(D2 / (-3.0 / 7.0 * ics_np.growth(1 / 50.0) ** 2) - 1.0) < 1e-3
+    assert abs(vf2 / (2.0 * z1[2][2]) - 1.0) < 0.01           # f2 ~ 2 f1 in the matter era
