@@ -149,11 +149,45 @@ __device__ __forceinline__ const float* tile_ptr(const DirectSources& src, int t
 // compute_energy at src/physics/lambda_cdm_kernels.cu:338-408) instead of the
 // acceleration: 7 (equal masses) / 8 lane-ops + 1 MUFU per pair, component 0 of the
 // partial records only.
-template <int R, int THREADS, int MINB, bool PERIODIC, bool UNIT, bool POT = false>
+//
+// PMODE_OPEN: open boundaries.
+// PMODE_FLOAT: periodic, minimum image in FP32 (d - box * rint(d / box) with the 1.5 * 2^23 trick): 9 more
+//   FP32-pipe lane-ops per pair, exact with respect to the input floats.
+// PMODE_FIXED_XY: periodic, x and y in FIXED POINT.  The CTA rewrites the x and y planes of each landed tile in
+//   shared memory as 32-bit integers in units of box / 2^32, so x_j - x_i wraps to the minimum image by itself
+//   (IADD3) and I2FP brings it back to FP32 -- both on the ALU pipe, which the FP32-pipe-bound loop leaves idle;
+//   z keeps the FP32 minimum image.  Per pair 4 ALU + 13 FP32-pipe lane-ops instead of 20 (+15 % measured; all
+//   three components in fixed point is slower again, the two pipes overlap only partly).  a_x, a_y come out in
+//   fixed-point units and are rescaled in FP64 by the finalize pass.  Positions are quantised to box * 2^-33
+//   (1.2e-8 of a 100 box, 1/300 of a float ulp there), which perturbs the force of a pair closer than eps by
+//   up to that over eps, relatively: the dispatcher uses this mode only while eps >= 1e-4 box.  In the
+//   equal-mass instance the mass plane of the tile is reused for a per-source eps^2 (+inf in the padding slots,
+//   whose rsqrt is then exactly 0).
+constexpr int PMODE_OPEN = 0, PMODE_FLOAT = 1, PMODE_FIXED_XY = 2;
+
+// x -> units of box / 2^32, modulo 2^32.  The upper half is shifted down by one unit so that a pair exactly
+// half a box apart keeps the sign of its raw separation, as minimum_image (lambda_cdm_kernels.cu:122-141) and
+// the FP32 path do; plain modular arithmetic would send both to -box/2.
+__device__ __forceinline__ uint32_t fixed_point(float x, double units_per_length) {
+    uint32_t e = (uint32_t)(unsigned long long)__double2ll_rn((double)x * units_per_length);
+    return e - (e >> 31);
+}
+
+// (a - b) + c as ONE opaque instruction.
+__device__ __forceinline__ int sub3(uint32_t a, uint32_t b, uint32_t c) {
+    int d;
+    asm("vsub.s32.s32.s32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+template <int R, int THREADS, int MINB, int PMODE, bool UNIT, bool POT = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 direct_kernel(const DirectSources src, const float4* __restrict__ targets, long long n_targets,
               float eps2, float box, double* __restrict__ partials, long long n_units, int n_tiles,
               const int* __restrict__ mass_diff) {
+    constexpr bool PERIODIC = (PMODE == PMODE_FLOAT);
+    constexpr bool FIXED = (PMODE == PMODE_FIXED_XY);
+    static_assert(!(FIXED && POT), "the potential keeps the FP32 minimum image");
     if (mass_diff != nullptr) {
         const bool uniform = (*mass_diff == 0);
         if (uniform != UNIT) return;
@@ -194,16 +228,26 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
     }
     int t_issue = (int)((u0 + (STAGES - 1)) % n_tiles);   // tile of unit k + STAGES-1
 
+    [[maybe_unused]] const double units = FIXED ? 4294967296.0 / (double)box : 1.0;
+    [[maybe_unused]] const uint32_t zero = (uint32_t)(n_tiles >> 31);      // 0 (n_tiles > 0), opaque to the compiler
     const u64 eps2_2 = pk(eps2, eps2);
-    u64 nxi[R], nyi[R], nzi[R];          // packed (-x_i, -x_i) per register-blocked target
+    constexpr int RF = FIXED ? 1 : R, RI = FIXED ? R : 1;
+    [[maybe_unused]] u64 nxi[RF], nyi[RF];                 // packed (-x_i, -x_i) per register-blocked target
+    u64 nzi[R];
+    [[maybe_unused]] uint32_t ixi[RI], iyi[RI];            // fixed point: x_i in units of box / 2^32
     auto load_targets = [&](long long blk) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             long long i = blk * BLOCK_I + r * THREADS + tid;
             float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
             if (i < n_targets) p = targets[i];
-            nxi[r] = pk(-p.x, -p.x);
-            nyi[r] = pk(-p.y, -p.y);
+            if constexpr (FIXED) {
+                ixi[r] = fixed_point(p.x, units);
+                iyi[r] = fixed_point(p.y, units);
+            } else {
+                nxi[r] = pk(-p.x, -p.x);
+                nyi[r] = pk(-p.y, -p.y);
+            }
             nzi[r] = pk(-p.z, -p.z);
             dsum[(0 * R + r) * THREADS + tid] = 0.0;
             dsum[(1 * R + r) * THREADS + tid] = 0.0;
@@ -212,8 +256,12 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
     };
     load_targets(b);
 
-    [[maybe_unused]] u64 inv_box2, magic2, nmagic2, nbox2;
-    if constexpr (PERIODIC) {
+    [[maybe_unused]] u64 inv_box2, magic2, nmagic2, nbox2, len2_2;
+    if constexpr (FIXED) {
+        const float l = (float)(1.0 / units);
+        len2_2 = pk(l * l, l * l);      // (box / 2^32)^2: fixed-point units^2 -> length^2
+    }
+    if constexpr (PERIODIC || FIXED) {
         float ib = 1.0f / box;
         inv_box2 = pk(ib, ib);
         magic2 = pk(12582912.0f, 12582912.0f);      // 1.5 * 2^23: round-to-nearest-integer trick
@@ -231,6 +279,19 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
         if (++t_issue == n_tiles) t_issue = 0;
         mbar_wait(&full[s], (uint32_t)((k / STAGES) & 1));
 
+        if constexpr (FIXED) {
+            // rewrite the landed tile in place: x, y -> fixed point; equal-mass instance: mass plane -> eps^2
+            // per source, +inf in the padding slots (parked at 1e18 by the packer)
+            float* tile = stage_buf + s * TILE_FLOATS;
+            for (int j = tid; j < TILE_J; j += THREADS) {
+                const float x = tile[j], y = tile[TILE_J + j];
+                tile[j] = __uint_as_float(fixed_point(x, units));
+                tile[TILE_J + j] = __uint_as_float(fixed_point(y, units));
+                if constexpr (UNIT) tile[3 * TILE_J + j] = (x >= 0.5f * FAR_AWAY) ? __int_as_float(0x7f800000) : eps2;
+            }
+            __syncthreads();
+        }
+
         const ulonglong2* sx = reinterpret_cast<const ulonglong2*>(stage_buf + s * TILE_FLOATS);
         const ulonglong2* sy = sx + TILE_J / 4;
         const ulonglong2* sz = sy + TILE_J / 4;
@@ -243,9 +304,20 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
         auto interact = [&](u64 X, u64 Y, u64 Z, u64 M) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                u64 dx = add2(X, nxi[r]);
-                u64 dy = add2(Y, nyi[r]);
-                u64 dz = add2(Z, nzi[r]);
+                u64 dx, dy, dz;
+                if constexpr (FIXED) {
+                    // the 32-bit difference IS the minimum image; IADD3 + I2FP run on the ALU pipe
+                    // (the third addend is a run-time zero: a three-input add can only be IADD3, whereas ptxas turns
+                    // plain subtractions into IMAD.IADD -- on the FP32 pipe this mode is meant to unload)
+                    dx = pk(__int2float_rn(sub3((uint32_t)X, ixi[r], zero)), __int2float_rn(sub3((uint32_t)(X >> 32), ixi[r], zero)));
+                    dy = pk(__int2float_rn(sub3((uint32_t)Y, iyi[r], zero)), __int2float_rn(sub3((uint32_t)(Y >> 32), iyi[r], zero)));
+                    dz = add2(Z, nzi[r]);
+                    dz = fma2(add2(fma2(dz, inv_box2, magic2), nmagic2), nbox2, dz);
+                } else {
+                    dx = add2(X, nxi[r]);
+                    dy = add2(Y, nyi[r]);
+                    dz = add2(Z, nzi[r]);
+                }
                 if constexpr (PERIODIC) {
                     u64 qx = add2(fma2(dx, inv_box2, magic2), nmagic2);      // rint(d / box): 3 lane-ops per component
                     u64 qy = add2(fma2(dy, inv_box2, magic2), nmagic2);
@@ -254,9 +326,14 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
                     dy = fma2(qy, nbox2, dy);
                     dz = fma2(qz, nbox2, dz);
                 }
-                u64 r2 = fma2(dx, dx, eps2_2);
-                r2 = fma2(dy, dy, r2);
-                r2 = fma2(dz, dz, r2);
+                u64 r2;
+                if constexpr (FIXED) {      // x, y in fixed-point units, z in length units
+                    r2 = fma2(fma2(dy, dy, mul2(dx, dx)), len2_2, fma2(dz, dz, UNIT ? M : eps2_2));
+                } else {
+                    r2 = fma2(dx, dx, eps2_2);
+                    r2 = fma2(dy, dy, r2);
+                    r2 = fma2(dz, dz, r2);
+                }
                 float r2a, r2b;
                 unpk(r2, r2a, r2b);
                 u64 rinv = pk(rsqrt_approx(r2a), rsqrt_approx(r2b));
@@ -278,7 +355,7 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
         for (int j4 = 0; j4 < TILE_J / 4; ++j4) {
             const ulonglong2 X = sx[j4], Y = sy[j4], Z = sz[j4];
             ulonglong2 M = make_ulonglong2(0ull, 0ull);
-            if constexpr (!UNIT) M = sm[j4];
+            if constexpr (!UNIT || FIXED) M = sm[j4];
             interact(X.x, Y.x, Z.x, M.x);
             interact(X.y, Y.y, Z.y, M.y);
         }
@@ -292,6 +369,7 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
                 unpk(az[r], lo, hi); dsum[(2 * R + r) * THREADS + tid] += (double)(lo + hi);
             }
         }
+        if constexpr (FIXED) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this CTA wrote the stage
         __syncthreads();      // every warp is done with stage s -> it may be refilled
 
         ++t;
@@ -321,7 +399,7 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
 __global__ void direct_finalize_kernel(const double* __restrict__ partials, float* __restrict__ acc3,
                                        long long n_targets, int block_i, long long n_units,
                                        int n_tiles, int G, const int* __restrict__ mass_diff,
-                                       const float* __restrict__ first_tile) {
+                                       const float* __restrict__ first_tile, double scale_xy) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_targets) return;
     long long b = i / block_i;
@@ -340,8 +418,8 @@ __global__ void direct_finalize_kernel(const double* __restrict__ partials, floa
         const double m0 = (double)first_tile[3 * DIRECT_TILE_J];     // mass of source 0
         sx *= m0; sy *= m0; sz *= m0;
     }
-    acc3[3 * i + 0] = (float)sx;
-    acc3[3 * i + 1] = (float)sy;
+    acc3[3 * i + 0] = (float)(sx * scale_xy);        // fixed-point components come out in their own units
+    acc3[3 * i + 1] = (float)(sy * scale_xy);
     acc3[3 * i + 2] = (float)sz;
 }
 
@@ -396,12 +474,12 @@ __global__ void energy_final_kernel(const double* __restrict__ part, int nblocks
     }
 }
 
-template <int R, int THREADS, int MINB, bool PERIODIC, bool POT = false>
+template <int R, int THREADS, int MINB, int PMODE, bool POT = false>
 int launch_direct(b200_ctx* ctx, const DirectSources& src, const float4* targets, size_t n_targets,
                   float eps, float box, float* acc3, const int* mass_diff, cudaStream_t st) {
     constexpr int BLOCK_I = THREADS * R;
-    auto kern_g = direct_kernel<R, THREADS, MINB, PERIODIC, false, POT>;
-    auto kern_u = direct_kernel<R, THREADS, MINB, PERIODIC, true, POT>;
+    auto kern_g = direct_kernel<R, THREADS, MINB, PMODE, false, POT>;
+    auto kern_u = direct_kernel<R, THREADS, MINB, PMODE, true, POT>;
     const size_t smem = STAGES * TILE_BYTES + 64 + (size_t)3 * R * THREADS * sizeof(double);
     // shared-memory opt-in and occupancy are per (device, kernel instance): cached in the context,
     // which belongs to one device and is used by one host thread at a time
@@ -441,10 +519,13 @@ int launch_direct(b200_ctx* ctx, const DirectSources& src, const float4* targets
         potential_finalize_kernel<<<(unsigned)((n_targets + fb - 1) / fb), fb, 0, st>>>(
             ctx->partials.as<double>(), targets, acc3, (long long)n_targets, BLOCK_I, U, NT, (int)G, eps * eps,
             mass_diff, src.tiles[0]);
-    else
+    else {
+        // PMODE_FIXED_XY: r in length units, d_x and d_y in fixed-point units of box / 2^32
+        const double sxy = PMODE == PMODE_FIXED_XY ? (double)box / 4294967296.0 : 1.0;
         direct_finalize_kernel<<<(unsigned)((n_targets + fb - 1) / fb), fb, 0, st>>>(
             ctx->partials.as<double>(), acc3, (long long)n_targets, BLOCK_I, U, NT, (int)G, mass_diff,
-            src.tiles[0]);
+            src.tiles[0], sxy);
+    }
     B200_CUDA(cudaGetLastError());
     ctx->launches += mass_diff ? 3 : 2;
     return B200_OK;
@@ -490,17 +571,19 @@ int direct_forces(b200_ctx* ctx, const DirectSources& src, const void* targets4,
     if (const char* v = getenv("B200_DIRECT_VARIANT")) {      // tuning hook: "R,THREADS,MINB"
         int r = 0, th = 0, mb = 0;
         if (sscanf(v, "%d,%d,%d", &r, &th, &mb) == 3 && box > 0.f) {
+            const bool fp = getenv("B200_DIRECT_PERIODIC_FLOAT") != nullptr;
 #define B200_PVARIANT(RR, TH, MB) \
     if (r == RR && th == TH && mb == MB) \
-        return launch_direct<RR, TH, MB, true>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
-            B200_PVARIANT(4, 256, 1) B200_PVARIANT(5, 256, 1) B200_PVARIANT(6, 256, 1) B200_PVARIANT(8, 256, 1)
+        return fp ? launch_direct<RR, TH, MB, PMODE_FLOAT>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st) \
+                  : launch_direct<RR, TH, MB, PMODE_FIXED_XY>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
+            B200_PVARIANT(4, 256, 1) B200_PVARIANT(8, 256, 1) B200_PVARIANT(4, 512, 1)
 #undef B200_PVARIANT
             return B200_ERR_UNSUPPORTED;
         }
         if (sscanf(v, "%d,%d,%d", &r, &th, &mb) == 3 && box == 0.f) {
 #define B200_VARIANT(RR, TH, MB) \
     if (r == RR && th == TH && mb == MB) \
-        return launch_direct<RR, TH, MB, false>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
+        return launch_direct<RR, TH, MB, PMODE_OPEN>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
             B200_VARIANT(2, 256, 2) B200_VARIANT(4, 256, 1) B200_VARIANT(4, 256, 2) B200_VARIANT(5, 256, 1)
             B200_VARIANT(6, 256, 1) B200_VARIANT(8, 256, 1) B200_VARIANT(4, 384, 1) B200_VARIANT(4, 512, 1)
             B200_VARIANT(3, 512, 1) B200_VARIANT(6, 128, 2) B200_VARIANT(8, 128, 2) B200_VARIANT(7, 256, 1)
@@ -513,11 +596,18 @@ int direct_forces(b200_ctx* ctx, const DirectSources& src, const void* targets4,
         }
     }
     if (box > 0.f) {
-        return small ? launch_direct<2, 256, 2, true>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st)
-                     : launch_direct<4, 256, 1, true>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
+        // fixed-point x, y only while the position quantum (box * 2^-33) is below ~1e-6 eps, and never
+        // for small problems (launch-bound anyway); B200_DIRECT_PERIODIC_FLOAT forces the FP32 minimum image (A/B)
+        const long long units4 = (((long long)n_targets + 2047) / 2048) * (long long)src.total_tiles;
+        const bool fixed_ok = eps >= 1e-4f * box && n_targets >= 4 * 2048 && units4 >= 4ll * ctx->sm_count &&
+                              getenv("B200_DIRECT_PERIODIC_FLOAT") == nullptr;
+        if (fixed_ok)
+            return launch_direct<4, 512, 1, PMODE_FIXED_XY>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
+        return small ? launch_direct<2, 256, 2, PMODE_FLOAT>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st)
+                     : launch_direct<4, 256, 1, PMODE_FLOAT>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
     }
-    return small ? launch_direct<2, 256, 2, false>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st)
-                 : launch_direct<8, 256, 1, false>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
+    return small ? launch_direct<2, 256, 2, PMODE_OPEN>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st)
+                 : launch_direct<8, 256, 1, PMODE_OPEN>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
 }
 
 // Per-target potential phi_i = sum_{j != i} m_j / sqrt(|d|^2 + eps^2) (positive, G = 1).
@@ -533,11 +623,15 @@ int direct_potential(b200_ctx* ctx, const DirectSources& src, const void* target
     float* out = (float*)phi;
     const long long units6 = (((long long)n_targets + 1535) / 1536) * (long long)src.total_tiles;
     const bool small = n_targets < 4 * 1536 || units6 < 4ll * ctx->sm_count;
-    if (box > 0.f)
-        return small ? launch_direct<2, 256, 2, true, true>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st)
-                     : launch_direct<4, 256, 1, true, true>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
-    return small ? launch_direct<2, 256, 2, false, true>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st)
-                 : launch_direct<6, 256, 1, false, true>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
+    if (box > 0.f) {
+        // always the general-mass instance: a padding slot (parked at 1e18) can wrap to distance 0 -- exactly so
+        // when box is a power of two -- where only its zero mass silences it (harmless for forces, d = 0; not
+        // for a potential)
+        return small ? launch_direct<2, 256, 2, PMODE_FLOAT, true>(ctx, src, tg, n_targets, eps, box, out, nullptr, st)
+                     : launch_direct<4, 256, 1, PMODE_FLOAT, true>(ctx, src, tg, n_targets, eps, box, out, nullptr, st);
+    }
+    return small ? launch_direct<2, 256, 2, PMODE_OPEN, true>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st)
+                 : launch_direct<6, 256, 1, PMODE_OPEN, true>(ctx, src, tg, n_targets, eps, box, out, mass_diff, st);
 }
 
 // out2 (device): [0] = sum 1/2 m v^2, [1] = -1/2 sum m phi over the n targets.

@@ -117,6 +117,25 @@ def test_direct_periodic_vs_oracle(engine, oracle):
     assert rel_l2(a[ok], want[ok]) < TOL
 
 
+@pytest.mark.parametrize("n,unit,eps,box", [(20000, True, 0.05, 100.0), (20000, False, 0.05, 100.0),
+                                            (20000, True, 0.05, 64.0), (9000, True, 0.05, 100.0),
+                                            (20000, False, 1e-3, 100.0)])
+def test_direct_periodic_both_minimum_image_paths(engine, oracle, n, unit, eps, box):
+    """Above 8192 targets with eps >= 1e-4 box the x and y separations are taken in 32-bit fixed point (the wrap
+    is the integer overflow); below either bound the FP32 minimum image runs.  Same gate for both; n is never a
+    multiple of the 512-source tile, so the padding slots are exercised too (equal and general masses)."""
+    rng = np.random.default_rng(n + int(box))
+    p = rng.uniform(0.0, box, (n, 3)).astype(np.float32)
+    m = np.full(n, 1.5, np.float32) if unit else masses_np(n, seed=16)
+    a = engine.direct_forces_host(p, m, eps=eps, box=box)
+    sel = slice(1234, 1234 + 1024)
+    want = oracle.direct_periodic_f32(p, m, eps, box, i0=sel.start, n_targets=1024)
+    d = np.abs(p[sel, None, :].astype(np.float64) - p[None, :, :].astype(np.float64))
+    ok = ~(np.abs(d - 0.5 * box) < 2e-6 * box).any(axis=(1, 2))    # see test_direct_periodic_vs_oracle
+    assert ok.sum() > 0.7 * 1024
+    assert rel_l2(a[sel][ok], want[ok]) < TOL
+
+
 def test_direct_deterministic(engine):
     p = uniform_mt(20000, seed=3)
     a = engine.direct_forces_host(p, None)

@@ -40,6 +40,21 @@ def test_energy_vs_oracle(engine, oracle, n, unit, box):
     assert abs(pe - pe0) <= _tol(pe0, mass, 0.01)
 
 
+def test_periodic_energy_power_of_two_box_equal_masses(engine, oracle):
+    """box = 64 and n not a multiple of the 512-source tile: the padding slots (parked at 1e18) wrap to distance
+    exactly 0 under the FP32 minimum image, so only their zero mass may silence them."""
+    n, box = 3001, 64.0
+    rng = np.random.default_rng(21)
+    pos = rng.uniform(0.0, box, (n, 3)).astype(np.float32)
+    mass = np.full(n, 2.5, np.float32)
+    vel = rng.normal(0.0, 10.0, (n, 3)).astype(np.float32)
+    posm = torch.from_numpy(np.concatenate([pos, mass[:, None]], 1)).cuda()
+    ke, pe = engine.energy_dev(posm, torch.from_numpy(vel).cuda(), eps=0.01, box=box)
+    ke0, pe0 = oracle.energy(pos, vel, mass, 0.01, box)
+    assert abs(ke - ke0) <= REL * abs(ke0)
+    assert abs(pe - pe0) <= _tol(pe0, mass, 0.01)
+
+
 def test_potential_per_particle_and_shards(engine, oracle):
     n = 7001
     pos, mass, vel, posm = _setup(n, unit=False, seed=11)

@@ -32,6 +32,14 @@ def main():
     eng.set_timing(True)
     ref = None
     for v in args.variants.split(";"):
+        # periodic only: "float:" / "mixed:" prefix picks the minimum-image flavour (default: fixed point)
+        os.environ.pop("B200_DIRECT_PERIODIC_FLOAT", None)
+        os.environ.pop("B200_DIRECT_PERIODIC_MIXED", None)
+        label = v
+        if v.startswith("float:"):
+            os.environ["B200_DIRECT_PERIODIC_FLOAT"] = "1"; v = v[6:]
+        elif v.startswith("mixed:"):
+            os.environ["B200_DIRECT_PERIODIC_MIXED"] = "1"; v = v[6:]
         if v.startswith("default"):
             os.environ.pop("B200_DIRECT_VARIANT", None)
             v = "default"
@@ -47,7 +55,7 @@ def main():
             ref = a
         err = float(np.sqrt(((a - ref) ** 2).sum() / (ref ** 2).sum()))
         rate = float(n) * n / (best * 1e-3)
-        print(f"variant {v:10s} kernel {best:9.3f} ms  {rate:.4e} int/s  {20 * rate / 1e12:6.2f} TFLOP/s  "
+        print(f"variant {label:16s} kernel {best:9.3f} ms  {rate:.4e} int/s  {20 * rate / 1e12:6.2f} TFLOP/s  "
               f"{20 * rate / 1e12 / peak:6.3f} of peak   rel diff vs first {err:.1e}")
     eng.close()
 
