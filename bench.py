@@ -489,7 +489,7 @@ def bench_gpu(args):
         if args.workload == "direct":
             line["roofline"] = {
                 "bound": "fp32_fma",
-                "kernel": ("direct_kernel<R=6,THREADS=256,1 CTA/SM,open,equal-mass> (11 FP32 lane-ops + 1 MUFU per "
+                "kernel": ("direct_kernel<R=8,THREADS=256,1 CTA/SM,open,equal-mass> (11 FP32 lane-ops + 1 MUFU per "
                            "interaction; unequal masses run the 12-op instance)"),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic,

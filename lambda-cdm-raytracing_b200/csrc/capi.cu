@@ -56,9 +56,10 @@ int b200_ctx_create(int device, size_t max_particles, b200_ctx** out) {
     if (!ctx) return B200_ERR_NOMEM;
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    B200_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    B200_CUDA(cudaEventCreate(&ctx->ev0));
-    B200_CUDA(cudaEventCreate(&ctx->ev1));
+    cudaError_t ce = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&ctx->ev0);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&ctx->ev1);
+    if (ce != cudaSuccess) { b200_ctx_destroy(ctx); return 1000 + (int)ce; }
     if (max_particles) {
         int s = ctx->src_tiles.reserve(direct_tiles_bytes(max_particles));
         if (s != B200_OK) { b200_ctx_destroy(ctx); return s; }

@@ -157,6 +157,39 @@ def test_tree_full_size(engine, oracle):
     assert rel_l2(a[500000:520000], want) < TOL_TREE
 
 
+def test_tree_c4_size_16m(engine, oracle):
+    """BASELINE config 4 size: 2^24 particles.  Topology, COM and masses bit-exact against the oracle's build
+    (6.7 M nodes), forces on two target samples (one of them the last particles), and one fused kick-kick-drift of
+    all 2^24 particles bit-exact against the oracle's leapfrog with the walk's accelerations."""
+    import torch
+    n = 1 << 24
+    p = uniform_mt(n, seed=42)
+    m = np.ones(n, np.float32)
+    posm, t = _build_export(engine, p, m, box=100.0, leaf_cap=8, max_depth=20)
+    o = oracle.tree_build(p, m)
+    for k in TREE_KEYS:
+        assert np.array_equal(t[k], getattr(o, k)), k
+    assert int(t["part_off"][-1]) == n
+    acc = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    engine.tree_walk_dev(acc, 0, n, theta=0.5)
+    torch.cuda.synchronize()
+    a = acc.cpu().numpy()
+    assert np.isfinite(a).all()
+    for i0, cnt in ((5000000, 4096), (n - 2048, 2048)):
+        want = oracle.tree_forces(o, p, 0.5, i0=i0, n_targets=cnt)
+        assert rel_l2(a[i0:i0 + cnt], want) < TOL_TREE
+    vel = torch.zeros((n, 3), dtype=torch.float32, device="cuda")
+    dt = np.float32(1e-4)
+    engine.leapfrog_dev(posm, vel, acc, n, 2, dt * np.float32(0.5), 1.0, dt, 0.0)
+    torch.cuda.synchronize()
+    vo, po = np.zeros((n, 3), np.float32), p.copy()
+    oracle.kick(vo, a, m, dt * np.float32(0.5), 1.0)
+    oracle.kick(vo, a, m, dt * np.float32(0.5), 1.0)
+    oracle.drift(po, vo, dt, 0.0)
+    assert np.array_equal(vel.cpu().numpy(), vo)
+    assert np.array_equal(posm[:, :3].cpu().numpy(), po)
+
+
 def test_tree_zeldovich_c3(engine, oracle):
     """BASELINE config 3 inputs: the reference's own "Zel'dovich" generator (grid 128 -> 2^20 particles,
     seed 12345, z = 49, box 100), shifted to the centred convention; run live from the prebuilt
