@@ -242,6 +242,7 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
             float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
             if (i < n_targets) p = targets[i];
             if constexpr (FIXED) {
+                if (!(p.x == p.x) || !(p.y == p.y)) p.z = p.x + p.y;      // a NaN must not vanish in the conversion
                 ixi[r] = fixed_point(p.x, units);
                 iyi[r] = fixed_point(p.y, units);
             } else {
@@ -285,6 +286,7 @@ direct_kernel(const DirectSources src, const float4* __restrict__ targets, long 
             float* tile = stage_buf + s * TILE_FLOATS;
             for (int j = tid; j < TILE_J; j += THREADS) {
                 const float x = tile[j], y = tile[TILE_J + j];
+                if (!(x == x) || !(y == y)) tile[2 * TILE_J + j] = x + y;     // a NaN must not vanish in the conversion
                 tile[j] = __uint_as_float(fixed_point(x, units));
                 tile[TILE_J + j] = __uint_as_float(fixed_point(y, units));
                 if constexpr (UNIT) tile[3 * TILE_J + j] = (x >= 0.5f * FAR_AWAY) ? __int_as_float(0x7f800000) : eps2;

@@ -136,6 +136,17 @@ def test_direct_periodic_both_minimum_image_paths(engine, oracle, n, unit, eps, 
     assert rel_l2(a[sel][ok], want[ok]) < TOL
 
 
+def test_direct_periodic_nan_propagates(engine):
+    """A NaN coordinate poisons every force in both minimum-image paths (the fixed-point conversion of x and y
+    must not swallow it)."""
+    rng = np.random.default_rng(3)
+    for n in (3000, 20000):
+        p = rng.uniform(0.0, 100.0, (n, 3)).astype(np.float32)
+        p[n // 2, 0] = np.nan
+        a = engine.direct_forces_host(p, None, eps=0.05, box=100.0)
+        assert np.isnan(a).all(axis=1).sum() >= n - 1 and np.isnan(a[n // 2]).all()
+
+
 def test_direct_deterministic(engine):
     p = uniform_mt(20000, seed=3)
     a = engine.direct_forces_host(p, None)
