@@ -1041,6 +1041,11 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
     // lane takes part.  Branch-free packed rows: a lane that is out, or is the particle itself (:321), or a
     // padding slot, adds f = 0.
     auto leaf_range = [&](int q, int cnt, bool on_lane) {
+        // A lane that is out takes eps^2 = +inf: rsqrt gives exactly 0 and every row adds 0 -- no select per row.
+        // The particle itself (:321) needs no test either: d = 0 makes its term exactly 0 (eps > 0); the index in
+        // .w is compared only when the interactions are being counted.  Padding slots are parked far away.
+        const float e2 = on_lane ? eps2 : __int_as_float(0x7f800000);
+        const u64 e2_2 = w_pk(e2, e2);
         auto row2 = [&](const ulonglong2& a, const ulonglong2& b) {      // a = {x0 x1 | y0 y1}, b = {z0 z1 | w0 w1}
             u64 dx = w_add2(a.x, npx), dy = w_add2(a.y, npy), dz = w_add2(b.x, npz);
             if constexpr (PERIODIC) {
@@ -1048,28 +1053,25 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
                 dy = w_fma2(w_add2(w_fma2(dy, inv_box2, magic2), nmagic2), nbox2, dy);
                 dz = w_fma2(w_add2(w_fma2(dz, inv_box2, magic2), nmagic2), nbox2, dz);
             }
-            u64 r2 = w_fma2(dx, dx, eps2_2);
+            u64 r2 = w_fma2(dx, dx, e2_2);
             r2 = w_fma2(dy, dy, r2);
             r2 = w_fma2(dz, dz, r2);
-            float r2a, r2b, w0, w1;
+            float r2a, r2b;
             w_unpk(r2, r2a, r2b);
-            w_unpk(b.y, w0, w1);
             const u64 rinv = w_pk(rsqrt_fast(r2a), rsqrt_fast(r2b));
             if constexpr (POT) {
-                float f0, f1;
-                w_unpk(w_mul2(rinv, b.y), f0, f1);
-                ax2 = w_add2(ax2, w_pk(on_lane ? f0 : 0.f, on_lane ? f1 : 0.f));
+                ax2 = w_fma2(rinv, b.y, ax2);
                 return;
             }
             u64 f = w_mul2(w_mul2(rinv, rinv), rinv);                    // unit mass (:253, :340)
             if (FIXED) f = w_mul2(f, b.y);
-            const bool on0 = FIXED ? on_lane : (on_lane && __float_as_int(w0) != i);
-            const bool on1 = FIXED ? on_lane : (on_lane && __float_as_int(w1) != i);
-            float f0, f1;
-            w_unpk(f, f0, f1);
-            f = w_pk(on0 ? f0 : 0.f, on1 ? f1 : 0.f);
             ax2 = w_fma2(f, dx, ax2); ay2 = w_fma2(f, dy, ay2); az2 = w_fma2(f, dz, az2);
-            if (COUNT && !FIXED) c_pp += (on0 && __float_as_int(w0) >= 0) + (on1 && __float_as_int(w1) >= 0);
+            if (COUNT && !FIXED) {
+                float w0, w1;
+                w_unpk(b.y, w0, w1);
+                c_pp += (on_lane && __float_as_int(w0) != i && __float_as_int(w0) >= 0) +
+                        (on_lane && __float_as_int(w1) != i && __float_as_int(w1) >= 0);
+            }
         };
         if (COUNT && FIXED && on_lane) c_pp += cnt;
         const ulonglong2* src = leaf_pairs + 2 * (size_t)q;
@@ -1107,33 +1109,33 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
         const float4 c = nodes[2 * k];                                   // centre of mass, M
         const float4 mf = nodes[2 * k + 1];                              // first | skip | cell edge | leaf-child particles
         const int first = __float_as_int(mf.x), skip = __float_as_int(mf.y), lcnt = __float_as_int(mf.w);
-        bool open = false;
-        if (active) {
-            float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
-            if constexpr (PERIODIC) {
-                dx = __fsub_rn(dx, __fmul_rn(box, roundf(__fdiv_rn(dx, box))));
-                dy = __fsub_rn(dy, __fmul_rn(box, roundf(__fdiv_rn(dy, box))));
-                dz = __fsub_rn(dz, __fmul_rn(box, roundf(__fdiv_rn(dz, box))));
-            }
-            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            bool wraps = false;      // periodic: a cell reaching across the half-box distance is never a monopole
-            if constexpr (PERIODIC) {
-                const float hb = __fmul_rn(box, 0.5f);
-                wraps = __fadd_rn(fabsf(dx), mf.z) > hb || __fadd_rn(fabsf(dy), mf.z) > hb || __fadd_rn(fabsf(dz), mf.z) > hb;
-            }
-            if (!wraps && accept_cell_sq(mf.z, d2, theta, theta2)) {     // :309
-                const float rinv = rsqrt_fast(d2 + eps2);
-                if constexpr (POT) {
-                    ax += c.w * rinv;
-                } else {
-                    const float f = c.w * rinv * rinv * rinv;            // :280-290
-                    ax += f * dx; ay += f * dy; az += f * dz;
-                }
-                if (COUNT) ++c_pc;
-                wake = skip;                                             // sleep through this subtree
+        // Branch-free: every lane runs the test and the monopole; a lane that sleeps or opens the cell takes
+        // eps^2 = +inf, so its rsqrt and with it its term are exactly 0.
+        float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
+        if constexpr (PERIODIC) {
+            dx = __fsub_rn(dx, __fmul_rn(box, roundf(__fdiv_rn(dx, box))));
+            dy = __fsub_rn(dy, __fmul_rn(box, roundf(__fdiv_rn(dy, box))));
+            dz = __fsub_rn(dz, __fmul_rn(box, roundf(__fdiv_rn(dz, box))));
+        }
+        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        bool wraps = false;          // periodic: a cell reaching across the half-box distance is never a monopole
+        if constexpr (PERIODIC) {
+            const float hb = __fmul_rn(box, 0.5f);
+            wraps = __fadd_rn(fabsf(dx), mf.z) > hb || __fadd_rn(fabsf(dy), mf.z) > hb || __fadd_rn(fabsf(dz), mf.z) > hb;
+        }
+        const bool accept = !wraps && accept_cell_sq(mf.z, d2, theta, theta2);          // :309
+        const bool take = active && accept;
+        const bool open = active && !accept;
+        {
+            const float rinv = rsqrt_fast(d2 + (take ? eps2 : __int_as_float(0x7f800000)));
+            if constexpr (POT) {
+                ax = fmaf(c.w, rinv, ax);
             } else {
-                open = true;
+                const float f = c.w * rinv * rinv * rinv;                // :280-290
+                ax = fmaf(f, dx, ax); ay = fmaf(f, dy, ay); az = fmaf(f, dz, az);
             }
+            if (COUNT) c_pc += take;
+            if (take) wake = skip;                                       // sleep through this subtree
         }
         if (__any_sync(FULL, open)) {                                    // :293-297
             if (COUNT && open) c_vis += 8;                               // its 8 children, leaves included
