@@ -1011,7 +1011,7 @@ template <bool COUNT, bool FIXED, bool PERIODIC = false, bool POT = false>
 __global__ void __launch_bounds__(128)
 walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order, int i0, int n_targets,
                  const float4* __restrict__ nodes, const int* __restrict__ leaf_off,
-                 const ulonglong2* __restrict__ leaf_pairs, float theta, float eps, float box,
+                 const ulonglong2* __restrict__ leaf_pairs, float theta, float theta2, float eps2, float box,
                  float* __restrict__ acc3, TreeGlobals* __restrict__ g) {
     typedef unsigned long long u64;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1021,8 +1021,8 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
     if (valid) p = posm[i];
     float ax = 0.f, ay = 0.f, az = 0.f;                                  // cells
     u64 ax2 = 0ull, ay2 = 0ull, az2 = 0ull;                              // leaf pairs, two sources per lane-op
-    const float eps2 = FIXED ? eps * eps : __fmul_rn(0.01f, 0.01f);      // :281-282, :334-335
-    const float theta2 = theta > 0.f ? theta * theta : 0.f;              // theta <= 0: nothing is ever accepted
+    // theta2 = theta^2 (0 when theta <= 0: nothing is ever accepted) and eps2 (0.01f * 0.01f, :281-282, :334-335,
+    // or the fixed mode's eps^2) come from the host as kernel parameters: constant-bank operands, no registers
     const u64 eps2_2 = w_pk(eps2, eps2);
     const u64 npx = w_pk(-p.x, -p.x), npy = w_pk(-p.y, -p.y), npz = w_pk(-p.z, -p.z);
     [[maybe_unused]] u64 inv_box2, magic2, nmagic2, nbox2;
@@ -1110,7 +1110,7 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
         const float4 mf = nodes[2 * k + 1];                              // first | skip | cell edge | leaf-child particles
         const int first = __float_as_int(mf.x), skip = __float_as_int(mf.y), lcnt = __float_as_int(mf.w);
         // Branch-free: every lane runs the test and the monopole; a lane that sleeps or opens the cell takes
-        // eps^2 = +inf, so its rsqrt and with it its term are exactly 0.
+        // 1/r = 0, so its term is exactly 0.
         float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
         if constexpr (PERIODIC) {
             dx = __fsub_rn(dx, __fmul_rn(box, roundf(__fdiv_rn(dx, box))));
@@ -1127,7 +1127,7 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
         const bool take = active && accept;
         const bool open = active && !accept;
         {
-            const float rinv = rsqrt_fast(d2 + (take ? eps2 : __int_as_float(0x7f800000)));
+            const float rinv = take ? rsqrt_fast(d2 + eps2) : 0.0f;
             if constexpr (POT) {
                 ax = fmaf(c.w, rinv, ax);
             } else {
@@ -1422,11 +1422,13 @@ int tree_walk(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* acc
     }
     if (ctx->timing) B200_CUDA(cudaEventRecord(ctx->ev0, st));
     const bool per_thread = !T->fixed && getenv("B200_WALK_PER_THREAD") != nullptr;     // tuning hook
+    const float theta2 = theta > 0.f ? theta * theta : 0.f;
+    const float eps2 = T->fixed ? T->eps * T->eps : 0.01f * 0.01f;
     // one launch macro for the warp walk's instances: <COUNT, FIXED, PERIODIC>
 #define B200_WALK(COUNT_, FIXED_, PERIODIC_)                                                                     \
     walk_warp_kernel<COUNT_, FIXED_, PERIODIC_><<<grid, 128, 0, st>>>(                                           \
         T->posm, T->order.as<int>(), (int)i0, (int)n_targets, T->nodes.as<float4>(), T->leaf_off.as<int>(),      \
-        T->leaf_pos.as<ulonglong2>(), theta, T->eps, T->periodic_box, (float*)acc3, g)
+        T->leaf_pos.as<ulonglong2>(), theta, theta2, eps2, T->periodic_box, (float*)acc3, g)
     if (T->fixed) {
         const bool periodic = T->periodic_box > 0.f;
         if (T->counting) { if (periodic) B200_WALK(true, true, true); else B200_WALK(true, true, false); }
@@ -1459,14 +1461,16 @@ int tree_potential(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void
     B200_TRY(tree_target_order(ctx, T, i0, n_targets, st));
     TreeGlobals* g = T->globals.as<TreeGlobals>();
     const unsigned grid = (unsigned)((n_targets + 127) / 128);
+    const float theta2 = theta > 0.f ? theta * theta : 0.f;
+    const float eps2 = T->eps * T->eps;
     if (T->periodic_box > 0.f)
         walk_warp_kernel<false, true, true, true><<<grid, 128, 0, st>>>(
             T->posm, T->order.as<int>(), (int)i0, (int)n_targets, T->nodes.as<float4>(), T->leaf_off.as<int>(),
-            T->leaf_pos.as<ulonglong2>(), theta, T->eps, T->periodic_box, (float*)phi, g);
+            T->leaf_pos.as<ulonglong2>(), theta, theta2, eps2, T->periodic_box, (float*)phi, g);
     else
         walk_warp_kernel<false, true, false, true><<<grid, 128, 0, st>>>(
             T->posm, T->order.as<int>(), (int)i0, (int)n_targets, T->nodes.as<float4>(), T->leaf_off.as<int>(),
-            T->leaf_pos.as<ulonglong2>(), theta, T->eps, T->periodic_box, (float*)phi, g);
+            T->leaf_pos.as<ulonglong2>(), theta, theta2, eps2, T->periodic_box, (float*)phi, g);
     B200_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return B200_OK;
