@@ -1008,7 +1008,7 @@ __device__ __forceinline__ unsigned long long w_fma2(unsigned long long a, unsig
 // The pair loop has no self test, so the i == i term m_i / eps is subtracted at the end; that is exact as
 // long as a target never accepts a cell that contains itself, i.e. theta <= 1/sqrt(3) (checked by the host).
 template <bool COUNT, bool FIXED, bool PERIODIC = false, bool POT = false>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 10)
 walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order, int i0, int n_targets,
                  const float4* __restrict__ nodes, const int* __restrict__ leaf_off,
                  const ulonglong2* __restrict__ leaf_pairs, float theta, float theta2, float eps2, float box,
