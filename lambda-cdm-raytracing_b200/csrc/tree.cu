@@ -1007,6 +1007,17 @@ __device__ __forceinline__ unsigned long long w_fma2(unsigned long long a, unsig
 // -- monopole M / r for an accepted cell -- instead of the acceleration; one float per target comes out.
 // The pair loop has no self test, so the i == i term m_i / eps is subtracted at the end; that is exact as
 // long as a target never accepts a cell that contains itself, i.e. theta <= 1/sqrt(3) (checked by the host).
+// One 256-bit read-only load (sm_100 LDG.E.ENL2.256): a walk record, or one pair row of leaf sources, is 32
+// bytes, 32-byte aligned -- half the L1 requests of two 128-bit loads.
+__device__ __forceinline__ void ld256(const float4* p, float4& a, float4& b) {
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+__device__ __forceinline__ void ld256(const ulonglong2* p, ulonglong2& a, ulonglong2& b) {
+    asm("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a.x), "=l"(a.y), "=l"(b.x), "=l"(b.y) : "l"(p));
+}
+
 template <bool COUNT, bool FIXED, bool PERIODIC = false, bool POT = false>
 __global__ void __launch_bounds__(128, 10)
 walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order, int i0, int n_targets,
@@ -1077,11 +1088,17 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
         const ulonglong2* src = leaf_pairs + 2 * (size_t)q;
         const int np = (cnt + 1) >> 1;
         int k2 = 0;
-        for (; k2 + 2 <= np; k2 += 2) {                  // 4 broadcast loads in flight, then 2 packed rows
-            const ulonglong2 a0 = src[2 * k2], b0 = src[2 * k2 + 1], a1 = src[2 * k2 + 2], b1 = src[2 * k2 + 3];
+        for (; k2 + 2 <= np; k2 += 2) {                  // 2 broadcast 256-bit loads in flight, then 2 packed rows
+            ulonglong2 a0, b0, a1, b1;
+            ld256(src + 2 * k2, a0, b0);
+            ld256(src + 2 * k2 + 2, a1, b1);
             row2(a0, b0); row2(a1, b1);
         }
-        if (k2 < np) row2(src[2 * k2], src[2 * k2 + 1]);
+        if (k2 < np) {
+            ulonglong2 a0, b0;
+            ld256(src + 2 * k2, a0, b0);
+            row2(a0, b0);
+        }
     };
 
     // a build that ran out of node slots (possible only in the fixed mode, whose node count has no a-priori
@@ -1106,8 +1123,8 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
     while (k >= 0) {
         if (wake == k) wake = AWAKE;
         const bool active = (wake == AWAKE);
-        const float4 c = nodes[2 * k];                                   // centre of mass, M
-        const float4 mf = nodes[2 * k + 1];                              // first | skip | cell edge | leaf-child particles
+        float4 c, mf;            // {centre of mass, M} {first | skip | cell edge | leaf-child particles}
+        ld256(nodes + 2 * (size_t)k, c, mf);
         const int first = __float_as_int(mf.x), skip = __float_as_int(mf.y), lcnt = __float_as_int(mf.w);
         // Branch-free: every lane runs the test and the monopole; a lane that sleeps or opens the cell takes
         // 1/r = 0, so its term is exactly 0.
