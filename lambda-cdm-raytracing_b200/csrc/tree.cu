@@ -964,11 +964,16 @@ __device__ __forceinline__ bool accept_cell(float size, float d2, float theta) {
 // interactions, in precisely the depth-first order, of the CPU walk.
 // size/|d| < theta taken as size^2 < theta^2 d^2 whenever the two sides differ by more than
 // 3e-5 relative (the roundings of either form are < 3e-7), else by the exact IEEE sequence.
-__device__ __forceinline__ bool accept_cell_sq(float size, float d2, float theta, float theta2) {
-    const float t = theta2 * d2;
+// The screening test runs on a contracted |d|^2 (3 lane-ops; within 2e-7 of the reference's rounding, far inside
+// the 3e-5 margin), and only an undecided case evaluates the reference's own sequence -- one rounding per
+// operation, no contraction.
+__device__ __forceinline__ bool accept_cell_d(float size, float dx, float dy, float dz, float d2_fast, float theta,
+                                              float theta2) {
+    const float t = theta2 * d2_fast;
     const float diff = size * size - t;
-    if (fabsf(diff) > 3.0e-5f * t) return diff < 0.0f;       // d2 == 0 -> t == 0 -> open, as size/0 = inf
-    return __fdiv_rn(size, __fsqrt_rn(d2)) < theta;              // :302-310, bit for bit
+    if (fabsf(diff) > 3.0e-5f * t) return diff < 0.0f;
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    return __fdiv_rn(size, __fsqrt_rn(d2)) < theta;
 }
 
 // FIXED: the "fixed physics" walk -- leaf sources carry their real mass in .w and there is no
@@ -1124,7 +1129,7 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
         if (wake == k) wake = AWAKE;
         const bool active = (wake == AWAKE);
         float4 c, mf;            // {centre of mass, M} {first | skip | cell edge | leaf-child particles}
-        ld256(nodes + 2 * (size_t)k, c, mf);
+        ld256(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nodes) + (size_t)(unsigned)k * 32), c, mf);
         const int first = __float_as_int(mf.x), skip = __float_as_int(mf.y), lcnt = __float_as_int(mf.w);
         // Branch-free: every lane runs the test and the monopole; a lane that sleeps or opens the cell takes
         // 1/r = 0, so its term is exactly 0.
@@ -1134,13 +1139,13 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
             dy = __fsub_rn(dy, __fmul_rn(box, roundf(__fdiv_rn(dy, box))));
             dz = __fsub_rn(dz, __fmul_rn(box, roundf(__fdiv_rn(dz, box))));
         }
-        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
         bool wraps = false;          // periodic: a cell reaching across the half-box distance is never a monopole
         if constexpr (PERIODIC) {
             const float hb = __fmul_rn(box, 0.5f);
             wraps = __fadd_rn(fabsf(dx), mf.z) > hb || __fadd_rn(fabsf(dy), mf.z) > hb || __fadd_rn(fabsf(dz), mf.z) > hb;
         }
-        const bool accept = !wraps && accept_cell_sq(mf.z, d2, theta, theta2);          // :309
+        const bool accept = !wraps && accept_cell_d(mf.z, dx, dy, dz, d2, theta, theta2);      // :309
         const bool take = active && accept;
         const bool open = active && !accept;
         {
