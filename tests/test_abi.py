@@ -80,3 +80,27 @@ def test_shard_range_matches_python_and_partitions():
                 covered += nl.value
             assert covered == n
     assert lib.b200_shard_range(10, 2, 2, None, None) == 1      # rank out of range
+
+
+def test_ic_params_layout_matches_header(tmp_path):
+    """The ctypes mirror of b200_ic_params has the header's size and field offsets (checked with gcc, no GPU), and
+    b200_ic_params_default -- a pure host function -- fills the reference's defaults (initial_conditions.hpp:19-45)."""
+    import ctypes as C
+    import subprocess
+    import b200grav
+    fields = [f[0] for f in b200grav.ICParams._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "b200grav.h"\nint main(void) {\n'
+                   '  printf("%zu\\n", sizeof(b200_ic_params));\n' +
+                   "".join(f'  printf("%zu\\n", offsetof(b200_ic_params, {f}));\n' for f in fields) +
+                   "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert out[0] == C.sizeof(b200grav.ICParams)
+    assert out[1:] == [getattr(b200grav.ICParams, f).offset for f in fields]
+    lib = b200grav.load_library()
+    p = b200grav.ICParams()
+    lib.b200_ic_params_default(C.byref(p))
+    assert (p.box, p.z_initial, p.seed, p.use_2lpt) == (100.0, 49.0, 12345, 0)
+    assert (p.omega_m, p.omega_lambda, p.omega_k, p.h, p.sigma_8, p.n_s) == (0.31, 0.69, 0.0, 0.67, 0.81, 0.965)
