@@ -56,3 +56,25 @@ def test_out_of_box_and_self():
     # 150 is the image of 50; -0.25 the image of 99.75
     assert abs(separation(encode(np.array([150.0], np.float32), box), encode(np.array([50.0], np.float32), box), box)[0]) < 1e-7
     assert abs(separation(e[:1], encode(np.array([99.75], np.float32), box), box)[0]) < 1e-7
+
+
+def test_fp32_magic_round_is_the_minimum_image():
+    """PMODE_FLOAT (and the z component of PMODE_FIXED_XY, and the tree's periodic pair rows):
+    q = (d * (1/box) + 1.5*2^23) - 1.5*2^23 is rint(d / box) for |d| < box, and d - box q (one FMA) is K2's minimum
+    image except for separations within a few ulps of half a box, where either image is equally near."""
+    F = np.float32
+    rng = np.random.default_rng(2)
+    for box in (F(100.0), F(64.0), F(1.0), F(737.5)):
+        xi = rng.uniform(0.0, float(box), 1_000_000).astype(F)
+        xj = rng.uniform(0.0, float(box), 1_000_000).astype(F)
+        d = (xj - xi).astype(F)
+        ib = (F(1.0) / box).astype(F)
+        magic = F(12582912.0)
+        t = (d.astype(np.float64) * float(ib) + float(magic)).astype(F)              # fma.rn
+        q = (t - magic).astype(F)
+        got = (q.astype(np.float64) * -float(box) + d.astype(np.float64)).astype(F)  # fma.rn
+        want = minimum_image(d.astype(np.float64), float(box))
+        border = np.abs(np.abs(d.astype(np.float64)) - 0.5 * float(box)) < 4e-7 * float(box)
+        assert np.all(np.isin(q, (-1.0, 0.0, 1.0)))
+        assert np.array_equal(got[~border].astype(np.float64), want[~border].astype(F).astype(np.float64))
+        assert np.all(np.abs(got[border]) <= 0.5 * float(box) * (1 + 1e-6))
