@@ -72,6 +72,39 @@ def test_direct_matches_reference_gpu_kernel(engine, refgpu, n, unit):
     assert rel_l2(ours, ref) < 2e-5, rel_l2(ours, ref)
 
 
+def test_direct_and_leapfrog_match_reference_gpu_golden(engine):
+    """The same comparison against the committed outputs of K2 / K4 (tests/golden/ref_gpu_kernels.npz, made on a
+    B200 by tests/golden/make_golden_gpu.py): needs no reference library at run time."""
+    import importlib.util
+    import torch
+    from conftest import GOLDEN, golden
+    spec = importlib.util.spec_from_file_location("make_golden_gpu", os.path.join(GOLDEN, "make_golden_gpu.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = golden("ref_gpu_kernels.npz")
+    posm, vel, force = mg.inputs()
+    n = posm.shape[0]
+    d_posm = torch.from_numpy(posm).cuda()
+    acc = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    engine.direct_forces_dev(d_posm, acc, eps=mg.EPS, box=mg.BOX)
+    torch.cuda.synchronize()
+    assert rel_l2(acc.cpu().numpy() * posm[:, 3:4], g["forces"]) < 2.5e-5      # K2's own sequential FP32 sum
+    nl = mg.N_LEAP
+    m = posm[:nl, 3]
+    d_p = torch.from_numpy(np.ascontiguousarray(posm[:nl])).cuda()
+    d_v = torch.from_numpy(vel).cuda()
+    d_a = torch.from_numpy(np.ascontiguousarray((force / m[:, None]).astype(np.float32))).cuda()
+    dt = np.float32(mg.DT)
+    engine.leapfrog_dev(d_p, d_v, d_a, nl, 1, dt * np.float32(0.5), mg.A, np.float32(0.0), mg.BOX)     # kick only
+    torch.cuda.synchronize()
+    assert np.abs(d_v.cpu().numpy() - g["kick_vel"]).max() <= 4e-7 * np.abs(g["kick_vel"]).max()
+    d_v = torch.from_numpy(g["kick_vel"].copy()).cuda()
+    engine.leapfrog_dev(d_p, d_v, d_a, nl, 0, np.float32(0.0), mg.A, dt, mg.BOX)                         # drift only
+    torch.cuda.synchronize()
+    d = np.abs(d_p.cpu().numpy()[:, :3] - g["drift_pos"])
+    assert np.minimum(d, mg.BOX - d).max() <= 2e-5
+
+
 def test_leapfrog_matches_reference_gpu_kernel(engine, refgpu):
     import torch
     n = 40000
