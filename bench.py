@@ -276,6 +276,460 @@ def _workload_config(args):
 
 
 # --------------------------------------------------------------------------- GPU arm
+NAN = float("nan")
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), \
+            "MEASURED_PEAKS.json hbm_gbs (burst copy figure; of measured)"
+    except Exception:
+        return 6532.2, "fallback 6532.2 GB/s (MEASURED_PEAKS.json not on this box)"
+
+
+def ncu_static(key, n):
+    """Per-launch figures that only a profiler can give (DRAM / L2 / L1 bytes, warp instructions executed) for
+    the launch this run repeats -- same inputs, same kernel, hence the same counts.  Captured once per kernel
+    revision under ncu (never timed there) and committed in profiles/ncu_traffic.json; null when no capture of
+    this size exists."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(key, {}).get(str(n))
+    except Exception:
+        return None
+
+
+class Dist:
+    """The few collectives the harness needs, no-ops on one GPU."""
+
+    def __init__(self, torch, dist, world, rank, dev):
+        self.torch, self.dist, self.world, self.rank, self.dev = torch, dist, world, rank, dev
+
+    def sync(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max(self, x):
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, x):
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t)
+        return float(t.item())
+
+    def all_ok(self, flag):
+        return self.max(0.0 if flag else 1.0) == 0.0
+
+
+class Sharded:
+    """Replicated float4 source array + this rank's target shard: contiguous original-index
+    ranges, sources all-gathered with NCCL.  poison() overwrites every row this rank does not own with NaN
+    (untimed, before each step), so a step whose all-gather did not deliver produces NaN forces;
+    gather_checksums_ok() compares, shard by shard, an integer checksum of the gathered rows with the one
+    their owner computed on its own copy."""
+
+    def __init__(self, D, posm_full_host, n):
+        torch = D.torch
+        self.D, self.n = D, n
+        self.lo, self.hi = D.rank * n // D.world, (D.rank + 1) * n // D.world
+        self.nl = self.hi - self.lo
+        self.posm = torch.from_numpy(posm_full_host).to(D.dev) if isinstance(posm_full_host, np.ndarray) \
+            else posm_full_host
+        self.shard = self.posm[self.lo:self.hi].clone() if D.world > 1 else self.posm
+        self.equal = (n % D.world == 0)
+
+    def poison(self):
+        if self.D.world > 1:
+            self.posm[:self.lo].fill_(NAN)
+            self.posm[self.hi:].fill_(NAN)
+
+    def gather(self):
+        D = self.D
+        if D.world > 1:
+            if self.equal:
+                D.dist.all_gather_into_tensor(self.posm.view(-1), self.shard.view(-1))
+            else:
+                outs = [self.posm[r * self.n // D.world:(r + 1) * self.n // D.world] for r in range(D.world)]
+                D.dist.all_gather(outs, self.shard)
+
+    def _checksum(self, rows):
+        return rows.contiguous().view(self.D.torch.int32).to(self.D.torch.int64).sum()
+
+    def gather_checksums_ok(self):
+        D = self.D
+        if D.world == 1:
+            return True
+        torch = D.torch
+        mine = self._checksum(self.shard).reshape(1)
+        owners = [torch.zeros(1, dtype=torch.int64, device=D.dev) for _ in range(D.world)]
+        D.dist.all_gather(owners, mine)
+        ok = True
+        for r in range(D.world):
+            got = self._checksum(self.posm[r * self.n // D.world:(r + 1) * self.n // D.world])
+            ok = ok and bool((got == owners[r][0]).item())
+        return D.all_ok(ok)
+
+
+def sample_block(lo, nl, want=1024):
+    """A contiguous block of `want` targets inside [lo, lo + nl) (the oracle takes target ranges)."""
+    cnt = min(want, nl)
+    return lo + (nl - cnt) // 3, cnt
+
+
+def parity_direct(D, S, acc, mass_unit):
+    """Untimed: >= 1024 targets per rank against the CPU oracle's FP64 direct sum over the gathered sources."""
+    from inputs import rel_l2
+    from oracle.pyoracle import Oracle
+    o = Oracle()
+    host = S.posm.cpu().numpy()
+    pos = np.ascontiguousarray(host[:, :3])
+    mass = None if mass_unit else np.ascontiguousarray(host[:, 3])
+    b0, cnt = sample_block(S.lo, S.nl)
+    finite = bool(np.isfinite(host).all())
+    ref = o.direct_f64(pos, mass, EPS, i0=b0, n_targets=cnt) if finite else np.full((cnt, 3), np.nan)
+    got = acc[b0 - S.lo:b0 - S.lo + cnt].cpu().numpy()
+    err = rel_l2(got, ref) if finite and np.isfinite(got).all() else float("inf")
+    err = D.max(err)
+    return {"rel_l2": err, "gate": 1e-5, "targets_per_rank": cnt, "oracle": "orc_direct_f64 (CPU, all gathered sources)",
+            "gather_checksums_ok": S.gather_checksums_ok(), "ok": bool(err <= 1e-5)}
+
+
+def parity_tree(D, S, acc, box=100.0, theta=0.5, on_rank0_only=False):
+    """Untimed: a block of targets per rank against the CPU oracle's tree (restated reference builder + walk) on
+    the gathered particles.  on_rank0_only: the oracle tree is built once, on rank 0, which checks every
+    rank's block (used at 2^24 particles, where the CPU build takes seconds and gigabytes)."""
+    from inputs import rel_l2
+    from oracle.pyoracle import Oracle
+    torch = D.torch
+    b0, cnt = sample_block(S.lo, S.nl)
+    got_dev = acc[b0 - S.lo:b0 - S.lo + cnt].contiguous()
+    err = 0.0
+    if on_rank0_only and D.world > 1:
+        blocks = [torch.empty((cnt, 3), dtype=torch.float32, device=D.dev) for _ in range(D.world)]
+        D.dist.all_gather(blocks, got_dev)      # every rank's block has the same size only when shards are equal
+        starts = [sample_block(r * S.n // D.world, (r + 1) * S.n // D.world - r * S.n // D.world)[0]
+                  for r in range(D.world)]
+        if D.rank == 0:
+            host = S.posm.cpu().numpy()
+            pos, mass = np.ascontiguousarray(host[:, :3]), np.ascontiguousarray(host[:, 3])
+            if np.isfinite(host).all():
+                o = Oracle()
+                t = o.tree_build(pos, mass, box=box)
+                for r in range(D.world):
+                    ref = o.tree_forces(t, pos, theta, i0=starts[r], n_targets=cnt)
+                    g = blocks[r].cpu().numpy()
+                    err = max(err, rel_l2(g, ref) if np.isfinite(g).all() else float("inf"))
+            else:
+                err = float("inf")
+    else:
+        host = S.posm.cpu().numpy()
+        pos, mass = np.ascontiguousarray(host[:, :3]), np.ascontiguousarray(host[:, 3])
+        got = got_dev.cpu().numpy()
+        if np.isfinite(host).all() and np.isfinite(got).all():
+            o = Oracle()
+            ref = o.tree_forces(o.tree_build(pos, mass, box=box), pos, theta, i0=b0, n_targets=cnt)
+            err = rel_l2(got, ref)
+        else:
+            err = float("inf")
+    err = D.max(err)
+    return {"rel_l2": err, "gate": 1e-3, "targets_per_rank": cnt,
+            "oracle": "orc_tree_build_levels + orc_tree_forces (CPU restatement of TreeForceComputer, all gathered particles)",
+            "gather_checksums_ok": S.gather_checksums_ok(), "ok": bool(err <= 1e-3)}
+
+
+def walk_roofline(eng, D, n_total, nl, cnt6, walk_s, clocks, static_ok):
+    """What bounds walk_warp_kernel: instruction issue on L1/L2-resident data.  No HBM fraction is quoted --
+    the algorithmic byte count of SURVEY 8d (32 B per node visit, 16 B per pair source, per LANE) is served by
+    broadcast loads and exceeds what any memory level moves by 10-1000x."""
+    vis, pc, pp, slots, nlanes, nawake = [float(x) for x in cnt6]
+    # instruction-weighted lane utilisation: a node visit costs ~38 instructions per warp, a packed pair row ~18
+    # (2 source slots per lane); SASS of the shipped kernel, profiles/r2_walk_sass_excerpt.txt
+    issued = 38.0 * nlanes + 9.0 * slots
+    useful = 38.0 * nawake + 9.0 * pp
+    inst = ncu_static("tree_walk_inst_executed", n_total) if static_ok else None
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    issue_peak = eng.sm_count * 4 * sm_mhz * 1e6            # warp instructions per second, 4 schedulers per SM
+    out = {
+        "bound": "issue",
+        "kernel": "walk_warp_kernel (a warp walks the union of the traversals of 32 Hilbert-adjacent targets; per-lane "
+                  "accept test; leaf particles grouped per parent, packed-FP32 pair rows)",
+        "kernel_ms": 1e3 * walk_s,
+        "interactions_per_s_walk_only": (pc + pp) / walk_s,
+        "fp32_tflops_at_20_flop": 20.0 * (pc + pp) / walk_s / 1e12,
+        "pair_row_lane_frac": pp / slots if slots else None,
+        "node_visit_lane_frac": nawake / nlanes if nlanes else None,
+        "useful_lane_frac": useful / issued if issued else None,
+        "lane_frac_weights": "38 instructions per node visit, 9 per pair-row source slot (SASS counts)",
+        "walk_counters_nodes_cells_pairs": [int(vis), int(pc), int(pp)],
+        "warp_instructions": inst,
+        "issue_frac": (inst / walk_s / issue_peak) if inst else None,
+        "issue_peak": f"{eng.sm_count} SMs x 4 schedulers x {sm_mhz:.0f} MHz (median SM clock sampled in this run)",
+        "warp_instructions_source": "ncu smsp__inst_executed.sum of this launch (profiles/ncu_traffic.json; same inputs, "
+                                    "same kernel => same count); time and clock are live",
+        "traffic": ncu_static("tree", n_total) if static_ok else None,
+        "ncu_l2_bytes": ncu_static("tree_l2_bytes", n_total) if static_ok else None,
+        "ncu_l1_bytes": ncu_static("tree_l1_bytes", n_total) if static_ok else None,
+    }
+    if out["issue_frac"] is not None:
+        out.update({"achieved": inst / walk_s / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instructions/s",
+                    "frac": out["issue_frac"]})
+    return out
+
+
+def tree_summary(eng, D, S, flush, steps=5, box=100.0, label="centred [-50,50)^3", with_parity=True, clocks=None,
+                 static_ok=False):
+    """BASELINE configs[2] on the device-resident particles: (all-gather +) build + walk per step, theta 0.5,
+    leaf 8, max_depth 20.  CUDA events around each step and around build / walk, L2 flushed between steps."""
+    torch = D.torch
+    n, lo, nl = S.n, S.lo, S.nl
+    acc = torch.empty((nl, 3), dtype=torch.float32, device=D.dev)
+
+    def step(ev=None):
+        S.gather()
+        if ev:
+            ev[1].record()
+        eng.tree_build_dev(S.posm, n, box, 8, 20)
+        if ev:
+            ev[2].record()
+        eng.tree_walk_dev(acc, lo, nl, theta=0.5)
+
+    for _ in range(3):
+        S.poison()
+        step()
+    D.sync()
+    tot, gat, bld, wlk = [], [], [], []
+    for _ in range(steps):
+        flush.zero_()
+        S.poison()
+        D.sync()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        step(ev)
+        ev[3].record()
+        torch.cuda.synchronize()
+        tot.append(ev[0].elapsed_time(ev[3])); gat.append(ev[0].elapsed_time(ev[1]))
+        bld.append(ev[1].elapsed_time(ev[2])); wlk.append(ev[2].elapsed_time(ev[3]))
+    D.sync()
+    eng.tree_set_counting(True)
+    eng.tree_walk_dev(acc, lo, nl, theta=0.5)
+    torch.cuda.synchronize()
+    cnt6 = eng.tree_walk_stats()
+    eng.tree_set_counting(False)
+    eng.tree_walk_dev(acc, lo, nl, theta=0.5)      # the parity block comes from the shipped (non-counting) instance
+    torch.cuda.synchronize()
+    step_s = D.max(float(np.mean(tot))) * 1e-3
+    walk_s = D.max(float(np.mean(wlk))) * 1e-3
+    inter = D.sum(float(cnt6[1] + cnt6[2]))
+    out = {"workload": f"TreeForceComputer theta=0.5 leaf=8 max_depth=20, {n} uniform particles {label}, root cube "
+                       f"[-{box / 2:g},{box / 2:g})^3; step = "
+                       + ("NCCL all-gather of the shards + replicated build + walk of this rank's targets" if D.world > 1
+                          else "build + walk"),
+           "ms_per_step": 1e3 * step_s, "allgather_ms": D.max(float(np.mean(gat))),
+           "build_ms": D.max(float(np.mean(bld))), "walk_kernel_ms": 1e3 * walk_s,
+           "interactions_per_s": inter / step_s, "particle_steps_per_s": n / step_s, "steps": steps,
+           "roofline": walk_roofline(eng, D, n, nl, cnt6, walk_s, clocks, static_ok and D.world == 1)}
+    if with_parity:
+        out["parity_check"] = parity_tree(D, S, acc, box=box)
+    return out
+
+
+def leapfrog_roofline(eng, D, n, reps=10):
+    """leapfrog_kernel alone on n particles (the fused kick-kick-drift pass of a KDK step): 16 + 12 + 12 B read,
+    12 + 16 B written per particle; the arrays (68 B x n) are far larger than L2, so no flush is needed."""
+    torch = D.torch
+    posm = torch.rand((n, 4), device=D.dev) + 0.5
+    vel = torch.zeros((n, 3), device=D.dev)
+    acc = torch.rand((n, 3), device=D.dev)
+    for _ in range(3):
+        eng.leapfrog_dev(posm, vel, acc, n, 2, np.float32(5e-5), 1.0, np.float32(1e-4), 0.0)
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.leapfrog_dev(posm, vel, acc, n, 2, np.float32(5e-5), 1.0, np.float32(1e-4), 0.0)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    t = float(np.mean(ms)) * 1e-3
+    peak, src = hbm_peak()
+    gbs = 68.0 * n / t / 1e9
+    del posm, vel, acc
+    return {"bound": "hbm", "kernel": "leapfrog_kernel (kick + kick + drift fused, 1024-particle tiles, coalesced 128-bit "
+                                      "accesses, velocities/accelerations transposed through shared memory)",
+            "particles": n, "kernel_ms": 1e3 * t, "bytes_per_particle": 68, "achieved": gbs, "peak": peak,
+            "unit": "GB/s", "frac": gbs / peak, "peak_source": src,
+            "traffic": ncu_static("leapfrog", n), "particle_steps_per_s": n / t}
+
+
+def c4_summary(eng, D, flush, n, steps, mode):
+    """BASELINE configs[3]: TreeForceComputer + Lambda-CDM leapfrog (omega_m 0.31, omega_lambda 0.69, h 0.67,
+    a0 = 1, dt = 1e-4), n particles uniform in [-50,50)^3 in RANDOM index order with N(0,100) velocities,
+    sharded over the ranks.  Every step = fused kick-kick-drift of the local particles, scale-factor update,
+    exchange, octree build, theta = 0.5 walk of the local targets.  Phases are timed with CUDA events on the
+    launching stream; every figure is the max over ranks."""
+    torch, dist = D.torch, D.dist
+    g = torch.Generator(device=D.dev)
+    g.manual_seed(4242)
+    posm = torch.empty((n, 4), dtype=torch.float32, device=D.dev)
+    velf = torch.empty((n, 3), dtype=torch.float32, device=D.dev)
+    if D.rank == 0:
+        posm[:, :3] = torch.rand((n, 3), generator=g, device=D.dev) * 100.0 - 50.0
+        posm[:, 3] = 1.0
+        velf.normal_(0.0, 100.0, generator=g)
+    if D.world > 1:
+        dist.broadcast(posm, 0)
+        dist.broadcast(velf, 0)
+    dt = 1e-4
+    run = C4Run(eng, D, posm, velf, n, mode)
+    del velf
+    a = 1.0
+    run.forces()                         # forces at the initial positions (first half-kick)
+    for _ in range(3):
+        a = run.step(a, dt)
+    D.sync()
+    sampler = ClockSampler(D.dev.index, period=0.005)
+    sampler.start()
+    names = run.phase_names
+    acc_ms = {k: [] for k in names}
+    tot = []
+    for _ in range(steps):
+        flush.zero_()
+        run.poison()
+        D.sync()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+        ev[0].record()
+        a = run.step(a, dt, ev)
+        torch.cuda.synchronize()
+        tot.append(ev[0].elapsed_time(ev[-1]))
+        for i, k in enumerate(names):
+            acc_ms[k].append(ev[i].elapsed_time(ev[i + 1]))
+    D.sync()
+    sampler.stop()
+    step_s = D.max(float(np.sum(tot))) * 1e-3 / steps
+    out = {"workload": f"TreeForceComputer theta=0.5 leaf=8 max_depth=20 + Lambda-CDM KDK leapfrog (omega_m 0.31, "
+                       f"omega_lambda 0.69, h 0.67, a0 1, dt 1e-4), {n} particles uniform [-50,50)^3 in random index "
+                       f"order, N(0,100) velocities, {D.world} GPU(s)",
+           "mode": run.mode_text, "ms_per_step": 1e3 * step_s, "particle_steps_per_s": n / step_s, "steps": steps,
+           "scale_factor_after": a}
+    for k in names:
+        out[k + "_ms"] = D.max(float(np.mean(acc_ms[k])))
+    out["clocks"] = sampler.summary()
+    peak, _ = hbm_peak()
+    out["leapfrog_hbm_frac"] = 68.0 * run.nl / (out["leapfrog_ms"] * 1e-3) / 1e9 / peak if out.get("leapfrog_ms") else None
+    out["parity_check"] = run.parity()
+    run.close()
+    return out
+
+
+class C4Run:
+    """One rank's state of the C4 run.  mode "replicated": contiguous index shards, positions all-gathered in
+    place, every rank builds the whole octree (round-1 scheme)."""
+
+    def __init__(self, eng, D, posm, velf, n, mode):
+        torch = D.torch
+        self.eng, self.D, self.n, self.mode = eng, D, n, mode
+        self.S = Sharded(D, posm, n)
+        self.lo, self.nl = self.S.lo, self.S.nl
+        self.vel = velf[self.lo:self.lo + self.nl].clone()
+        self.acc = torch.zeros((self.nl, 3), dtype=torch.float32, device=D.dev)
+        self.phase_names = ["leapfrog", "allgather", "build", "walk"]
+        self.mode_text = ("contiguous index shards; NCCL all-gather of the float4 shards; every rank builds the whole "
+                          "octree (graph replay) and walks its own targets")
+
+    def poison(self):
+        self.S.poison()
+
+    def forces(self, ev=None):
+        S, eng = self.S, self.eng
+        S.gather()
+        if ev:
+            ev[2].record()
+        eng.tree_build_dev(S.posm, self.n, 100.0, 8, 20)
+        if ev:
+            ev[3].record()
+        eng.tree_walk_dev(self.acc, self.lo, self.nl, theta=0.5)
+        if ev:
+            ev[4].record()
+
+    def step(self, a, dt, ev=None):
+        eng = self.eng
+        # closing half-kick of the previous step + opening half-kick + drift: one pass (b200_leapfrog_dev, n_kicks = 2)
+        eng.leapfrog_dev(self.S.shard, self.vel, self.acc, self.nl, 2, np.float32(dt * 0.5), a, np.float32(dt), 0.0)
+        a = eng.scale_factor_step(a, dt)
+        if ev:
+            ev[1].record()
+        self.forces(ev)
+        return a
+
+    def parity(self):
+        return parity_tree(self.D, self.S, self.acc, on_rank0_only=True)
+
+    def close(self):
+        pass
+
+
+def c1_summary(eng, D, steps=10):
+    """BASELINE configs[0]: DirectForceComputer, 16 384 uniform particles, 10 KDK leapfrog steps (dt 1e-3, eps
+    0.01), device-resident between steps; wall clock around the 10 steps with a synchronise on both sides."""
+    import b200grav
+    from inputs import uniform_mt
+    n = 16384
+    pos = uniform_mt(n, seed=42)
+    rng = np.random.default_rng(12345)
+    vel = rng.normal(0.0, 100.0, size=(n, 3)).astype(np.float32)
+    sim = b200grav.LambdaCDMSimulation(eng, pos, vel, np.ones(n, np.float32), force="direct", wrap=False)
+    sim.step(1e-3)
+    D.torch.cuda.synchronize()
+    e0, e1 = D.torch.cuda.Event(enable_timing=True), D.torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        sim.step(1e-3)
+    e1.record()
+    D.torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"workload": f"DirectForceComputer, {n} uniform particles, {steps} KDK leapfrog steps, dt 1e-3, eps 0.01, "
+                        "open boundary, state device-resident (b200grav.LambdaCDMSimulation)",
+            "ms_per_step": ms, "particle_steps_per_s": n / (ms * 1e-3),
+            "interactions_per_s": float(n) * n / (ms * 1e-3), "steps": steps}
+
+
+def c5_summary(eng, D, flush, n=1 << 23):
+    """BASELINE configs[4]: DirectForceComputer 2^23 particles, strong scaling; ONE timed evaluation (24 s on one
+    GPU) after a warm-up on 1/16 of the targets; NCCL all-gather of the shards inside the timed region."""
+    torch = D.torch
+    pos, mass = make_particles(n, seed=7)
+    S = Sharded(D, np.ascontiguousarray(np.concatenate([pos, mass[:, None]], 1), np.float32), n)
+    acc = torch.zeros((S.nl, 3), dtype=torch.float32, device=D.dev)
+    S.gather()
+    eng.direct_forces_dev(S.posm, acc, S.lo, max(1, S.nl // 16), eps=EPS)
+    flush.zero_()
+    S.poison()
+    D.sync()
+    eng.set_timing(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    S.gather()
+    eng.direct_forces_dev(S.posm, acc, S.lo, S.nl, eps=EPS)
+    e1.record()
+    torch.cuda.synchronize()
+    kern_s = D.max(eng.last_kernel_ms()) * 1e-3
+    eng.set_timing(False)
+    t = D.max(e0.elapsed_time(e1)) * 1e-3
+    out = {"workload": f"DirectForceComputer, {n} particles, uniform, unit masses, eps {EPS}, one evaluation; targets "
+                       f"sharded over {D.world} GPU(s), sources all-gathered (NCCL)",
+           "ms_per_step": 1e3 * t, "kernel_ms": 1e3 * kern_s, "interactions_per_s": float(n) * n / t, "steps": 1,
+           "fp32_tflops_per_gpu_at_20_flop": 20.0 * float(S.nl) * n / kern_s / 1e12,
+           "parity_check": parity_direct(D, S, acc, True)}
+    del S, acc
+    return out
+
+
 def bench_gpu(args):
     import torch
     import torch.distributed as dist
@@ -295,40 +749,31 @@ def bench_gpu(args):
     os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    D = Dist(torch, dist, world, rank, dev)
     eng = b200grav.Engine(local)
 
     n = args.particles
-    lo, hi = rank * n // world, (rank + 1) * n // world
-    nl = hi - lo
     if args.ic == "zeldovich":
         # generated on the device by the engine's own IC step (b200_zeldovich_ics_dev): every rank
         # produces the same replicated particle set (counter-based RNG), origin-centred convention
-        posm = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        posm0 = torch.empty((n, 4), dtype=torch.float32, device=dev)
         vel_ic = torch.empty((n, 3), dtype=torch.float32, device=dev)
-        ic_stats = eng.zeldovich_ics_dev(posm, vel_ic, n_particles=n, grid=zeldovich_grid(n), box=100.0,
-                                         z_initial=args.z_initial, seed=12345, origin_shift=50.0)
+        eng.zeldovich_ics_dev(posm0, vel_ic, n_particles=n, grid=zeldovich_grid(n), box=100.0,
+                              z_initial=args.z_initial, seed=12345, origin_shift=50.0)
         del vel_ic
         torch.cuda.synchronize()
-        posm_host = posm.cpu().numpy()
+        posm_host = posm0.cpu().numpy()
+        del posm0
         pos, mass = np.ascontiguousarray(posm_host[:, :3]), np.ascontiguousarray(posm_host[:, 3])
     else:
         pos, mass = make_particles(n, order=args.order)
         posm_host = np.ascontiguousarray(np.concatenate([pos, mass[:, None]], 1), np.float32)
-        posm = torch.from_numpy(posm_host).to(dev)             # full source set, resident in HBM
-    shard = posm[lo:hi].clone() if world > 1 else posm     # this rank's particles (all-gather input)
+    S = Sharded(D, posm_host, n)                            # full source set resident in HBM + this rank's shard
+    posm, shard, lo, hi, nl = S.posm, S.shard, S.lo, S.hi, S.nl
     acc = torch.zeros((nl, 3), dtype=torch.float32, device=dev)
     vel = torch.zeros((nl, 3), dtype=torch.float32, device=dev)
     kdk = {"a": 1.0, "dt": 1e-4}                           # C4: a0 = 1, dt = 1e-4
     flush = torch.empty(128 * 1024 * 1024, dtype=torch.float32, device=dev)   # 512 MB > 126 MB L2
-    equal_shards = (n % world == 0)
-
-    def gather_sources():
-        if world > 1:
-            if equal_shards:
-                dist.all_gather_into_tensor(posm.view(-1), shard.view(-1))
-            else:
-                outs = [posm[r * n // world:(r + 1) * n // world] for r in range(world)]
-                dist.all_gather(outs, shard)
 
     masses_equal = bool((mass == mass[0]).all())    # every rank holds the same (replicated) initial masses
     peers = None
@@ -351,18 +796,14 @@ def bench_gpu(args):
         if args.kdk:    # closing half-kick of the previous step + opening half-kick + drift, one pass
             eng.leapfrog_dev(shard, vel, acc, nl, 2, np.float32(kdk["dt"] * 0.5), kdk["a"], np.float32(kdk["dt"]), 0.0)
             kdk["a"] = eng.scale_factor_step(kdk["a"], kdk["dt"])
-        gather_sources()
+        S.gather()
         if args.workload == "direct":
             eng.direct_forces_dev(posm, acc, lo, nl, eps=EPS)
         else:
             eng.tree_build_dev(posm, n, 100.0, 8, 20)
             eng.tree_walk_dev(acc, lo, nl, theta=0.5)
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+    sync_all = D.sync
 
     # FP32 peak of this GPU, measured now (the roofline denominator)
     peak_ffma, _ = eng.fp32_peak_probe(0, 4000)
@@ -370,6 +811,7 @@ def bench_gpu(args):
     peak = max(peak_ffma, peak_ffma2)
 
     for _ in range(max(args.warmup, 3)):
+        S.poison()
         step()
     sync_all()
 
@@ -381,6 +823,7 @@ def bench_gpu(args):
     kernel_ms = []
     for k in range(args.steps):
         flush.zero_()                                      # evict L2 (untimed)
+        S.poison()                                         # rows this rank does not own: NaN until the step's all-gather
         sync_all()
         ev[k][0].record()
         step()
@@ -392,51 +835,56 @@ def bench_gpu(args):
     eng.set_timing(False)
     sampler.stop()
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    kern_ms = torch.tensor([float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
-    total_s = float(total_ms.item()) * 1e-3
-    kern_s = float(kern_ms.item()) * 1e-3
+    total_s = D.max(sum(step_ms)) * 1e-3
+    kern_s = D.max(float(np.mean(kernel_ms))) * 1e-3
+    clocks = sampler.summary()
 
-    # ---- end-to-end through the host-pointer C ABI (pinned host memory) ----
+    # ---- untimed: is the result of the last timed step right, and did the all-gather deliver? ----
+    if args.workload == "direct":
+        parity = parity_direct(D, S, acc, masses_equal) if peers is None else None
+    else:
+        parity = parity_tree(D, S, acc)
+
+    # ---- end-to-end through the host-pointer C ABI ----
     pin_pos = torch.from_numpy(pos).pin_memory()
     pin_mass = torch.from_numpy(mass).pin_memory()
     pin_out = torch.empty((n if world == 1 else nl, 3), dtype=torch.float32).pin_memory()
     pin_shard = torch.from_numpy(posm_host[lo:hi].copy()).pin_memory()
+    page_pos, page_mass = pos.copy(), mass.copy()           # plain malloc'd arrays: what the engine's unique_ptr<float[]> is
+    page_out = np.empty((n, 3), np.float32)
 
-    def e2e_step():
+    def e2e_step(pageable=False):
         if world == 1:
+            p, m, o = (page_pos, page_mass, page_out) if pageable else (pin_pos.numpy(), pin_mass.numpy(), pin_out.numpy())
             if args.workload == "direct":
-                eng.direct_forces_host(pin_pos.numpy(), pin_mass.numpy(), eps=EPS, out=pin_out.numpy())
+                eng.direct_forces_host(p, m, eps=EPS, out=o)
             else:
-                eng.tree_forces_host(pin_pos.numpy(), pin_mass.numpy(), 0.5, 8, 20, 100.0, out=pin_out.numpy())
+                eng.tree_forces_host(p, m, 0.5, 8, 20, 100.0, out=o)
         else:   # each rank owns its shard on the host: H2D shard, all-gather, kernels, D2H shard result
             shard.copy_(pin_shard, non_blocking=True)
             step()
             pin_out.copy_(acc, non_blocking=True)
             torch.cuda.synchronize()
 
-    e2e_steps = max(2, min(args.steps, 5))
-    e2e_step()
-    sync_all()
-    t_e2e = []
-    for _ in range(e2e_steps):
-        flush.zero_()
+    def e2e_time(pageable):
+        e2e_step(pageable)
         sync_all()
-        t0 = time.perf_counter()
-        e2e_step()
-        torch.cuda.synchronize()
-        t_e2e.append(time.perf_counter() - t0)
-    e2e_t = torch.tensor([sum(t_e2e)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_t.item())
+        ts = []
+        for _ in range(e2e_steps):
+            flush.zero_()
+            S.poison()
+            sync_all()
+            t0 = time.perf_counter()
+            e2e_step(pageable)
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        return D.max(sum(ts))
 
-    clocks = sampler.summary()
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_s = e2e_time(False)
+    e2e_page_s = e2e_time(True) if world == 1 and not args.kdk else None
 
-    tree_bytes = None
+    tree_counts = None
     if args.workload == "direct":
         per_step = float(n) * float(n)                      # whole job: all targets x all sources
         per_launch = float(nl) * float(n)                   # this rank's main kernel
@@ -444,32 +892,15 @@ def bench_gpu(args):
         eng.tree_set_counting(True)
         eng.tree_walk_dev(acc, lo, nl, theta=0.5)
         torch.cuda.synchronize()
-        cnt = eng.tree_counters()
+        tree_counts = eng.tree_walk_stats()
         eng.tree_set_counting(False)
-        c = torch.tensor([float(cnt[1] + cnt[2])], dtype=torch.float64, device=dev)
-        per_launch = float(c.item())
-        if world > 1:
-            dist.all_reduce(c)
-        per_step = float(c.item())
-        # algorithmic bytes of one walk launch: 32 B per visited node (centre of mass +
-        # node record), 16 B per leaf-pair source, 16 B in + 12 B out per target
-        tree_bytes = 32.0 * float(cnt[0]) + 16.0 * float(cnt[2]) + 28.0 * nl
-        tree_counts = [int(x) for x in cnt]
+        per_launch = float(tree_counts[1] + tree_counts[2])
+        per_step = D.sum(per_launch)
 
-    traffic = l2_bytes = l1_bytes = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        if world == 1 and args.ic == "uniform":
-            traffic = tr.get(args.workload, {}).get(str(n))
-            l2_bytes = tr.get(args.workload + "_l2_bytes", {}).get(str(n))
-            l1_bytes = tr.get(args.workload + "_l1_bytes", {}).get(str(n))
-    except Exception:
-        pass
-
+    line = None
     if rank == 0:
         value = per_step * args.steps / total_s
         e2e_value = per_step * e2e_steps / e2e_s
-        achieved = FLOP_PER_INTERACTION * per_launch / kern_s / 1e12
         line = {
             "metric": "pairwise_interactions_per_s", "value": value, "unit": "interactions/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -485,50 +916,64 @@ def bench_gpu(args):
                            "per-rank pinned shard H2D + NCCL all-gather + b200_*_dev + D2H"},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "parity_check": parity,
         }
-        if args.workload == "direct":
+        if e2e_page_s is not None:
+            line["e2e_pageable"] = {
+                "value": per_step * e2e_steps / e2e_page_s, "unit": "interactions/s",
+                "ms_per_step": 1e3 * e2e_page_s / e2e_steps,
+                "api": "the same call on plain (pageable) host arrays -- what IForceComputer::compute_forces receives "
+                       "from the engine's unique_ptr<float[]> (simulation_engine.hpp:60-63)"}
+    if args.workload == "direct":
+        if rank == 0:
+            achieved = FLOP_PER_INTERACTION * per_launch / kern_s / 1e12
             line["roofline"] = {
                 "bound": "fp32_fma",
                 "kernel": ("direct_kernel<R=8,THREADS=256,1 CTA/SM,open,equal-mass> (11 FP32 lane-ops + 1 MUFU per "
                            "interaction; unequal masses run the 12-op instance)"),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic,
-                "peak_source": "FFMA/FFMA2 register-chain probe run in this process (b200_fp32_peak_probe); "
-                               "MEASURED_PEAKS.json has no FP32 figure",
+                "traffic": ncu_static("direct", n) if world == 1 and args.ic == "uniform" else None,
+                "peak_source": "FFMA/FFMA2 register-chain probe run in this process (b200_fp32_peak_probe: the builder's "
+                               "own probe); MEASURED_PEAKS.json has no FP32 figure",
                 "peak_ffma": peak_ffma, "peak_ffma2": peak_ffma2,
                 "nominal_peak": 148 * 128 * 2 * (clocks.get("sm_max_mhz") or 1965) * 1e6 / 1e12,
                 "flop_per_interaction": FLOP_PER_INTERACTION,
                 "kernel_ms": 1e3 * kern_s,
             }
-        else:
-            hbm = 6532.2
-            try:
-                hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-                src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
-            except Exception:
-                src = "fallback 6532.2 GB/s (MEASURED_PEAKS.json not on this box)"
-            gbs = tree_bytes / kern_s / 1e9
-            line["roofline"] = {
-                "bound": "hbm", "kernel": "walk_warp_kernel (stackless theta walk over internal nodes; a warp walks the "
-                                          "union of the traversals of 32 Hilbert-adjacent targets, per-lane accept test, "
-                                          "leaf particles grouped per parent)",
-                "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": traffic,
-                "peak_source": src,
-                "note": "algorithmic bytes = 32 B x nodes visited + 16 B x leaf-pair sources + 28 B x targets; most of it "
-                        "is served by L1/L2 (a warp's 32 Hilbert-adjacent targets visit nearly the same nodes), so this is "
-                        "an L1/L2 figure quoted against the HBM peak and can exceed it; the ncu capture of the same launch (traffic = DRAM "
-                        "bytes, ncu_l2_bytes, ncu_l1_bytes; profiles/r1_walk_warp_kernel_ncu_full.txt) shows a kernel bound by "
-                        "instruction issue (81 % of issue slots, l1tex 57 %), not by any memory level",
-                "ncu_l2_bytes": l2_bytes, "ncu_l1_bytes": l1_bytes,
-                "ncu_l2_gbs": (l2_bytes / kern_s / 1e9) if l2_bytes else None,
-                "ncu_l1_gbs": (l1_bytes / kern_s / 1e9) if l1_bytes else None,
-                "walk_counters_nodes_cells_pairs": tree_counts, "kernel_ms": 1e3 * kern_s,
-                "interactions_per_s_walk_only": per_launch / kern_s,
-            }
-        if world == 1 and args.workload == "direct" and not args.kdk and not args.no_tree_summary:
-            # the second kernel family of the hot path, same particles, a few steps: so that the default
-            # run's one line also says where the Barnes-Hut path (BASELINE configs[2]) stands
-            line["tree_summary"] = tree_summary(eng, posm, n, flush)
+    else:
+        rl = walk_roofline(eng, D, n, nl, tree_counts, kern_s, clocks, world == 1 and args.ic == "uniform"
+                           and args.order == "random")
+        if rank == 0:
+            line["roofline"] = rl
+
+    # ---- the other BASELINE configs, each a short measurement of its own (collective: every rank takes part) ----
+    extras = args.workload == "direct" and not args.kdk and not args.no_extras and args.ic == "uniform" \
+        and peers is None and n == (1 << 20)
+    if extras:
+        del pin_pos, pin_mass, pin_out, pin_shard
+        ts = tree_summary(eng, D, S, flush, clocks=clocks, static_ok=(args.order == "random"))
+        lf = leapfrog_roofline(eng, D, (1 << 24) // world)
+        c4 = c4_summary(eng, D, flush, 1 << 24, 8, args.c4_mode)
+        c5 = c5_summary(eng, D, flush) if not args.no_c5 else None
+        box_line = c1 = None
+        if world == 1:
+            # the [0,100) convention the reference's generators emit (initial_conditions.cpp:808-820): 7/8 of the
+            # particles lie outside the origin-centred root cube and end in max-depth overflow leaves
+            pb, mb = make_particles(n, seed=43)
+            Sb = Sharded(D, np.ascontiguousarray(np.concatenate([pb + np.float32(50.0), mb[:, None]], 1), np.float32), n)
+            box_line = tree_summary(eng, D, Sb, flush, steps=3, label="box convention [0,100)^3", clocks=clocks)
+            del Sb
+            c1 = c1_summary(eng, D)
+        if rank == 0:
+            line["tree_summary"] = ts
+            line["leapfrog_roofline"] = lf
+            line["c4_summary"] = c4
+            if c5 is not None:
+                line["c5_summary"] = c5
+            if box_line is not None:
+                line["tree_box_convention_summary"] = box_line
+                line["c1_summary"] = c1
+    if rank == 0:
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = run_cpu_baseline(args.workload)
         sys.stdout.flush()
@@ -539,41 +984,6 @@ def bench_gpu(args):
             peers.close()
         dist.destroy_process_group()
     eng.close()
-
-
-def tree_summary(eng, posm, n, flush, steps=5):
-    """Barnes-Hut theta = 0.5, leaf 8, max_depth 20 on the device-resident particles: build + walk per step,
-    CUDA events around each step, L2 flushed between steps.  The full line is `--workload tree`."""
-    import torch
-    acc = torch.empty((n, 3), dtype=torch.float32, device=posm.device)
-    for _ in range(3):
-        eng.tree_build_dev(posm, n, 100.0, 8, 20)
-        eng.tree_walk_dev(acc, 0, n, theta=0.5)
-    torch.cuda.synchronize()
-    eng.set_timing(True)
-    ms, walk_ms = [], []
-    for _ in range(steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        eng.tree_build_dev(posm, n, 100.0, 8, 20)
-        eng.tree_walk_dev(acc, 0, n, theta=0.5)
-        e1.record()
-        torch.cuda.synchronize()
-        ms.append(e0.elapsed_time(e1))
-        walk_ms.append(eng.last_kernel_ms())
-    eng.set_timing(False)
-    eng.tree_set_counting(True)
-    eng.tree_walk_dev(acc, 0, n, theta=0.5)
-    torch.cuda.synchronize()
-    cnt = eng.tree_counters()
-    eng.tree_set_counting(False)
-    step_s = float(np.mean(ms)) * 1e-3
-    return {"workload": f"TreeForceComputer theta=0.5 leaf=8 max_depth=20, {n} particles, build + walk per step",
-            "ms_per_step": 1e3 * step_s, "walk_kernel_ms": float(np.mean(walk_ms)),
-            "interactions_per_s": float(cnt[1] + cnt[2]) / step_s, "particle_steps_per_s": n / step_s,
-            "walk_counters_nodes_cells_pairs": [int(x) for x in cnt], "steps": steps}
 
 
 def main():
@@ -591,8 +1001,13 @@ def main():
     ap.add_argument("--order", default="random", choices=["random", "morton"],
                     help="index order of the uniform particles: as drawn (default) or sorted along a Morton curve")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-tree-summary", action="store_true",
-                    help="default (direct, 1 GPU) run: skip the short Barnes-Hut measurement added as `tree_summary`")
+    ap.add_argument("--no-extras", "--no-tree-summary", dest="no_extras", action="store_true",
+                    help="default (direct, 2^20) run: skip the short measurements of the other BASELINE configs "
+                         "(tree_summary, c4_summary, c5_summary, c1_summary, leapfrog_roofline)")
+    ap.add_argument("--no-c5", action="store_true", help="skip c5_summary (2^23-particle direct sum: 24 s on one GPU)")
+    ap.add_argument("--c4-mode", default="replicated", choices=["replicated", "sharded"],
+                    help="c4_summary: every rank builds the whole octree on contiguous index shards (round-1 scheme), "
+                         "or octant-sharded build + Hilbert-owned targets")
     ap.add_argument("--sources", default="allgather", choices=["allgather", "peer"],
                     help="N>1 direct sum: NCCL all-gather of the shards (default) or peer-mapped source tiles "
                          "pulled over NVLink by the force kernel itself")

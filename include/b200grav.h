@@ -161,7 +161,9 @@ int b200_tree_walk_dev(b200_ctx* ctx, size_t i0, size_t n_targets, float theta,
                        void* acc3, void* stream);
 /* The two phases the reference class exposes separately (include/forces/tree_force_computer.hpp:78-80,
  * build_tree / compute_tree_forces) on host arrays; the particles stay on the device in between.
- * b200_tree_walk_host walks all n particles of the last b200_tree_build_host. */
+ * b200_tree_walk_host walks all n particles of the last b200_tree_build_host; the packed particles sit in a
+ * buffer only b200_tree_build_host / b200_tree_forces_fixed_host write, so other host entry points may be
+ * called in between. */
 int b200_tree_build_host(b200_ctx* ctx, const float* pos3, const float* mass, size_t n, float box,
                          int leaf_cap, int max_depth);
 int b200_tree_walk_host(b200_ctx* ctx, float* acc3, size_t n, float theta);
@@ -224,6 +226,14 @@ int b200_tree_export(b200_ctx* ctx, int32_t* level, float* center, float* size,
  * [0] nodes visited, [1] monopole, [2] leaf pair interactions. */
 int b200_tree_set_counting(b200_ctx* ctx, int enabled);
 int b200_tree_counters(b200_ctx* ctx, uint64_t counters[3]);
+/* Lane utilisation of the same counting walk (the measurement behind bench.py's `useful_lane_frac`):
+ * [0..2] as b200_tree_counters; [3] pair-row source slots issued (64 per packed row a warp executes --
+ * [2] / [3] is the fraction of them some target wanted); [4] node-visit lanes issued (32 per record a
+ * warp loads), [5] of those, lanes that were awake (took part in the accept test). */
+int b200_tree_walk_stats(b200_ctx* ctx, uint64_t stats[6]);
+/* 1 if the last build ran out of node slots (fixed-physics mode only; the reference tree is bounded by
+ * n / leaf_cap splits): the walk of such a tree fills its output with NaN.  Synchronises. */
+int b200_tree_overflowed(b200_ctx* ctx, int* overflowed);
 
 /* ---- leapfrog (rows L1-L3) -------------------------------------------------
  * Replaces leapfrog_update / launch_leapfrog_update

@@ -78,6 +78,7 @@ int b200_ctx_destroy(b200_ctx* ctx) {
     ctx->energy_part.release(); ctx->energy_phi.release(); ctx->energy_out.release();
     ctx->ic_wk.release(); ctx->ic_tmp.release(); ctx->ic_psi.release(); ctx->ic_stats.release();
     ctx->h_pos3.release(); ctx->h_vel3.release(); ctx->h_mass.release(); ctx->h_posm4.release(); ctx->h_acc3.release();
+    ctx->h_tree_posm4.release();
     ctx->probe.release(); ctx->sort_scratch.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -308,8 +309,9 @@ int b200_tree_forces_fixed_host(b200_ctx* ctx, const float* pos3, const float* m
         B200_CUDA(cudaMemcpyAsync(ctx->h_mass.p, mass, n * sizeof(float), cudaMemcpyHostToDevice, st));
         d_mass = ctx->h_mass.as<float>();
     }
-    B200_TRY(pack_posm(ctx, ctx->h_pos3.p, d_mass, n, ctx->h_posm4.p, st));
-    B200_TRY(tree_build(ctx, ctx->h_posm4.p, n, 0.f, leaf_cap, max_depth, true, eps, st));
+    B200_TRY(ctx->h_tree_posm4.reserve(n * 4 * sizeof(float)));
+    B200_TRY(pack_posm(ctx, ctx->h_pos3.p, d_mass, n, ctx->h_tree_posm4.p, st));
+    B200_TRY(tree_build(ctx, ctx->h_tree_posm4.p, n, 0.f, leaf_cap, max_depth, true, eps, st));
     B200_TRY(tree_walk(ctx, 0, n, theta, ctx->h_acc3.p, st));
     B200_CUDA(cudaMemcpyAsync(acc3, ctx->h_acc3.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
@@ -334,13 +336,15 @@ int b200_tree_build_host(b200_ctx* ctx, const float* pos3, const float* mass, si
     if (!pos3 || !mass) return B200_ERR_INVALID;
     B200_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    // The packed particles live in a buffer of their own (not the staging the other host entry points
+    // reuse), so a direct / leapfrog host call between build_host and walk_host cannot clobber them.
     B200_TRY(ctx->h_pos3.reserve(n * 3 * sizeof(float)));
     B200_TRY(ctx->h_mass.reserve(n * sizeof(float)));
-    B200_TRY(ctx->h_posm4.reserve(n * 4 * sizeof(float)));
+    B200_TRY(ctx->h_tree_posm4.reserve(n * 4 * sizeof(float)));
     B200_CUDA(cudaMemcpyAsync(ctx->h_pos3.p, pos3, n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaMemcpyAsync(ctx->h_mass.p, mass, n * sizeof(float), cudaMemcpyHostToDevice, st));
-    B200_TRY(pack_posm(ctx, ctx->h_pos3.p, ctx->h_mass.p, n, ctx->h_posm4.p, st));
-    return tree_build(ctx, ctx->h_posm4.p, n, box, leaf_cap, max_depth, false, 0.01f, st);
+    B200_TRY(pack_posm(ctx, ctx->h_pos3.p, ctx->h_mass.p, n, ctx->h_tree_posm4.p, st));
+    return tree_build(ctx, ctx->h_tree_posm4.p, n, box, leaf_cap, max_depth, false, 0.01f, st);
 }
 
 int b200_tree_walk_host(b200_ctx* ctx, float* acc3, size_t n, float theta) {
@@ -419,6 +423,18 @@ int b200_tree_counters(b200_ctx* ctx, uint64_t counters[3]) {
     if (!ctx || !counters) return B200_ERR_INVALID;
     B200_CUDA(cudaSetDevice(ctx->device));
     return tree_counters(ctx, counters);
+}
+
+int b200_tree_walk_stats(b200_ctx* ctx, uint64_t stats[6]) {
+    if (!ctx || !stats) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return tree_walk_stats(ctx, stats);
+}
+
+int b200_tree_overflowed(b200_ctx* ctx, int* overflowed) {
+    if (!ctx || !overflowed) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return tree_overflowed(ctx, overflowed);
 }
 
 // ---- leapfrog ---------------------------------------------------------------

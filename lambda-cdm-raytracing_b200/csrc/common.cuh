@@ -63,6 +63,7 @@ struct b200_ctx {
     DevBuf ic_wk, ic_tmp, ic_psi, ic_stats;       // initial-conditions scratch (released after each call)
     // host-entry staging
     DevBuf h_pos3, h_vel3, h_mass, h_posm4, h_acc3;
+    DevBuf h_tree_posm4;    // particles of the last b200_tree_build_host: stay valid until the next host tree build
     // probe / standalone sort scratch
     DevBuf probe, sort_scratch;
 

@@ -4,14 +4,21 @@
 // which is launched three times per step (kick, drift, kick) and touches every
 // array each time.  Here one pass applies up to two half-kicks and the drift:
 // 40 B read + 28 B written per particle-step instead of 3 x ~40 B.
-// Pure HBM streaming: each thread owns 4 consecutive particles so velocities
-// and accelerations (3 floats per particle) move as aligned 128-bit vectors.
+// Pure HBM streaming.  A CTA owns a tile of 1024 particles; every global access is a
+// fully coalesced 128-bit vector (lane l of a warp touches bytes [16 l, 16 l + 16) of a
+// 512-byte run): positions as one float4 per particle, velocities and accelerations
+// (3 floats per particle, AoS) as the tile's 768 float4 words staged through shared
+// memory, where thread t reads floats 3p .. 3p+2 of its particles (stride 3: no bank
+// conflicts).  B200_LEAPFROG=v1 selects the round-1 kernel (a thread owns 4 consecutive
+// particles; 128-bit accesses at a 48/64-byte lane stride) for comparison.
 //
 // The arithmetic keeps the reference's operation order with one rounding per
 // operation (no FMA contraction) so trajectories are bit-identical to the CPU
 // restatement given identical accelerations:
 //     v += ((acc*m) * (1/m)) * dt * (1/a^2)        (:307-318; F = acc*m, :217-219)
 //     x  = fmodf((x + v*dt) + box, box)            (:322-329)
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "leapfrog.cuh"
 
@@ -49,8 +56,8 @@ __device__ __forceinline__ void step_particle(float4& p, float& vx, float& vy, f
 }
 
 __global__ void __launch_bounds__(256)
-leapfrog_kernel(float4* __restrict__ posm, float4* __restrict__ vel4, const float4* __restrict__ acc4,
-                long long n, int n_kicks, float dt_kick, float a2inv, float dt_drift, float box) {
+leapfrog_v1_kernel(float4* __restrict__ posm, float4* __restrict__ vel4, const float4* __restrict__ acc4,
+                   long long n, int n_kicks, float dt_kick, float a2inv, float dt_drift, float box) {
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // group of 4 particles
     const long long i0 = q * 4;
     if (i0 >= n) return;
@@ -93,6 +100,50 @@ leapfrog_kernel(float4* __restrict__ posm, float4* __restrict__ vel4, const floa
     }
 }
 
+// Tile kernel: full tiles of LF_TILE particles only (the host sends the ragged tail to the v1 kernel).
+constexpr int LF_THREADS = 256;
+constexpr int LF_PER = 4;
+constexpr int LF_TILE = LF_THREADS * LF_PER;          // 1024 particles, 768 float4 words of vel / acc
+
+__global__ void __launch_bounds__(LF_THREADS)
+leapfrog_kernel(float4* __restrict__ posm, float4* __restrict__ vel4, const float4* __restrict__ acc4,
+                int n_tiles, int n_kicks, float dt_kick, float a2inv, float dt_drift, float box) {
+    __shared__ __align__(16) float sv[3 * LF_TILE];
+    __shared__ __align__(16) float sa[3 * LF_TILE];
+    const int t = threadIdx.x;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        float4* pt = posm + (size_t)tile * LF_TILE;
+        float4* vt = vel4 + (size_t)tile * (3 * LF_TILE / 4);
+        const float4* at = acc4 + (size_t)tile * (3 * LF_TILE / 4);
+        float4 p[LF_PER];
+#pragma unroll
+        for (int j = 0; j < LF_PER; ++j) p[j] = pt[j * LF_THREADS + t];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            reinterpret_cast<float4*>(sv)[j * LF_THREADS + t] = vt[j * LF_THREADS + t];
+            reinterpret_cast<float4*>(sa)[j * LF_THREADS + t] = __ldg(at + j * LF_THREADS + t);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < LF_PER; ++j) {
+            const int q = 3 * (j * LF_THREADS + t);
+            float vx = sv[q], vy = sv[q + 1], vz = sv[q + 2];
+            step_particle(p[j], vx, vy, vz, sa[q], sa[q + 1], sa[q + 2], n_kicks, dt_kick, a2inv, dt_drift, box);
+            sv[q] = vx; sv[q + 1] = vy; sv[q + 2] = vz;
+        }
+        __syncthreads();
+        if (n_kicks > 0) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) vt[j * LF_THREADS + t] = reinterpret_cast<const float4*>(sv)[j * LF_THREADS + t];
+        }
+        if (dt_drift != 0.f) {
+#pragma unroll
+            for (int j = 0; j < LF_PER; ++j) pt[j * LF_THREADS + t] = p[j];
+        }
+        __syncthreads();          // sv / sa are refilled by the next tile
+    }
+}
+
 __global__ void pack_posm_kernel(const float* __restrict__ pos3, const float* __restrict__ mass,
                                  long long n, float4* __restrict__ posm) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -124,12 +175,23 @@ int leapfrog(b200_ctx* ctx, void* posm4, void* vel3, const void* acc3, size_t n,
     if (((uintptr_t)vel3 | (uintptr_t)acc3 | (uintptr_t)posm4) & 15) return B200_ERR_INVALID;
     // lambda_cdm_kernels.cu:308: const float a2_inv = 1.0f / (scale_factor * scale_factor);
     const float a2inv = (float)(1.0f / (a * a));
-    const long long groups = ((long long)n + 3) / 4;
-    leapfrog_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(
-        (float4*)posm4, (float4*)vel3, (const float4*)acc3, (long long)n, n_kicks, dt_kick, a2inv,
-        dt_drift, box);
+    static const bool use_v1 = getenv("B200_LEAPFROG") != nullptr && getenv("B200_LEAPFROG")[1] == '1';   // tuning hook
+    const long long full = use_v1 ? 0 : (long long)n / LF_TILE;                // particles [0, full * LF_TILE)
+    if (full > 0) {
+        const long long cap = (long long)ctx->sm_count * 8;                    // 8 CTAs (24 KB of shared memory each) per SM
+        leapfrog_kernel<<<(unsigned)(full < cap ? full : cap), LF_THREADS, 0, st>>>(
+            (float4*)posm4, (float4*)vel3, (const float4*)acc3, (int)full, n_kicks, dt_kick, a2inv, dt_drift, box);
+        ctx->launches += 1;
+    }
+    const long long done = full * LF_TILE, rest = (long long)n - done;          // tail: a multiple-of-4 offset keeps vel/acc 16-byte aligned
+    if (rest > 0) {
+        const long long groups = (rest + 3) / 4;
+        leapfrog_v1_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(
+            (float4*)posm4 + done, (float4*)((float*)vel3 + 3 * done), (const float4*)((const float*)acc3 + 3 * done),
+            rest, n_kicks, dt_kick, a2inv, dt_drift, box);
+        ctx->launches += 1;
+    }
     B200_CUDA(cudaGetLastError());
-    ctx->launches += 1;
     return B200_OK;
 }
 

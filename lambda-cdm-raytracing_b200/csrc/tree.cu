@@ -53,7 +53,8 @@ struct TreeGlobals {
     unsigned int totals[8];     // digit totals of the level being processed
     int error;                  // 1 = node table overflow
     int stored_total;
-    unsigned long long counters[3];
+    unsigned long long counters[6];   // walk (counting instance): nodes visited, cell, pair interactions | pair-row
+                                      // lane slots issued, node-visit lanes issued, node-visit lanes awake
     int bbox[6];                // fixed mode: order-preserving int codes of min x,y,z / max x,y,z
     float root[4];              // fixed mode: root cube centre and edge
 };
@@ -189,7 +190,7 @@ __global__ void tree_init_kernel(TreeGlobals* g, float4* center, float4* com, in
         g->lv[0].n_entries = n;
         g->error = 0;
         g->stored_total = 0;
-        g->counters[0] = g->counters[1] = g->counters[2] = 0;
+        for (int c = 0; c < 6; ++c) g->counters[c] = 0;
         center[0] = fixed ? make_float4(g->root[0], g->root[1], g->root[2], g->root[3])
                           : make_float4(0.f, 0.f, 0.f, box);     // tree_force_computer.cpp:132-133
         com[0] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1050,6 +1051,7 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
         nbox2 = w_pk(-box, -box);
     }
     unsigned long long c_vis = valid ? 1 : 0, c_pc = 0, c_pp = 0;        // the root is visited by everyone
+    [[maybe_unused]] unsigned long long c_slots = 0, c_nl = 0, c_na = 0;  // lane-utilisation counters (COUNT only)
     constexpr int AWAKE = -2, NEVER = -3;
     int wake = valid ? AWAKE : NEVER;     // node id at which a sleeping lane resumes
 
@@ -1079,6 +1081,7 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
                 ax2 = w_fma2(rinv, b.y, ax2);
                 return;
             }
+            if (COUNT) c_slots += 2;                                     // every lane issues the row: two source slots
             u64 f = w_mul2(w_mul2(rinv, rinv), rinv);                    // unit mass (:253, :340)
             if (FIXED) f = w_mul2(f, b.y);
             ax2 = w_fma2(f, dx, ax2); ay2 = w_fma2(f, dy, ay2); az2 = w_fma2(f, dz, az2);
@@ -1128,6 +1131,7 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
     while (k >= 0) {
         if (wake == k) wake = AWAKE;
         const bool active = (wake == AWAKE);
+        if (COUNT) { c_nl += 1; c_na += active; }
         float4 c, mf;            // {centre of mass, M} {first | skip | cell edge | leaf-child particles}
         ld256(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nodes) + (size_t)(unsigned)k * 32), c, mf);
         const int first = __float_as_int(mf.x), skip = __float_as_int(mf.y), lcnt = __float_as_int(mf.w);
@@ -1185,11 +1189,17 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
             c_vis += __shfl_down_sync(FULL, c_vis, s);
             c_pc += __shfl_down_sync(FULL, c_pc, s);
             c_pp += __shfl_down_sync(FULL, c_pp, s);
+            c_slots += __shfl_down_sync(FULL, c_slots, s);
+            c_nl += __shfl_down_sync(FULL, c_nl, s);
+            c_na += __shfl_down_sync(FULL, c_na, s);
         }
         if ((threadIdx.x & 31) == 0) {
             atomicAdd(&g->counters[0], c_vis);
             atomicAdd(&g->counters[1], c_pc);
             atomicAdd(&g->counters[2], c_pp);
+            atomicAdd(&g->counters[3], c_slots);
+            atomicAdd(&g->counters[4], c_nl);
+            atomicAdd(&g->counters[5], c_na);
         }
     }
 }
@@ -1200,7 +1210,7 @@ __global__ void add_offset_kernel(int* __restrict__ v, int n, int off) {
     if (t < n) v[t] += off;
 }
 __global__ void zero_counters_kernel(TreeGlobals* g) {
-    g->counters[0] = g->counters[1] = g->counters[2] = 0;
+    for (int c = 0; c < 6; ++c) g->counters[c] = 0;
 }
 
 }  // namespace
@@ -1534,6 +1544,16 @@ int tree_counters(b200_ctx* ctx, uint64_t counters[3]) {
     TreeGlobals h;
     B200_TRY(fetch_globals(ctx, T, &h));
     for (int k = 0; k < 3; ++k) counters[k] = h.counters[k];
+    return B200_OK;
+}
+
+// all six counters of the last counting walk (see TreeGlobals::counters)
+int tree_walk_stats(b200_ctx* ctx, uint64_t stats[6]) {
+    TreeState* T = ctx->tree;
+    if (!T || !T->built) return B200_ERR_STATE;
+    TreeGlobals h;
+    B200_TRY(fetch_globals(ctx, T, &h));
+    for (int k = 0; k < 6; ++k) stats[k] = h.counters[k];
     return B200_OK;
 }
 

@@ -10,6 +10,7 @@ int tree_set_periodic(b200_ctx* ctx, float box);
 int tree_potential(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* phi, cudaStream_t st);
 const void* tree_posm(b200_ctx* ctx);
 int tree_counters(b200_ctx* ctx, uint64_t counters[3]);
+int tree_walk_stats(b200_ctx* ctx, uint64_t stats[6]);
 int tree_overflowed(b200_ctx* ctx, int* flag);
 int tree_stats(b200_ctx* ctx, size_t* n_nodes, size_t* n_leaves, size_t* depth, size_t* n_stored);
 int tree_export(b200_ctx* ctx, int32_t* level, float* center, float* size, int32_t* first_child,

@@ -54,6 +54,20 @@ void B200ComputerBase::finalize() {
     }
 }
 
+// ForceComputeParameters::cuda_device_id (force_computer_factory.hpp:39): a caller that hands parameters
+// through compute_forces' std::any names the device there; the context moves to it (its scratch is
+// reallocated on first use).  Fails loudly if that device is not a usable sm_100 part.
+void B200ComputerBase::use_device(int device) {
+    if (device == device_ && ctx_) return;
+    if (device < 0) return;
+    b200_ctx* fresh = nullptr;
+    const int rc = b200_ctx_create(device, 0, &fresh);
+    if (rc != B200_OK) fail((get_type() + ": cuda_device_id " + std::to_string(device)).c_str(), rc);
+    if (ctx_) b200_ctx_destroy(ctx_);
+    ctx_ = fresh;
+    device_ = device;
+}
+
 void B200ComputerBase::require_ctx() const {
     if (!ctx_) throw std::runtime_error(get_type() + ": not initialized (no B200 context; there is no CPU fallback)");
 }
@@ -63,7 +77,7 @@ void DirectForceComputer::compute_forces(const float* positions, const float* ma
     if (num_particles == 0) return;                    // tree_force_computer.cpp:83
     require_ctx();
     float eps = softening_;
-    if (const ForceComputeParameters* p = params_of(params)) eps = p->softening_length;
+    if (const ForceComputeParameters* p = params_of(params)) { eps = p->softening_length; use_device(p->cuda_device_id); }
     const int rc = b200_direct_forces_host(ctx_, positions, masses, forces, num_particles, eps, box_size_);
     if (rc != B200_OK) {
         std::cerr << "DirectForceComputer::compute_forces failed: " << b200_error_string(rc) << std::endl;
@@ -82,6 +96,7 @@ void B200TreeForceComputer::compute_forces(const float* positions, const float* 
     float eps = softening_;
     if (const ForceComputeParameters* p = params_of(params)) {
         theta = p->theta; cap = p->leaf_capacity; depth = p->tree_max_depth; eps = p->softening_length;
+        use_device(p->cuda_device_id);
     }
     const int rc = fixed_physics_
                        ? b200_tree_forces_fixed_host(ctx_, positions, masses, forces, num_particles, theta, (int)cap,

@@ -46,6 +46,7 @@ protected:
 
     explicit B200ComputerBase(const std::string& name) : name_(name) {}
     void require_ctx() const;
+    void use_device(int device);               // ForceComputeParameters::cuda_device_id
 
 public:
     ~B200ComputerBase() override;

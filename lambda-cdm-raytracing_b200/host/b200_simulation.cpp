@@ -59,7 +59,9 @@ void B200LambdaCDMSimulation::set_particles(const float* pos3, const float* vel3
     if (n_local_)
         check(b200_memcpy_h2d(ctx_, d_vel_, vel3 + 3 * i0_, n_local_ * 12, stream_), "upload velocities");
     check(b200_ctx_sync(ctx_, stream_), "sync");
+    generated_frame_ = Frame::Unknown;
     have_forces_ = false;
+    pending_kick_ = false;
     current_step_ = 0;
 }
 
@@ -68,7 +70,7 @@ void B200LambdaCDMSimulation::set_particles_spatially_ordered(const float* pos3,
     order_.assign(n, 0);
     if (n == 0) return;
     // keys need positions relative to a cube centred on the origin
-    const bool centred = method_ == B200ForceMethod::Tree || method_ == B200ForceMethod::TreeFixed;
+    const bool centred = needs_centred_frame(method_);
     const float shift = centred ? 0.0f : 0.5f * box_size_;
     std::vector<float> p(3 * n);
     for (size_t i = 0; i < 3 * n; ++i) p[i] = pos3[i] - shift;
@@ -92,15 +94,19 @@ void B200LambdaCDMSimulation::set_particles_spatially_ordered(const float* pos3,
 void B200LambdaCDMSimulation::initialize_particles(uint32_t seed) {
     // generate_initial_conditions (lambda_cdm_impl.cu:26-49): uniform positions in the box, Gaussian
     // velocities with dispersion 100*sqrt(omega_m) (:153), unit masses -- seeded here.
+    // The tree methods' root cube is centred on the origin (tree_force_computer.cpp:132-133), the periodic
+    // methods wrap into [0, box): positions are drawn in the frame the force method works in.
+    const float shift = needs_centred_frame(method_) ? 0.5f * box_size_ : 0.0f;
     std::mt19937 rng(seed);
     std::uniform_real_distribution<float> uni(0.0f, box_size_);
     std::normal_distribution<float> nrm(0.0f, 100.0f * (float)std::sqrt(params_.omega_m));
     std::vector<float> pos(3 * num_particles_), vel(3 * num_particles_);
     for (size_t i = 0; i < num_particles_; ++i) {
-        for (int k = 0; k < 3; ++k) pos[3 * i + k] = uni(rng);
+        for (int k = 0; k < 3; ++k) pos[3 * i + k] = uni(rng) - shift;
         for (int k = 0; k < 3; ++k) vel[3 * i + k] = nrm(rng);
     }
     set_particles(pos.data(), vel.data(), nullptr);
+    generated_frame_ = shift > 0.0f ? Frame::Centred : Frame::Box;
 }
 
 void B200LambdaCDMSimulation::set_initial_conditions_from_power_spectrum(uint32_t seed, double z_initial,
@@ -118,7 +124,7 @@ void B200LambdaCDMSimulation::set_initial_conditions_from_power_spectrum(uint32_
     p.use_2lpt = use_2lpt ? 1 : 0;
     p.omega_m = params_.omega_m; p.omega_lambda = params_.omega_lambda; p.omega_k = params_.omega_k;
     p.h = params_.h; p.sigma_8 = params_.sigma_8; p.n_s = params_.n_s;
-    const bool centred = method_ == B200ForceMethod::Tree || method_ == B200ForceMethod::TreeFixed;
+    const bool centred = needs_centred_frame(method_);
     p.origin_shift = centred ? 0.5f * box_size_ : 0.0f;
     // all N velocities land in the staging buffer; this rank keeps its own range
     void* d_vel_all = nullptr;
@@ -133,13 +139,16 @@ void B200LambdaCDMSimulation::set_initial_conditions_from_power_spectrum(uint32_
     b200_device_free(ctx_, d_vel_all);
     check(rc, "Zel'dovich initial conditions");
     scale_factor_ = 1.0 / (1.0 + z_initial);
+    generated_frame_ = centred ? Frame::Centred : Frame::Box;
     have_forces_ = false;
+    pending_kick_ = false;
     current_step_ = 0;
 }
 
 void B200LambdaCDMSimulation::copy_particles_to_host(std::vector<Particle>& particles) const {
     particles.resize(n_local_);
     if (!n_local_) return;
+    flush_pending_kick();
     std::vector<float> posm(4 * n_local_), vel(3 * n_local_);
     check(b200_memcpy_d2h(ctx_, posm.data(), (const char*)d_posm_ + i0_ * 16, n_local_ * 16, stream_), "download particles");
     check(b200_memcpy_d2h(ctx_, vel.data(), d_vel_, n_local_ * 12, stream_), "download velocities");
@@ -161,7 +170,25 @@ void B200LambdaCDMSimulation::power_spectrum(int grid, std::vector<float>& k, st
           "power spectrum");
 }
 
+bool B200LambdaCDMSimulation::needs_centred_frame(B200ForceMethod m) {
+    return m == B200ForceMethod::Tree || m == B200ForceMethod::TreeFixed;
+}
+
 void B200LambdaCDMSimulation::set_force_method(B200ForceMethod m, float theta, int leaf_capacity, int max_depth) {
+    // Particles this object generated sit in the frame of the method that was current then (origin-centred for
+    // Tree / TreeFixed, [0, box) otherwise).  The reference tree's root cube is fixed at the origin and the periodic
+    // methods wrap into [0, box), so a method that needs the other frame would silently see 7/8 of the particles
+    // outside its domain: refuse.  (Particles handed in through set_particles are the caller's responsibility.)
+    if (generated_frame_ != Frame::Unknown) {
+        const bool want_centred = needs_centred_frame(m);
+        const bool frame_matters = m == B200ForceMethod::Tree || m == B200ForceMethod::Direct ||
+                                   m == B200ForceMethod::TreeFixedPeriodic;       // TreeFixed / DirectOpen fit any frame
+        if (frame_matters && want_centred != (generated_frame_ == Frame::Centred))
+            throw std::logic_error("B200LambdaCDMSimulation::set_force_method: the particles were generated in the "
+                                   "coordinate frame of the previous force method; set the force method before "
+                                   "initialize_particles / set_initial_conditions_from_power_spectrum");
+    }
+    flush_pending_kick();
     method_ = m; theta_ = theta; leaf_capacity_ = leaf_capacity; max_depth_ = max_depth;
     have_forces_ = false;
 }
@@ -169,6 +196,7 @@ void B200LambdaCDMSimulation::set_force_method(B200ForceMethod m, float theta, i
 void B200LambdaCDMSimulation::compute_forces() {
     const size_t n = num_particles_;
     if (n == 0) return;
+    flush_pending_kick();          // a deferred closing kick still needs the accelerations about to be replaced
     // every rank sees all sources (replicated positions), and evaluates its own targets only
     if (method_ == B200ForceMethod::Tree || method_ == B200ForceMethod::TreeFixed ||
         method_ == B200ForceMethod::TreeFixedPeriodic) {
@@ -194,6 +222,8 @@ void B200LambdaCDMSimulation::compute_energy() {
     // particle can no longer accept a cell that contains it), every other method takes the O(N^2) pair sum of
     // the direct-sum kernel -- minimum image whenever the force method is periodic.
     double e[2] = {0.0, 0.0};
+    check_tree_overflow();
+    flush_pending_kick();
     const bool tree_fixed = method_ == B200ForceMethod::TreeFixed || method_ == B200ForceMethod::TreeFixedPeriodic;
     if (tree_fixed && num_particles_ > 0) {
         check(b200_tree_build_fixed_dev(ctx_, d_posm_, num_particles_, leaf_capacity_, max_depth_, softening_, stream_),
@@ -216,40 +246,75 @@ void B200LambdaCDMSimulation::update_scale_factor(double dt) {
     scale_factor_ += scale_factor_ * cosmology_.hubble_parameter_a(scale_factor_) * dt;   // lambda_cdm_impl.cu:261-269
 }
 
+float B200LambdaCDMSimulation::wrap_box() const {
+    return (method_ == B200ForceMethod::Direct || method_ == B200ForceMethod::TreeFixedPeriodic)
+               ? box_size_ : 0.0f;                                   // the periodic methods wrap into [0, box)
+}
+
+// The closing half-kick of a step is not launched by step(): it rides in the NEXT step's single
+// kick-kick-drift pass (same scale factor, same dt/2 -- one launch per step instead of two, bit-identical
+// velocities because the per-particle operations and their order do not change).  Anything that reads
+// velocities first calls this.
+void B200LambdaCDMSimulation::flush_pending_kick() const {
+    if (!pending_kick_) return;
+    pending_kick_ = false;
+    void* my_posm = (char*)d_posm_ + i0_ * 16;
+    check(b200_leapfrog_dev(ctx_, my_posm, d_vel_, d_acc_, n_local_, 1, pending_dt_kick_, pending_a_, 0.0f, wrap_box(),
+                            stream_),
+          "closing kick");
+}
+
 void B200LambdaCDMSimulation::step(double dt) {
     const size_t n = num_particles_;
     if (n == 0) { ++current_step_; return; }
     if (!have_forces_) compute_forces();
-    const float wrap = (method_ == B200ForceMethod::Direct || method_ == B200ForceMethod::TreeFixedPeriodic)
-                           ? box_size_ : 0.0f;                                   // the periodic methods wrap into [0, box)
+    const float wrap = wrap_box();
+    const float dt_kick = (float)(dt * 0.5);
     // lambda_cdm_impl.cu:167-213: kick(dt/2, a) -> drift(dt) -> a update -> forces -> kick(dt/2, a_new)
     void* my_posm = (char*)d_posm_ + i0_ * 16;
-    check(b200_leapfrog_dev(ctx_, my_posm, d_vel_, d_acc_, n_local_, 1, (float)(dt * 0.5), scale_factor_, (float)dt, wrap,
+    if (pending_kick_ && (pending_dt_kick_ != dt_kick || pending_a_ != scale_factor_)) flush_pending_kick();
+    const int n_kicks = pending_kick_ ? 2 : 1;       // previous step's closing kick + this step's opening kick
+    pending_kick_ = false;
+    check(b200_leapfrog_dev(ctx_, my_posm, d_vel_, d_acc_, n_local_, n_kicks, dt_kick, scale_factor_, (float)dt, wrap,
                             stream_),
           "kick+drift");
     update_scale_factor(dt);
     if (world_ > 1) check(b200_allgather_sources_dev(ctx_, d_posm_, n, stream_), "all-gather sources");
     compute_forces();
-    check(b200_leapfrog_dev(ctx_, my_posm, d_vel_, d_acc_, n_local_, 1, (float)(dt * 0.5), scale_factor_, 0.0f, wrap,
-                            stream_),
-          "closing kick");
-    check(b200_ctx_sync(ctx_, stream_), "sync");
-    ++current_step_;
+    pending_kick_ = true;                             // closing kick with the new scale factor: deferred
+    pending_dt_kick_ = dt_kick;
+    pending_a_ = scale_factor_;
+    ++current_step_;                                  // no host synchronisation here: read-backs synchronise
+}
+
+// The fixed-physics node table has no a-priori bound short of 2.3 N; a build that ran out of slots makes the walk
+// write NaN.  Checked where the host synchronises anyway (read-backs, energies), not per step.
+void B200LambdaCDMSimulation::check_tree_overflow() const {
+    if (!have_forces_) return;
+    if (method_ != B200ForceMethod::TreeFixed && method_ != B200ForceMethod::TreeFixedPeriodic) return;
+    int overflow = 0;
+    if (b200_tree_overflowed(ctx_, &overflow) == B200_OK && overflow)
+        throw std::runtime_error("B200LambdaCDMSimulation: the fixed-physics octree ran out of node slots "
+                                 "(pathological clustering); accelerations and everything integrated from them are NaN");
 }
 
 void B200LambdaCDMSimulation::copy_positions_to_host(float* positions) const {
     if (!num_particles_) return;
+    check_tree_overflow();
     check(b200_unpack_pos3_dev(ctx_, d_posm_, num_particles_, d_tmp3_, stream_), "unpack");
     check(b200_memcpy_d2h(ctx_, positions, d_tmp3_, num_particles_ * 12, stream_), "download positions");
 }
 
 void B200LambdaCDMSimulation::copy_velocities_to_host(float* velocities) const {
     if (!n_local_) return;
+    check_tree_overflow();
+    flush_pending_kick();
     check(b200_memcpy_d2h(ctx_, velocities, d_vel_, n_local_ * 12, stream_), "download velocities");
 }
 
 void B200LambdaCDMSimulation::copy_forces_to_host(float* accelerations) const {
     if (!n_local_) return;
+    check_tree_overflow();
     check(b200_memcpy_d2h(ctx_, accelerations, d_acc_, n_local_ * 12, stream_), "download accelerations");
 }
 

@@ -8,7 +8,9 @@
 //  * step() orders kick -> drift -> forces -> kick on ONE stream (the reference
 //    races its kick and drift on two streams, lambda_cdm_impl.cu:170-189) and the
 //    first half-kick uses forces computed at the initial positions (the reference
-//    reads uninitialised memory there);
+//    reads uninitialised memory there); the closing half-kick is folded into the next
+//    step's single kick-kick-drift pass (one leapfrog launch per step; velocity
+//    read-backs apply it first), and step() does not synchronise the host;
 //  * initialize_particles() is seeded (the reference seeds curand from the clock);
 //  * the force method is selectable: Direct (periodic minimum image, like the
 //    reference's K1/K2 kernels) or Tree (the CPU TreeForceComputer's semantics);
@@ -61,7 +63,19 @@ class B200LambdaCDMSimulation {
     void* d_acc_ = nullptr;                 // float[3N]
     void* d_tmp3_ = nullptr;                // float[3N] staging
 
+    // closing half-kick of the last step(), folded into the next step's kick-kick-drift pass
+    mutable bool pending_kick_ = false;
+    mutable float pending_dt_kick_ = 0.0f;
+    mutable double pending_a_ = 1.0;
+
+    enum class Frame { Unknown, Box, Centred };
+    Frame generated_frame_ = Frame::Unknown;    // frame of the particles this object generated itself
+    static bool needs_centred_frame(B200ForceMethod m);
+    void check_tree_overflow() const;
+
     void check(int status, const char* where) const;
+    void flush_pending_kick() const;
+    float wrap_box() const;
 
 public:
     B200LambdaCDMSimulation(size_t num_particles, float box_size, const CosmologyParams& params = CosmologyParams(),
@@ -71,7 +85,9 @@ public:
     B200LambdaCDMSimulation& operator=(const B200LambdaCDMSimulation&) = delete;
 
     // Initialization (lambda_cdm.hpp:41-44)
-    void initialize_particles(uint32_t seed = 12345);          // uniform [0,box), v ~ N(0, 100*sqrt(omega_m)), m = 1
+    // uniform in the box, v ~ N(0, 100*sqrt(omega_m)), m = 1; positions in [0, box), or in [-box/2, box/2) for the
+    // tree methods, whose root cube is centred on the origin.  Set the force method FIRST.
+    void initialize_particles(uint32_t seed = 12345);
     // host arrays of all N particles (every rank passes the same data), mass may be null
     void set_particles(const float* pos3, const float* vel3, const float* mass);
     // Same, but the particles are first put in space-filling-curve order (b200_spatial_order_dev; the cube is

@@ -21,7 +21,7 @@ EXPORTS = [
     "b200_pack_tiles_dev", "b200_direct_forces_parts_dev",
     "b200_morton_keys_dev", "b200_sort_pairs_dev", "b200_tree_build_dev",
     "b200_tree_walk_dev", "b200_tree_forces_host", "b200_tree_stats", "b200_tree_export",
-    "b200_tree_set_counting", "b200_tree_counters",
+    "b200_tree_set_counting", "b200_tree_counters", "b200_tree_walk_stats", "b200_tree_overflowed",
     "b200_leapfrog_dev", "b200_leapfrog_host", "b200_hubble_a", "b200_scale_factor_step", "b200_pack_posm_dev",
     "b200_device_alloc", "b200_device_free", "b200_memcpy_h2d", "b200_memcpy_d2h", "b200_unpack_pos3_dev", "b200_ipc_export", "b200_ipc_open", "b200_ipc_close",
     "b200_shard_range", "b200_shard_unique_id", "b200_shard_init", "b200_shard_finalize", "b200_shard_info",
@@ -83,6 +83,8 @@ def load_library(path=None):
     L.b200_tree_export.argtypes = [vp] + [vp] * 9
     L.b200_tree_set_counting.argtypes = [vp, i32]
     L.b200_tree_counters.argtypes = [vp, vp]
+    L.b200_tree_walk_stats.argtypes = [vp, vp]
+    L.b200_tree_overflowed.argtypes = [vp, C.POINTER(i32)]
     L.b200_leapfrog_dev.argtypes = [vp, vp, vp, vp, sz, i32, f32, f64, f32, f32, vp]
     L.b200_leapfrog_host.argtypes = [vp, vp, vp, vp, vp, sz, i32, f32, f64, f32, f32]
     L.b200_hubble_a.argtypes = [f64] * 5
@@ -289,6 +291,18 @@ class Engine:
         c = np.zeros(3, np.uint64)
         self._check(self.L.b200_tree_counters(self._h, _ptr(c)))
         return c
+
+    def tree_walk_stats(self):
+        """Counters of the last counting walk + lane utilisation: nodes visited, cell, pair interactions,
+        pair-row source slots issued, node-visit lanes issued, node-visit lanes awake."""
+        c = np.zeros(6, np.uint64)
+        self._check(self.L.b200_tree_walk_stats(self._h, _ptr(c)))
+        return c
+
+    def tree_overflowed(self):
+        f = C.c_int()
+        self._check(self.L.b200_tree_overflowed(self._h, C.byref(f)))
+        return bool(f.value)
 
     # -- leapfrog ------------------------------------------------------------
     def leapfrog_dev(self, posm, vel, acc, n, n_kicks, dt_kick, a, dt_drift, box, stream=None):

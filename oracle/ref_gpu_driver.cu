@@ -2,8 +2,9 @@
 //
 // A C-ABI handle on the reference's own CUDA kernels for the hot path, so that tests/ can run
 // them on the B200 next to libb200grav.so: the tiled direct sum K2 / all-pairs K3 behind
-// launch_force_computation (src/physics/lambda_cdm_kernels.cu:444-468) and the leapfrog K4
-// behind launch_leapfrog_update (:470-490).  The reference source is compiled where it lies
+// launch_force_computation (src/physics/lambda_cdm_kernels.cu:444-468), the leapfrog K4
+// behind launch_leapfrog_update (:470-490) and the energy kernel K6 behind
+// launch_energy_computation (:492-516).  The reference source is compiled where it lies
 // (oracle/Makefile target `refgpu`, flags of the reference's CMakeLists.txt:93: -O3
 // --use_fast_math --expt-relaxed-constexpr) for sm_100a into oracle/_ref/liblcdm_ref_gpu.so;
 // nothing of it is copied into this repository.  "Those recompiled kernels are the baseline"
@@ -66,6 +67,31 @@ int refgpu_leapfrog(float* posm4, float* vel3, const float* forces3, int n, floa
     cudaFree(d_pos);
     cudaFree(d_v);
     cudaFree(d_f);
+    return 0;
+}
+
+// launch_energy_computation on host arrays: kinetic and potential energy as the reference computes them
+// (one thread per particle over j > i, float partial sums, float atomics across blocks).
+int refgpu_energy(const float* posm4, const float* vel3, int n, float box, float softening, float* kinetic,
+                  float* potential) {
+    float4* d_pos = nullptr;
+    float3* d_v = nullptr;
+    float* d_e = nullptr;
+    TRY(cudaMalloc(&d_pos, (size_t)n * sizeof(float4)));
+    TRY(cudaMalloc(&d_v, (size_t)n * sizeof(float3)));
+    TRY(cudaMalloc(&d_e, 2 * sizeof(float)));
+    TRY(cudaMemcpy(d_pos, posm4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice));
+    TRY(cudaMemcpy(d_v, vel3, (size_t)n * sizeof(float3), cudaMemcpyHostToDevice));
+    physics::kernels::launch_energy_computation(d_pos, d_v, d_e, d_e + 1, n, box, softening, 0);
+    TRY(cudaDeviceSynchronize());
+    TRY(cudaGetLastError());
+    float h[2] = {0.f, 0.f};
+    TRY(cudaMemcpy(h, d_e, sizeof h, cudaMemcpyDeviceToHost));
+    *kinetic = h[0];
+    *potential = h[1];
+    cudaFree(d_pos);
+    cudaFree(d_v);
+    cudaFree(d_e);
     return 0;
 }
 

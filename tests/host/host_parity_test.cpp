@@ -209,6 +209,25 @@ int main() {
         bool inside = true;
         for (float q : xp) inside = inside && q >= 0.0f && q < 100.0f && std::isfinite(q);
         CHECK(inside && per.get_current_step() == 3, "periodic direct driver keeps particles in [0, box)");
+
+        // Tree + initialize_particles: the generated particles must sit inside the origin-centred root cube, and
+        // the forces must be the CPU tree's on those positions; a later switch to a method that works in the
+        // other frame is refused
+        physics::B200LambdaCDMSimulation tr(4096, 100.0f);
+        tr.set_force_method(physics::B200ForceMethod::Tree);
+        tr.initialize_particles(777);
+        std::vector<float> xt(3 * 4096), ft(3 * 4096), fr(3 * 4096), mt(4096, 1.0f);
+        tr.copy_positions_to_host(xt.data());
+        bool centred = true;
+        for (float q : xt) centred = centred && q >= -50.0f && q < 50.0f;
+        tr.compute_forces();
+        tr.copy_forces_to_host(ft.data());
+        cpu_tree->compute_forces(xt.data(), mt.data(), fr.data(), 4096);
+        bool refused = false;
+        try { tr.set_force_method(physics::B200ForceMethod::Direct); } catch (const std::logic_error&) { refused = true; }
+        CHECK(centred && rel_l2(ft, fr) < 1e-3 && refused,
+              "Tree + initialize_particles: particles inside the root cube, forces vs CPU tree rel-L2 %.1e, frame switch %s",
+              rel_l2(ft, fr), refused ? "refused" : "ACCEPTED");
     }
 
     std::cout.rdbuf(quiet.rdbuf());

@@ -182,3 +182,23 @@ def test_direct_full_size_properties(engine, oracle):
     # linearity in the source masses: doubling every mass doubles every acceleration
     b = engine.direct_forces_host(p, 2.0 * m)
     assert rel_l2(b[::4096], 2.0 * a[::4096]) < 1e-6
+
+
+def test_direct_full_size_unit_mass_sample(engine, oracle):
+    """The benchmarked instance itself: 2^20 particles, all masses equal (the 11-op UNIT kernel, R = 8), a
+    2048-target block against the FP64 oracle over all sources -- through the host call and through the
+    target-sharded device call bench.py times."""
+    import torch
+    n = 1 << 20
+    rng = np.random.default_rng(42)                         # bench.py's make_particles
+    p = rng.uniform(-50.0, 50.0, size=(n, 3)).astype(np.float32)
+    a = engine.direct_forces_host(p, np.ones(n, np.float32))
+    sel = slice(349184, 349184 + 2048)
+    want = oracle.direct_f64(p, None, i0=sel.start, n_targets=2048)
+    assert rel_l2(a[sel], want) < TOL
+    posm = torch.from_numpy(np.concatenate([p, np.ones((n, 1), np.float32)], 1)).cuda()
+    acc = torch.empty((n // 8, 3), dtype=torch.float32, device="cuda")
+    lo = 2 * (n // 8)                                       # rank 2 of 8
+    engine.direct_forces_dev(posm, acc, lo, n // 8, eps=0.01)
+    torch.cuda.synchronize()
+    assert rel_l2(acc.cpu().numpy(), a[lo:lo + n // 8]) < 1e-7         # the shard of rank 2 of 8 = the same rows

@@ -98,3 +98,51 @@ def test_c1_config_16k_10_steps(engine, oracle):
     po, vo, ao = oracle.kdk_run(p, v, m, lambda x: oracle.direct_f32(x, m, eps=0.01), 10, 1e-3, box=0.0)
     assert abs(sim.get_scale_factor() - ao) < 1e-12
     assert _max_dev_min_image(sim.positions(), po, 0.0) < 1e-4 * 100.0
+
+
+def test_kdk_100_steps_tree_256k(engine, oracle):
+    """North-star trajectory gate at scale ("parity run" for config 4): 100 KDK steps of the Barnes-Hut
+    path on 2^18 particles, dt = 1e-4, a: 1 -> 1.84, against the restated CPU tree (OpenMP over targets, ~1 s per
+    step); positions within 1e-4 of the box."""
+    import b200grav
+    n = 1 << 18
+    p = uniform_mt(n, seed=19)
+    rng = np.random.default_rng(20)
+    v = rng.normal(0, 100, size=(n, 3)).astype(np.float32)
+    m = np.ones(n, np.float32)
+    sim = b200grav.LambdaCDMSimulation(engine, p, v, m, box=100.0, force="tree", theta=0.5, wrap=False)
+    for _ in range(100):
+        sim.step(1e-4)
+
+    def f(x):
+        return oracle.tree_forces(oracle.tree_build(x, m), x, 0.5)
+
+    po, vo, ao = oracle.kdk_run(p, v, m, f, 100, 1e-4, box=0.0)
+    assert abs(sim.get_scale_factor() - ao) < 1e-12 and 1.8 < ao < 2.0
+    assert _max_dev_min_image(sim.positions(), po, 0.0) < 1e-4 * 100.0
+    assert rel_l2(sim.velocities(), vo) < 1e-4
+
+
+def test_kdk_100_steps_direct_16k_vs_reference(engine, oracle):
+    """BASELINE config 1's particle count, 100 KDK steps of the direct path.  CPU side: the restated pair loop on all
+    cores every step -- bitwise the reference's own (oracle/_ref = TreeForceComputer with one root leaf), which is
+    asserted here on the first and on the last positions of the run (the reference itself is single-threaded:
+    1.3 s per evaluation)."""
+    import b200grav
+    from oracle.pyoracle import Ref
+    n = 16384
+    p = uniform_mt(n, seed=42)
+    rng = np.random.default_rng(12345)
+    v = rng.normal(0, 100, size=(n, 3)).astype(np.float32)
+    m = np.ones(n, np.float32)
+    sim = b200grav.LambdaCDMSimulation(engine, p, v, m, box=100.0, force="direct", eps=0.01, wrap=False)
+    for _ in range(100):
+        sim.step(1e-4)
+    po, vo, ao = oracle.kdk_run(p, v, m, lambda x: oracle.direct_f32(x, None, eps=0.01), 100, 1e-4, box=0.0)
+    if Ref.available():
+        r = Ref()
+        for x in (p, po):
+            assert np.array_equal(r.direct(x), oracle.direct_f32(x, None, eps=0.01))
+    assert abs(sim.get_scale_factor() - ao) < 1e-12
+    assert _max_dev_min_image(sim.positions(), po, 0.0) < 1e-4 * 100.0
+    assert rel_l2(sim.velocities(), vo) < 1e-4

@@ -34,6 +34,7 @@ def refgpu():
     fp = C.POINTER(C.c_float)
     lib.refgpu_direct.argtypes = [fp, fp, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, fp]
     lib.refgpu_leapfrog.argtypes = [fp, fp, fp, C.c_int, C.c_float, C.c_float, C.c_double, C.c_int]
+    lib.refgpu_energy.argtypes = [fp, fp, C.c_int, C.c_float, C.c_float, fp, fp]
     return lib
 
 
@@ -163,3 +164,42 @@ def test_reference_gpu_kernel_speed_at_config2(engine, refgpu):
     print(json.dumps(out))
     assert err < 1e-4, err            # 2^20 sequential FP32 terms per target in the reference kernel
     assert ms_ours < ms_ref
+
+
+def _golden_gen():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_gpu", os.path.join(ROOT, "tests", "golden", "make_golden_gpu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_energy_matches_reference_gpu_golden(engine):
+    """b200_energy_dev against the committed output of the reference's own energy kernel K6
+    (launch_energy_computation, lambda_cdm_kernels.cu:492-516) on the same 10 240 particles."""
+    import torch
+    mg = _golden_gen()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_gpu_energy.npz"))
+    posm, _, _ = mg.inputs()
+    vel = torch.from_numpy(mg.energy_velocities()).cuda()
+    d = torch.from_numpy(posm).cuda()
+    for tag, box in (("periodic", mg.BOX), ("open", 0.0)):
+        ke, pe = engine.energy_dev(d, vel, eps=mg.EPS, box=box)
+        assert abs(ke - float(g["ke_" + tag])) <= 2e-5 * abs(ke)
+        assert abs(pe - float(g["pe_" + tag])) <= 1e-4 * abs(pe)
+
+
+def test_energy_matches_reference_gpu_kernel_live(engine, refgpu):
+    """The same comparison against K6 run now, on fresh inputs (20 000 particles)."""
+    import torch
+    n = 20000
+    rng = np.random.default_rng(99)
+    posm = np.empty((n, 4), np.float32)
+    posm[:, :3] = rng.uniform(0.0, 100.0, (n, 3))
+    posm[:, 3] = masses_np(n, seed=100)
+    vel = rng.normal(0.0, 100.0, (n, 3)).astype(np.float32)
+    ke_r, pe_r = np.zeros(1, np.float32), np.zeros(1, np.float32)
+    assert refgpu.refgpu_energy(_p(posm), _p(vel), n, 100.0, 0.01, _p(ke_r), _p(pe_r)) == 0
+    ke, pe = engine.energy_dev(torch.from_numpy(posm).cuda(), torch.from_numpy(vel).cuda(), eps=0.01, box=100.0)
+    assert abs(ke - float(ke_r[0])) <= 2e-5 * abs(ke)
+    assert abs(pe - float(pe_r[0])) <= 1e-4 * abs(pe)

@@ -39,3 +39,17 @@ def test_oracle_leapfrog_matches_reference_gpu_kernel(oracle):
     d = np.abs(po - g["drift_pos"])
     assert np.minimum(d, mg.BOX - d).max() <= 2e-5              # 2 ulp at 100
     assert g["drift_pos"].min() >= 0.0 and g["drift_pos"].max() < mg.BOX
+
+
+def test_oracle_energy_matches_reference_gpu_kernel(oracle):
+    """K6 compute_energy behind launch_energy_computation (lambda_cdm_kernels.cu:338-408, 492-516), run on a B200:
+    float pair terms, float per-thread sums over up to 10 239 partners, float atomics across blocks -- the restated
+    energy (FP64 sums) agrees to the reference's own round-off."""
+    mg, g = _gen(), golden("ref_gpu_energy.npz")
+    posm, _, _ = mg.inputs()
+    vel = mg.energy_velocities()
+    pos, mass = posm[:, :3].copy(), posm[:, 3].copy()
+    for tag, box in (("periodic", mg.BOX), ("open", 0.0)):
+        ke, pe = oracle.energy(pos, vel, mass, mg.EPS, box)
+        assert abs(ke - float(g["ke_" + tag])) <= 2e-5 * abs(ke)
+        assert abs(pe - float(g["pe_" + tag])) <= 1e-4 * abs(pe)
