@@ -549,13 +549,14 @@ def leapfrog_roofline(eng, D, n, reps=10):
         eng.leapfrog_dev(posm, vel, acc, n, 2, np.float32(5e-5), 1.0, np.float32(1e-4), 0.0)
     torch.cuda.synchronize()
     ms = []
-    for _ in range(reps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(reps):            # 4 launches back to back per event pair: the ~5 us of event + launch overhead
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)      # would be 3 % of one
         e0.record()
-        eng.leapfrog_dev(posm, vel, acc, n, 2, np.float32(5e-5), 1.0, np.float32(1e-4), 0.0)
+        for _ in range(4):
+            eng.leapfrog_dev(posm, vel, acc, n, 2, np.float32(5e-5), 1.0, np.float32(1e-4), 0.0)
         e1.record()
         torch.cuda.synchronize()
-        ms.append(e0.elapsed_time(e1))
+        ms.append(e0.elapsed_time(e1) / 4)
     t = float(np.mean(ms)) * 1e-3
     peak, src = hbm_peak()
     gbs = 68.0 * n / t / 1e9

@@ -164,6 +164,34 @@ int shard_allgather(b200_ctx* ctx, void* posm4_full, size_t n_total, cudaStream_
     return B200_OK;
 }
 
+// Raw byte collectives for the tree-table exchange (tree.cu): every rank contributes `bytes` bytes.
+int shard_allgather_bytes(b200_ctx* ctx, const void* send, void* recv, size_t bytes, cudaStream_t st) {
+    ShardState* s = ctx->shard;
+    if (!s || s->world == 1) return B200_ERR_STATE;
+    const NcclApi* api = nccl();
+    if (!api) return B200_ERR_UNSUPPORTED;
+    B200_NCCL(api->AllGather(send, recv, bytes, ncclChar, s->comm, st));
+    return B200_OK;
+}
+
+// `count` broadcasts in one NCCL group: item i goes from send[i] on rank root[i] to recv[i] on every rank
+// (send[i] is read on the root only; the root's recv[i] receives a copy as well).
+int shard_bcast_group(b200_ctx* ctx, int count, const void* const* send, void* const* recv, const size_t* bytes,
+                      const int* root, cudaStream_t st) {
+    ShardState* s = ctx->shard;
+    if (!s || s->world == 1) return B200_ERR_STATE;
+    const NcclApi* api = nccl();
+    if (!api) return B200_ERR_UNSUPPORTED;
+    B200_NCCL(api->GroupStart());
+    for (int i = 0; i < count; ++i) {
+        if (bytes[i] == 0) continue;
+        ncclResult_t e = api->Broadcast(send[i], recv[i], bytes[i], ncclChar, root[i], s->comm, st);
+        if (e != ncclSuccess) { api->GroupEnd(); return 2000 + (int)e; }
+    }
+    B200_NCCL(api->GroupEnd());
+    return B200_OK;
+}
+
 // Sum `count` host doubles over the ranks (diagnostics: energies).  Blocking.
 int shard_allreduce_f64(b200_ctx* ctx, double* values, size_t count) {
     ShardState* s = ctx->shard;

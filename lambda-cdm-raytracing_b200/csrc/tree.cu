@@ -33,6 +33,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "shard.cuh"
 #include "sort.cuh"
 #include "tree.cuh"
 
@@ -89,10 +90,23 @@ struct TreeState {
     size_t graph_key = 0;
     int graph_launches = 0;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    // Part build (octant-sharded octree): this tree holds the root, its 8 children and the subtrees of the
+    // octants in oct_mask only; the other octants are empty leaves.  The walk tables of all parts make a FOREST.
+    int part = 0, n_parts = 1;
+    unsigned oct_mask = 0xffu;
+    struct ForestSlot {
+        DevBuf nodes, leaf_off, leaf_pairs;
+        size_t nn = 0, npairs = 0;
+        bool valid = false;
+    } forest[8];
+    DevBuf forest_root;           // {global centre of mass, M} {-, -, root edge, -}
+    DevBuf forest_hdr;            // device: int2 {nodes, source pairs} per part
+    int* forest_hdr_host = nullptr;   // pinned mirror
     size_t fingerprint() const {
         size_t h = 1469598103934665603ull;
         auto mix = [&h](size_t v) { h = (h ^ v) * 1099511628211ull; };
         mix((size_t)posm); mix(n); mix((size_t)cap); mix((size_t)max_depth); mix(fixed ? 1 : 0);
+        mix((size_t)oct_mask); mix((size_t)forest_hdr.p);
         unsigned bb, eb;
         memcpy(&bb, &box, 4); memcpy(&eb, &eps, 4);
         mix(bb); mix(eb);
@@ -110,6 +124,10 @@ struct TreeState {
     }
     void release() {
         drop_graph();
+        for (ForestSlot& f : forest) { f.nodes.release(); f.leaf_off.release(); f.leaf_pairs.release(); f.valid = false; }
+        forest_root.release(); forest_hdr.release();
+        if (forest_hdr_host) cudaFreeHost(forest_hdr_host);
+        forest_hdr_host = nullptr;
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_out) cudaEventDestroy(ev_out);
         ev_in = ev_out = nullptr;
@@ -361,7 +379,7 @@ __device__ __forceinline__ unsigned digit_mask(unsigned bv, unsigned b0, unsigne
 }
 
 __global__ void __launch_bounds__(ET_THREADS)
-entry_digit_kernel(const TreeGlobals* __restrict__ g, int level, int keep,
+entry_digit_kernel(const TreeGlobals* __restrict__ g, int level, int keep, unsigned oct_mask,
                    const float4* __restrict__ posm, const float4* __restrict__ center,
                    const int4* __restrict__ meta, const int* __restrict__ nstart,
                    const int* __restrict__ nsplit_rank, const int* __restrict__ ent_idx,
@@ -396,6 +414,9 @@ entry_digit_kernel(const TreeGlobals* __restrict__ g, int level, int keep,
                     const float4 x = posm[idx];
                     d = (x.x > c.x ? 1 : 0) | (x.y > c.y ? 2 : 0) | (x.z > c.z ? 4 : 0);   // :188-194
                     if (rel == keep) { first_live = true; sr = nsplit_rank[k]; }
+                    // part build: a particle bound for an octant another part owns leaves the build here (the
+                    // root's child of that octant stays an empty leaf in this part's tree)
+                    if (level == 0 && !((oct_mask >> d) & 1u)) d = 8;
                 }
                 digit[p] = (unsigned char)d;
             }
@@ -599,12 +620,13 @@ __device__ __forceinline__ int tree_node_count(const TreeGlobals* g, int max_dep
 // parent are contiguous and PAIR-INTERLEAVED, pair p = {x0 x1 y0 y1} {z0 z1 w0 w1}, so that one
 // packed-FP32 instruction of the walk handles two sources (lscan: rank of a leaf's first particle
 // among all leaf particles; pscan: first pair of a sibling group).
-__global__ void stored_pos_kernel(const int* __restrict__ part_idx, const int* __restrict__ slot_node,
+__global__ void stored_pos_kernel(const TreeGlobals* __restrict__ g, const int* __restrict__ part_idx,
+                                  const int* __restrict__ slot_node,
                                   const int4* __restrict__ meta, const int* __restrict__ lscan,
                                   const int* __restrict__ pscan, const float4* __restrict__ posm, int n,
                                   float4* __restrict__ part_pos, float* __restrict__ leaf_pairs, int fixed) {
     int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
+    if (q >= n || q >= g->stored_total) return;            // a part build stores only its octants' particles
     const int idx = part_idx[q];
     float4 p = posm[idx];
     if (!fixed) p.w = __int_as_float(idx);
@@ -841,11 +863,17 @@ constexpr int ROOT_LEAF = -2;
 __global__ void __launch_bounds__(256)
 pack_walk_kernel(const TreeGlobals* __restrict__ g, int max_depth, const float4* __restrict__ com,
                  const int4* __restrict__ meta, const int* __restrict__ lscan, const int* __restrict__ pscan,
-                 float4* __restrict__ nodes, int* __restrict__ leaf_off) {
+                 float4* __restrict__ nodes, int* __restrict__ leaf_off, int* __restrict__ hdr) {
     const int nn = tree_node_count(g, max_depth);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nn; k += gridDim.x * blockDim.x) {
         const int4 m = meta[k];
-        if (m.x < 0 && k != 0) continue;
+        if (m.x < 0 && k != 0) {
+            if (k <= 8) {                            // the root's children: the forest's root record is merged from these
+                nodes[2 * k] = com[k];
+                nodes[2 * k + 1] = make_float4(__int_as_float(-1), __int_as_float(-1), 0.f, 0.f);
+            }
+            continue;
+        }
         int first, skip = -1, loff, lcnt;
         // the walk visits internal nodes that carry mass; everything else is stepped over here, once
         auto stepped_over = [&](int j) { return meta[j].x < 0 || com[j].w == 0.0f; };     // leaf, or :260
@@ -864,6 +892,36 @@ pack_walk_kernel(const TreeGlobals* __restrict__ g, int max_depth, const float4*
                                        __int_as_float(lcnt));      // m.w of an internal node = cell edge bits
         leaf_off[k] = loff;
     }
+    if (hdr && blockIdx.x == 0 && threadIdx.x == 0) {       // sizes of this part's walk tables
+        hdr[0] = nn;
+        hdr[1] = nn > 1 ? pscan[(nn - 1) / 8] : (lscan[1] + 1) / 2;
+    }
+}
+
+// Global root of a forest: its centre of mass from the 8 level-1 records of the owning parts, in the order and
+// rounding of compute_center_of_mass (:226-241, children 0..7 with M > 0) -- the value the unsharded build gives.
+struct ForestTables {
+    const float4* nodes[8];
+    const int* leaf_off[8];
+    const ulonglong2* leaf_pairs[8];
+    int owner[8];                 // part that owns octant d
+    int n_parts;
+};
+__global__ void forest_root_kernel(ForestTables F, float4* __restrict__ root) {
+    float total = 0.f, wx = 0.f, wy = 0.f, wz = 0.f;
+    for (int d = 0; d < 8; ++d) {
+        const float4 c = F.nodes[F.owner[d]][2 * (1 + d)];
+        if (c.w > 0.f) {
+            total = __fadd_rn(total, c.w);
+            wx = __fadd_rn(wx, __fmul_rn(c.x, c.w));
+            wy = __fadd_rn(wy, __fmul_rn(c.y, c.w));
+            wz = __fadd_rn(wz, __fmul_rn(c.z, c.w));
+        }
+    }
+    float4 o = make_float4(0.f, 0.f, 0.f, total);
+    if (total > 0.f) { o.x = __fdiv_rn(wx, total); o.y = __fdiv_rn(wy, total); o.z = __fdiv_rn(wz, total); }
+    root[0] = o;
+    root[1] = F.nodes[0][1];      // every part's root record carries the same cell edge
 }
 
 // ------------------------------------------------------------------ walk ---
@@ -1024,12 +1082,19 @@ __device__ __forceinline__ void ld256(const ulonglong2* p, ulonglong2& a, ulongl
     asm("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a.x), "=l"(a.y), "=l"(b.x), "=l"(b.y) : "l"(p));
 }
 
-template <bool COUNT, bool FIXED, bool PERIODIC = false, bool POT = false>
+// FOREST: the octree arrives as the walk tables of several part builds (octant-sharded build: each part holds
+// the subtrees of its own octants of the root, the other octants are empty leaves there) plus one merged root
+// record.  A target tests the root once, then walks part after part -- octant order, i.e. the depth-first order
+// of the whole tree -- with the same loop; node ids are local to a part's table.
+// by_slot: acc3 is indexed by the target's position in `order` (an explicit target list), not by index - i0.
+template <bool COUNT, bool FIXED, bool PERIODIC = false, bool POT = false, bool FOREST = false>
 __global__ void __launch_bounds__(128, 10)
 walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order, int i0, int n_targets,
                  const float4* __restrict__ nodes, const int* __restrict__ leaf_off,
                  const ulonglong2* __restrict__ leaf_pairs, float theta, float theta2, float eps2, float box,
-                 float* __restrict__ acc3, TreeGlobals* __restrict__ g) {
+                 float* __restrict__ acc3, TreeGlobals* __restrict__ g,
+                 const ForestTables* __restrict__ forest = nullptr, const float4* __restrict__ forest_root = nullptr,
+                 int by_slot = 0) {
     typedef unsigned long long u64;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = t < n_targets;
@@ -1058,7 +1123,7 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
     // `cnt` leaf particles stored as pairs from pair `q` on, against this lane's target; on_lane = the
     // lane takes part.  Branch-free packed rows: a lane that is out, or is the particle itself (:321), or a
     // padding slot, adds f = 0.
-    auto leaf_range = [&](int q, int cnt, bool on_lane) {
+    auto leaf_range = [&](const ulonglong2* __restrict__ pairs, int q, int cnt, bool on_lane) {
         // A lane that is out takes eps^2 = +inf: rsqrt gives exactly 0 and every row adds 0 -- no select per row.
         // The particle itself (:321) needs no test either: d = 0 makes its term exactly 0 (eps > 0); the index in
         // .w is compared only when the interactions are being counted.  Padding slots are parked far away.
@@ -1093,7 +1158,7 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
             }
         };
         if (COUNT && FIXED && on_lane) c_pp += cnt;
-        const ulonglong2* src = leaf_pairs + 2 * (size_t)q;
+        const ulonglong2* src = pairs + 2 * (size_t)q;
         const int np = (cnt + 1) >> 1;
         int k2 = 0;
         for (; k2 + 2 <= np; k2 += 2) {                  // 2 broadcast 256-bit loads in flight, then 2 packed rows
@@ -1115,60 +1180,95 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
         if (valid) {
             const float nan = __int_as_float(0x7fc00000);
             if (POT) acc3[i - i0] = nan;
-            else { const size_t o = (size_t)(i - i0) * 3; acc3[o] = acc3[o + 1] = acc3[o + 2] = nan; }
+            else { const size_t o = (size_t)(by_slot ? t : i - i0) * 3; acc3[o] = acc3[o + 1] = acc3[o + 2] = nan; }
         }
         return;
     }
-    // the root: massless -> nothing to do (:260); a leaf -> one pair loop (:268-270).  Every node the
-    // links lead to after that is internal and carries mass (pack_walk_kernel).
-    int k = 0;
-    {
-        const float4 c = nodes[0];
-        const float4 mf = nodes[1];
-        if (c.w == 0.0f) k = -1;
-        else if (__float_as_int(mf.x) == ROOT_LEAF) { leaf_range(0, __float_as_int(mf.w), valid); k = -1; }
-    }
-    while (k >= 0) {
-        if (wake == k) wake = AWAKE;
-        const bool active = (wake == AWAKE);
-        if (COUNT) { c_nl += 1; c_na += active; }
-        float4 c, mf;            // {centre of mass, M} {first | skip | cell edge | leaf-child particles}
-        ld256(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nodes) + (size_t)(unsigned)k * 32), c, mf);
-        const int first = __float_as_int(mf.x), skip = __float_as_int(mf.y), lcnt = __float_as_int(mf.w);
-        // Branch-free: every lane runs the test and the monopole; a lane that sleeps or opens the cell takes
-        // 1/r = 0, so its term is exactly 0.
-        float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
-        if constexpr (PERIODIC) {
-            dx = __fsub_rn(dx, __fmul_rn(box, roundf(__fdiv_rn(dx, box))));
-            dy = __fsub_rn(dy, __fmul_rn(box, roundf(__fdiv_rn(dy, box))));
-            dz = __fsub_rn(dz, __fmul_rn(box, roundf(__fdiv_rn(dz, box))));
-        }
-        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        bool wraps = false;          // periodic: a cell reaching across the half-box distance is never a monopole
-        if constexpr (PERIODIC) {
-            const float hb = __fmul_rn(box, 0.5f);
-            wraps = __fadd_rn(fabsf(dx), mf.z) > hb || __fadd_rn(fabsf(dy), mf.z) > hb || __fadd_rn(fabsf(dz), mf.z) > hb;
-        }
-        const bool accept = !wraps && accept_cell_d(mf.z, dx, dy, dz, d2, theta, theta2);      // :309
-        const bool take = active && accept;
-        const bool open = active && !accept;
-        {
-            const float rinv = take ? rsqrt_fast(d2 + eps2) : 0.0f;
-            if constexpr (POT) {
-                ax = fmaf(c.w, rinv, ax);
-            } else {
-                const float f = c.w * rinv * rinv * rinv;                // :280-290
-                ax = fmaf(f, dx, ax); ay = fmaf(f, dy, ay); az = fmaf(f, dz, az);
+    // One table: every node the links lead to is internal and carries mass (pack_walk_kernel).
+    auto walk_table = [&](const float4* __restrict__ nd, const int* __restrict__ loff,
+                          const ulonglong2* __restrict__ pairs, int k) {
+        while (k >= 0) {
+            if (wake == k) wake = AWAKE;
+            const bool active = (wake == AWAKE);
+            if (COUNT) { c_nl += 1; c_na += active; }
+            float4 c, mf;            // {centre of mass, M} {first | skip | cell edge | leaf-child particles}
+            ld256(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nd) + (size_t)(unsigned)k * 32), c, mf);
+            const int first = __float_as_int(mf.x), skip = __float_as_int(mf.y), lcnt = __float_as_int(mf.w);
+            // Branch-free: every lane runs the test and the monopole; a lane that sleeps or opens the cell takes
+            // 1/r = 0, so its term is exactly 0.
+            float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
+            if constexpr (PERIODIC) {
+                dx = __fsub_rn(dx, __fmul_rn(box, roundf(__fdiv_rn(dx, box))));
+                dy = __fsub_rn(dy, __fmul_rn(box, roundf(__fdiv_rn(dy, box))));
+                dz = __fsub_rn(dz, __fmul_rn(box, roundf(__fdiv_rn(dz, box))));
             }
-            if (COUNT) c_pc += take;
-            if (take) wake = skip;                                       // sleep through this subtree
+            const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            bool wraps = false;          // periodic: a cell reaching across the half-box distance is never a monopole
+            if constexpr (PERIODIC) {
+                const float hb = __fmul_rn(box, 0.5f);
+                wraps = __fadd_rn(fabsf(dx), mf.z) > hb || __fadd_rn(fabsf(dy), mf.z) > hb || __fadd_rn(fabsf(dz), mf.z) > hb;
+            }
+            const bool accept = !wraps && accept_cell_d(mf.z, dx, dy, dz, d2, theta, theta2);      // :309
+            const bool take = active && accept;
+            const bool open = active && !accept;
+            {
+                const float rinv = take ? rsqrt_fast(d2 + eps2) : 0.0f;
+                if constexpr (POT) {
+                    ax = fmaf(c.w, rinv, ax);
+                } else {
+                    const float f = c.w * rinv * rinv * rinv;                // :280-290
+                    ax = fmaf(f, dx, ax); ay = fmaf(f, dy, ay); az = fmaf(f, dz, az);
+                }
+                if (COUNT) c_pc += take;
+                if (take) wake = skip;                                       // sleep through this subtree
+            }
+            if (__any_sync(FULL, open)) {                                    // :293-297
+                if (COUNT && open) c_vis += 8;                               // its 8 children, leaves included
+                if (lcnt > 0) leaf_range(pairs, loff[k], lcnt, open);
+                k = first;
+            } else {
+                k = skip;
+            }
         }
-        if (__any_sync(FULL, open)) {                                    // :293-297
-            if (COUNT && open) c_vis += 8;                               // its 8 children, leaves included
-            if (lcnt > 0) leaf_range(leaf_off[k], lcnt, open);
-            k = first;
-        } else {
-            k = skip;
+    };
+    if constexpr (!FOREST) {
+        // the root: massless -> nothing to do (:260); a leaf -> one pair loop (:268-270)
+        int k = 0;
+        {
+            const float4 c = nodes[0];
+            const float4 mf = nodes[1];
+            if (c.w == 0.0f) k = -1;
+            else if (__float_as_int(mf.x) == ROOT_LEAF) { leaf_range(leaf_pairs, 0, __float_as_int(mf.w), valid); k = -1; }
+        }
+        walk_table(nodes, leaf_off, leaf_pairs, k);
+    } else {
+        // the merged root: one accept test per target (:257-300 at depth 0), then part after part
+        const float4 c = forest_root[0], mf = forest_root[1];
+        if (c.w != 0.0f) {                                                   // :260
+            if (COUNT) { c_nl += 1; c_na += valid; }
+            const float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
+            const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const bool accept = accept_cell_d(mf.z, dx, dy, dz, d2, theta, theta2);
+            const bool take = valid && accept, open = valid && !accept;
+            const float rinv = take ? rsqrt_fast(d2 + eps2) : 0.0f;
+            const float f = c.w * rinv * rinv * rinv;
+            ax = fmaf(f, dx, ax); ay = fmaf(f, dy, ay); az = fmaf(f, dz, az);
+            if (COUNT) c_pc += take;
+            if (take) wake = NEVER;                                          // the whole tree is one monopole for this target
+            if (__any_sync(FULL, open)) {
+                if (COUNT && open) c_vis += 8;
+                const int n_parts = forest->n_parts;
+                for (int q = 0; q < n_parts; ++q) {
+                    const float4* nd = forest->nodes[q];
+                    const int* loff = forest->leaf_off[q];
+                    const ulonglong2* pairs = forest->leaf_pairs[q];
+                    const float4 r1 = nd[1];                                 // this part's root record: its own octants
+                    if (wake != NEVER) wake = AWAKE;                         // a lane sleeping to the end of a part wakes here
+                    const int lcnt = __float_as_int(r1.w);
+                    if (lcnt > 0) leaf_range(pairs, loff[0], lcnt, open);    // root children that are leaves
+                    walk_table(nd, loff, pairs, __float_as_int(r1.x));
+                }
+            }
         }
     }
     if (valid) {
@@ -1179,7 +1279,7 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
         } else {
             w_unpk(ay2, lo, hi); ay += lo + hi;
             w_unpk(az2, lo, hi); az += lo + hi;
-            const size_t o = (size_t)(i - i0) * 3;
+            const size_t o = (size_t)(by_slot ? t : i - i0) * 3;
             acc3[o + 0] = ax; acc3[o + 1] = ay; acc3[o + 2] = az;
         }
     }
@@ -1231,8 +1331,30 @@ void tree_destroy(b200_ctx* ctx) {
 
 static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st);
 
+static int tree_build_impl(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_cap, int max_depth,
+                           bool fixed, float eps, int part, int n_parts, cudaStream_t st);
+
 int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_cap, int max_depth,
                bool fixed, float eps, cudaStream_t st) {
+    return tree_build_impl(ctx, posm4, n, box, leaf_cap, max_depth, fixed, eps, 0, 1, st);
+}
+
+// Octants [part * 8 / n_parts, (part + 1) * 8 / n_parts) of the root belong to part `part`.
+static unsigned part_octants(int part, int n_parts) {
+    unsigned m = 0;
+    for (int d = part * 8 / n_parts; d < (part + 1) * 8 / n_parts; ++d) m |= 1u << d;
+    return m;
+}
+
+int tree_build_part(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_cap, int max_depth, int part,
+                    int n_parts, cudaStream_t st) {
+    if (n_parts < 1 || n_parts > 8 || part < 0 || part >= n_parts) return B200_ERR_INVALID;
+    if (n <= (size_t)leaf_cap) return B200_ERR_UNSUPPORTED;      // the root does not split: nothing to shard
+    return tree_build_impl(ctx, posm4, n, box, leaf_cap, max_depth, false, 0.01f, part, n_parts, st);
+}
+
+static int tree_build_impl(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_cap, int max_depth,
+                           bool fixed, float eps, int part, int n_parts, cudaStream_t st) {
     if (!posm4 || n == 0) return B200_ERR_INVALID;
     if (fixed ? !(eps > 0.f) : !(box > 0.f)) return B200_ERR_INVALID;
     if (leaf_cap < 1 || max_depth < 0 || max_depth > MAX_LEVELS - 2) return B200_ERR_UNSUPPORTED;
@@ -1246,6 +1368,15 @@ int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_c
     T->fixed = fixed;
     T->eps = fixed ? eps : 0.01f;
     T->posm = (const float4*)posm4;
+    T->part = part; T->n_parts = n_parts;
+    T->oct_mask = n_parts > 1 ? part_octants(part, n_parts) : 0xffu;
+    if (n_parts > 1) {
+        B200_TRY(T->forest_hdr.reserve(8 * 2 * sizeof(int)));
+        // every rank of a communicator rebuilds its part in the same step: all slots go stale together; a
+        // single process playing all parts (tests) replaces them one at a time
+        if (ctx->shard != nullptr) for (auto& f : T->forest) f.valid = false;
+        T->forest[part].valid = false;
+    }
     // reference tree: every internal node keeps exactly leaf_cap particles => at most n/leaf_cap
     // internal nodes.  Fixed tree: internal nodes of one level hold disjoint sets of > leaf_cap
     // particles, typically ~n/(3 leaf_cap) in all; room for n/2 (deep chains under close pairs) --
@@ -1370,7 +1501,7 @@ static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st) {
         node_apply_kernel<<<ngrid, 256, 0, st>>>(g, L, leaf_cap, keep, max_depth, ncount, T->node_tile_sum.as<u64>(),
                                                  meta, nsr, T->split_node.as<int>());
         entry_digit_kernel<<<egrid, ET_THREADS, 0, st>>>(
-            g, L, keep, T->posm, center, meta, nstart, nsr, T->ent_idx[cur].as<int>(),
+            g, L, keep, T->oct_mask, T->posm, center, meta, nstart, nsr, T->ent_idx[cur].as<int>(),
             T->ent_node[cur].as<int>(), T->digit.as<unsigned char>(), T->part_idx.as<int>(),
             T->slot_node.as<int>(), T->tile_hist.as<unsigned>(), T->tile_warp_prefix.as<unsigned>(), T->split_where.as<int>(),
             T->split_local.as<unsigned>());
@@ -1404,11 +1535,12 @@ static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st) {
     leaf_scan_kernel<1><<<1, 1024, 0, st>>>(g, max_depth, tsum);
     leaf_apply_kernel<1><<<pgrid, 256, 0, st>>>(g, max_depth, meta, lscan, tsum, pscan);
     stored_pos_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-        T->part_idx.as<int>(), T->slot_node.as<int>(), meta, lscan, pscan, T->posm, (int)n,
+        g, T->part_idx.as<int>(), T->slot_node.as<int>(), meta, lscan, pscan, T->posm, (int)n,
         T->part_pos.as<float4>(), T->leaf_pos.as<float>(), fixed ? 1 : 0);
     pair_pad_kernel<<<pgrid, 256, 0, st>>>(g, max_depth, lscan, pscan, T->leaf_pos.as<float>(), fixed ? 1 : 0);
     pack_walk_kernel<<<pgrid, 256, 0, st>>>(g, max_depth, com, meta, lscan, pscan, T->nodes.as<float4>(),
-                                            T->leaf_off.as<int>());
+                                            T->leaf_off.as<int>(),
+                                            T->forest_hdr.p ? T->forest_hdr.as<int>() + 2 * T->part : nullptr);
     ctx->launches += 9;
     B200_CUDA(cudaGetLastError());
     return B200_OK;
@@ -1440,12 +1572,28 @@ static int tree_target_order(b200_ctx* ctx, TreeState* T, size_t i0, size_t n_ta
     return B200_OK;
 }
 
-int tree_walk(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* acc3, cudaStream_t st) {
+// Targets: the index range [i0, i0 + n_targets) (list == nullptr; warps are formed from a Hilbert order of the
+// range computed here; acc3 indexed by index - i0) or an explicit list of particle indices (warps = runs of 32
+// list entries, acc3 in list order).  forest: walk the published forest of part builds, else this context's tree.
+static int tree_walk_impl(b200_ctx* ctx, const int* list, size_t i0, size_t n_targets, float theta, void* acc3,
+                          bool forest, cudaStream_t st) {
     TreeState* T = ctx->tree;
     if (!T || !T->built) return B200_ERR_STATE;
     if (n_targets == 0) return B200_OK;
-    if (!acc3 || i0 + n_targets > T->n) return B200_ERR_INVALID;
-    B200_TRY(tree_target_order(ctx, T, i0, n_targets, st));
+    if (!acc3 || (!list && i0 + n_targets > T->n)) return B200_ERR_INVALID;
+    if (forest) {
+        if (T->fixed || T->n_parts < 2) return B200_ERR_STATE;
+        for (int q = 0; q < T->n_parts; ++q)
+            if (!T->forest[q].valid) return B200_ERR_STATE;               // a part has not been published since its rebuild
+    } else if (T->n_parts > 1) {
+        return B200_ERR_STATE;                                            // a part build alone is not the whole tree
+    }
+    const int* order = list;
+    if (!list) {
+        B200_TRY(tree_target_order(ctx, T, i0, n_targets, st));
+        order = T->order.as<int>();
+    }
+    const int by_slot = list ? 1 : 0;
     TreeGlobals* g = T->globals.as<TreeGlobals>();
     const unsigned grid = (unsigned)((n_targets + 127) / 128);
     if (T->counting) {
@@ -1453,32 +1601,130 @@ int tree_walk(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* acc
         ctx->launches += 1;
     }
     if (ctx->timing) B200_CUDA(cudaEventRecord(ctx->ev0, st));
-    const bool per_thread = !T->fixed && getenv("B200_WALK_PER_THREAD") != nullptr;     // tuning hook
+    const bool per_thread = !T->fixed && !forest && !list && getenv("B200_WALK_PER_THREAD") != nullptr;     // tuning hook
     const float theta2 = theta > 0.f ? theta * theta : 0.f;
     const float eps2 = T->fixed ? T->eps * T->eps : 0.01f * 0.01f;
-    // one launch macro for the warp walk's instances: <COUNT, FIXED, PERIODIC>
-#define B200_WALK(COUNT_, FIXED_, PERIODIC_)                                                                     \
-    walk_warp_kernel<COUNT_, FIXED_, PERIODIC_><<<grid, 128, 0, st>>>(                                           \
-        T->posm, T->order.as<int>(), (int)i0, (int)n_targets, T->nodes.as<float4>(), T->leaf_off.as<int>(),      \
-        T->leaf_pos.as<ulonglong2>(), theta, theta2, eps2, T->periodic_box, (float*)acc3, g)
-    if (T->fixed) {
+    // one launch macro for the warp walk's instances: <COUNT, FIXED, PERIODIC, POT, FOREST>
+#define B200_WALK(COUNT_, FIXED_, PERIODIC_, FOREST_)                                                            \
+    walk_warp_kernel<COUNT_, FIXED_, PERIODIC_, false, FOREST_><<<grid, 128, 0, st>>>(                           \
+        T->posm, order, (int)i0, (int)n_targets, T->nodes.as<float4>(), T->leaf_off.as<int>(),                   \
+        T->leaf_pos.as<ulonglong2>(), theta, theta2, eps2, T->periodic_box, (float*)acc3, g,                     \
+        T->forest_root.as<ForestTables>() ? (const ForestTables*)(T->forest_root.as<char>() + 64) : nullptr,     \
+        T->forest_root.as<float4>(), by_slot)
+    if (forest) {
+        if (T->counting) B200_WALK(true, false, false, true); else B200_WALK(false, false, false, true);
+    } else if (T->fixed) {
         const bool periodic = T->periodic_box > 0.f;
-        if (T->counting) { if (periodic) B200_WALK(true, true, true); else B200_WALK(true, true, false); }
-        else             { if (periodic) B200_WALK(false, true, true); else B200_WALK(false, true, false); }
+        if (T->counting) { if (periodic) B200_WALK(true, true, true, false); else B200_WALK(true, true, false, false); }
+        else             { if (periodic) B200_WALK(false, true, true, false); else B200_WALK(false, true, false, false); }
     } else if (!per_thread) {
-        if (T->counting) B200_WALK(true, false, false); else B200_WALK(false, false, false);
+        if (T->counting) B200_WALK(true, false, false, false); else B200_WALK(false, false, false, false);
 #undef B200_WALK
     } else if (T->counting)
-        walk_kernel<true><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
+        walk_kernel<true><<<grid, 128, 0, st>>>(T->posm, order, (int)i0, (int)n_targets,
                                                 T->com.as<float4>(), T->center.as<float4>(), T->meta.as<int4>(),
                                                 T->part_pos.as<float4>(), theta, (float*)acc3, g);
     else
-        walk_kernel<false><<<grid, 128, 0, st>>>(T->posm, T->order.as<int>(), (int)i0, (int)n_targets,
+        walk_kernel<false><<<grid, 128, 0, st>>>(T->posm, order, (int)i0, (int)n_targets,
                                                  T->com.as<float4>(), T->center.as<float4>(), T->meta.as<int4>(),
                                                  T->part_pos.as<float4>(), theta, (float*)acc3, g);
     if (ctx->timing) B200_CUDA(cudaEventRecord(ctx->ev1, st));
     B200_CUDA(cudaGetLastError());
     ctx->launches += 1;
+    return B200_OK;
+}
+
+int tree_walk(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* acc3, cudaStream_t st) {
+    return tree_walk_impl(ctx, nullptr, i0, n_targets, theta, acc3, false, st);
+}
+
+int tree_walk_list(b200_ctx* ctx, const int* list, size_t n_list, float theta, void* acc3, int forest, cudaStream_t st) {
+    if (n_list && !list) return B200_ERR_INVALID;
+    return tree_walk_impl(ctx, list, 0, n_list, theta, acc3, forest != 0, st);
+}
+
+// ---- forest of part builds -------------------------------------------------------------------
+namespace {
+__global__ void set_forest_kernel(ForestTables F, ForestTables* dst) { *dst = F; }
+}
+
+// Makes this part's walk tables (node records, leaf offsets, leaf source pairs) available to every walker:
+// with a communicator of n_parts ranks (b200_shard_init) the parts exchange their tables over NCCL -- sizes first
+// (one 8-byte all-gather and a host read-back), then one grouped broadcast per table and owner; without one (a
+// single process building the parts one after another) the tables are copied into this context's slot.
+// When all slots are current the merged root record and the table directory are written.
+int tree_forest_publish(b200_ctx* ctx, cudaStream_t st) {
+    TreeState* T = ctx->tree;
+    if (!T || !T->built || T->n_parts < 2 || T->fixed) return B200_ERR_STATE;
+    const int P = T->n_parts, part = T->part;
+    int rank = 0, world = 1;
+    shard_info(ctx, &rank, &world);
+    const bool collective = ctx->shard != nullptr && world > 1;
+    if (collective && (world != P || rank != part)) return B200_ERR_STATE;
+    if (!T->forest_hdr_host) B200_CUDA(cudaMallocHost((void**)&T->forest_hdr_host, 16 * sizeof(int)));
+    int* hdr = T->forest_hdr.as<int>();
+    if (collective) B200_TRY(shard_allgather_bytes(ctx, hdr + 2 * part, hdr, 2 * sizeof(int), st));
+    B200_CUDA(cudaMemcpyAsync(T->forest_hdr_host, hdr, 16 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    {
+        TreeGlobals* g = T->globals.as<TreeGlobals>();
+        int err = 0;
+        B200_CUDA(cudaMemcpy(&err, &g->error, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err) return B200_ERR_NOMEM;
+    }
+    const void* send[24]; void* recv[24]; size_t bytes[24]; int root[24];
+    int items = 0;
+    for (int q = 0; q < P; ++q) {
+        if (!collective && q != part) continue;
+        TreeState::ForestSlot& f = T->forest[q];
+        f.nn = (size_t)T->forest_hdr_host[2 * q];
+        f.npairs = (size_t)T->forest_hdr_host[2 * q + 1];
+        if (f.nn < 9) return B200_ERR_STATE;
+        B200_TRY(f.nodes.reserve(f.nn * 2 * sizeof(float4)));
+        B200_TRY(f.leaf_off.reserve(f.nn * sizeof(int)));
+        B200_TRY(f.leaf_pairs.reserve((f.npairs + 1) * 2 * sizeof(float4)));
+        const void* src[3] = {T->nodes.p, T->leaf_off.p, T->leaf_pos.p};
+        void* dst[3] = {f.nodes.p, f.leaf_off.p, f.leaf_pairs.p};
+        const size_t sz[3] = {f.nn * 2 * sizeof(float4), f.nn * sizeof(int), f.npairs * 2 * sizeof(float4)};
+        for (int k = 0; k < 3; ++k) { send[items] = src[k]; recv[items] = dst[k]; bytes[items] = sz[k]; root[items] = q; ++items; }
+    }
+    if (collective) {
+        B200_TRY(shard_bcast_group(ctx, items, send, recv, bytes, root, st));
+        for (int q = 0; q < P; ++q) T->forest[q].valid = true;
+    } else {
+        for (int k = 0; k < items; ++k)
+            if (bytes[k]) B200_CUDA(cudaMemcpyAsync(recv[k], send[k], bytes[k], cudaMemcpyDeviceToDevice, st));
+        T->forest[part].valid = true;
+    }
+    ctx->launches += 0;
+    bool all = true;
+    for (int q = 0; q < P; ++q) all = all && T->forest[q].valid;
+    if (all) {
+        ForestTables F;
+        memset(&F, 0, sizeof F);
+        F.n_parts = P;
+        for (int q = 0; q < P; ++q) {
+            F.nodes[q] = T->forest[q].nodes.as<float4>();
+            F.leaf_off[q] = T->forest[q].leaf_off.as<int>();
+            F.leaf_pairs[q] = T->forest[q].leaf_pairs.as<ulonglong2>();
+            for (int d = q * 8 / P; d < (q + 1) * 8 / P; ++d) F.owner[d] = q;
+        }
+        // forest_root buffer: [0, 32) the merged root record, [64, 64 + sizeof F) the table directory
+        B200_TRY(T->forest_root.reserve(64 + sizeof(ForestTables)));
+        forest_root_kernel<<<1, 1, 0, st>>>(F, T->forest_root.as<float4>());
+        set_forest_kernel<<<1, 1, 0, st>>>(F, (ForestTables*)(T->forest_root.as<char>() + 64));
+        ctx->launches += 2;
+        B200_CUDA(cudaGetLastError());
+    }
+    return B200_OK;
+}
+
+// {x, y, z, M} {first, skip, edge, leaf count} of the merged root (host; synchronises)
+int tree_forest_root(b200_ctx* ctx, float out[8]) {
+    TreeState* T = ctx->tree;
+    if (!T || !T->forest_root.p) return B200_ERR_STATE;
+    B200_CUDA(cudaDeviceSynchronize());
+    B200_CUDA(cudaMemcpy(out, T->forest_root.p, 8 * sizeof(float), cudaMemcpyDeviceToHost));
     return B200_OK;
 }
 
