@@ -587,7 +587,7 @@ def c4_summary(eng, D, flush, n, steps, mode):
         dist.broadcast(posm, 0)
         dist.broadcast(velf, 0)
     dt = 1e-4
-    run = C4Run(eng, D, posm, velf, n, mode)
+    run = (C4RunSharded if mode == "sharded" else C4Run)(eng, D, posm, velf, n, mode)
     del velf
     a = 1.0
     run.forces()                         # forces at the initial positions (first half-kick)
@@ -673,6 +673,124 @@ class C4Run:
 
     def close(self):
         pass
+
+
+class C4RunSharded:
+    """mode "sharded": (1) OWNERSHIP by space-filling curve -- the particles are ordered once along a Hilbert curve
+    (b200_spatial_order_dev) and rank r owns the r-th N/G run of that order for the whole run (positions, velocities
+    and accelerations packed in that order), so a rank's targets are a compact region whatever the index order; each
+    step the packed float4 shards are all-gathered (NCCL) and scattered back to their original indices
+    (b200_scatter_rows_dev), because the reference's tree depends on index order.  (2) OCTANT-SHARDED BUILD -- rank r
+    builds only the subtrees of its octants of the root (b200_tree_build_part_dev) and the ranks exchange their walk
+    tables (b200_tree_forest_publish: NCCL broadcasts on the context's own communicator).  (3) The walk runs over the
+    forest for the rank's target list (b200_tree_walk_list_dev)."""
+
+    def __init__(self, eng, D, posm, velf, n, mode):
+        torch, dist = D.torch, D.dist
+        self.eng, self.D, self.n = eng, D, n
+        if n % D.world or D.world > 8:
+            raise SystemExit("c4 sharded mode needs n divisible by the rank count and at most 8 ranks")
+        if D.world > 1:
+            box = [eng.shard_unique_id() if D.rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            eng.shard_init(box[0], D.rank, D.world)
+        self.posm = posm
+        self.perm = torch.empty(n, dtype=torch.int32, device=D.dev)
+        eng.spatial_order_dev(posm, n, 100.0, self.perm)
+        self.nl = n // D.world
+        self.lo = D.rank * self.nl
+        self.own = self.perm[self.lo:self.lo + self.nl].contiguous()
+        self.posm_own = torch.empty((self.nl, 4), dtype=torch.float32, device=D.dev)
+        self.vel = torch.empty((self.nl, 3), dtype=torch.float32, device=D.dev)
+        eng.gather_rows_dev(posm, velf, self.own, self.nl, self.posm_own, self.vel)
+        self.acc = torch.zeros((self.nl, 3), dtype=torch.float32, device=D.dev)
+        self.staging = torch.empty((n, 4), dtype=torch.float32, device=D.dev) if D.world > 1 else None
+        self.phase_names = ["leapfrog", "exchange", "build", "walk"]
+        self.mode_text = ("Hilbert-curve ownership fixed at step 0 (packed shards); per step: NCCL all-gather of the packed "
+                          "float4 shards + scatter to original indices, octant-sharded octree build (each rank its own "
+                          "octants of the root) + NCCL exchange of the walk tables, forest walk of the rank's target list")
+
+    def poison(self):
+        if self.D.world > 1:
+            self.posm.fill_(NAN)
+            self.staging.fill_(NAN)
+
+    def forces(self, ev=None):
+        D, eng = self.D, self.eng
+        if D.world > 1:
+            D.dist.all_gather_into_tensor(self.staging.view(-1), self.posm_own.view(-1))
+            eng.scatter_rows_dev(self.staging, self.perm, self.n, self.posm)
+        else:
+            eng.scatter_rows_dev(self.posm_own, self.perm, self.n, self.posm)
+        if ev:
+            ev[2].record()
+        if D.world > 1:
+            eng.tree_build_part_dev(self.posm, self.n, D.rank, D.world, 100.0, 8, 20)
+            eng.tree_forest_publish()
+        else:
+            eng.tree_build_dev(self.posm, self.n, 100.0, 8, 20)
+        if ev:
+            ev[3].record()
+        eng.tree_walk_list_dev(self.acc, self.own, self.nl, theta=0.5, forest=D.world > 1)
+        if ev:
+            ev[4].record()
+
+    def step(self, a, dt, ev=None):
+        eng = self.eng
+        eng.leapfrog_dev(self.posm_own, self.vel, self.acc, self.nl, 2, np.float32(dt * 0.5), a, np.float32(dt), 0.0)
+        a = eng.scale_factor_step(a, dt)
+        if ev:
+            ev[1].record()
+        self.forces(ev)
+        return a
+
+    def parity(self, per_rank=256):
+        """Untimed.  Rank 0 builds the CPU oracle's tree from the positions it holds after the exchange and walks
+        `per_rank` targets of every rank's list; the exchange itself is checked by comparing rank 0's index-ordered
+        array with every owner's packed shard (gathered again, independently, with torch indexing)."""
+        from inputs import rel_l2
+        from oracle.pyoracle import Oracle
+        D, torch = self.D, self.D.torch
+        sel = torch.linspace(0, self.nl - 1, per_rank, device=D.dev).long()
+        idx = self.own[sel].contiguous()
+        got = self.acc[sel].contiguous()
+        if D.world > 1:
+            idxs = [torch.empty_like(idx) for _ in range(D.world)]
+            gots = [torch.empty_like(got) for _ in range(D.world)]
+            shards = [torch.empty_like(self.posm_own) for _ in range(D.world)]
+            D.dist.all_gather(idxs, idx)
+            D.dist.all_gather(gots, got)
+            D.dist.all_gather(shards, self.posm_own)
+        else:
+            idxs, gots, shards = [idx], [got], [self.posm_own]
+        err, exchange_ok = 0.0, True
+        if D.rank == 0:
+            check = torch.empty_like(self.posm)
+            check[self.perm.long()] = torch.cat(shards, 0)
+            exchange_ok = bool(torch.equal(check.view(torch.int32), self.posm.view(torch.int32)))
+            del check
+            host = self.posm.cpu().numpy()
+            if np.isfinite(host).all():
+                pos, mass = np.ascontiguousarray(host[:, :3]), np.ascontiguousarray(host[:, 3])
+                o = Oracle()
+                t = o.tree_build(pos, mass)
+                for r in range(D.world):
+                    ii = idxs[r].cpu().numpy()
+                    ref = np.concatenate([o.tree_forces(t, pos, 0.5, i0=int(i), n_targets=1) for i in ii], 0)
+                    g = gots[r].cpu().numpy()
+                    err = max(err, rel_l2(g, ref) if np.isfinite(g).all() else float("inf"))
+            else:
+                err = float("inf")
+        err = D.max(err)
+        exchange_ok = D.all_ok(exchange_ok)
+        return {"rel_l2": err, "gate": 1e-3, "targets_per_rank": per_rank,
+                "oracle": "orc_tree_build_levels + orc_tree_forces on rank 0 (CPU restatement of TreeForceComputer, "
+                          "all particles as exchanged)",
+                "gather_checksums_ok": exchange_ok, "ok": bool(err <= 1e-3 and exchange_ok)}
+
+    def close(self):
+        if self.D.world > 1:
+            self.eng.shard_finalize()
 
 
 def c1_summary(eng, D, steps=10):
@@ -955,6 +1073,8 @@ def bench_gpu(args):
         ts = tree_summary(eng, D, S, flush, clocks=clocks, static_ok=(args.order == "random"))
         lf = leapfrog_roofline(eng, D, (1 << 24) // world)
         c4 = c4_summary(eng, D, flush, 1 << 24, 8, args.c4_mode)
+        # the round-1 scheme (index shards, every rank builds the whole tree) beside it, where the two differ
+        c4_rep = c4_summary(eng, D, flush, 1 << 24, 4, "replicated") if world > 1 and args.c4_mode == "sharded" else None
         c5 = c5_summary(eng, D, flush) if not args.no_c5 else None
         box_line = c1 = None
         if world == 1:
@@ -969,6 +1089,8 @@ def bench_gpu(args):
             line["tree_summary"] = ts
             line["leapfrog_roofline"] = lf
             line["c4_summary"] = c4
+            if c4_rep is not None:
+                line["c4_summary_replicated_build"] = c4_rep
             if c5 is not None:
                 line["c5_summary"] = c5
             if box_line is not None:
@@ -1006,7 +1128,7 @@ def main():
                     help="default (direct, 2^20) run: skip the short measurements of the other BASELINE configs "
                          "(tree_summary, c4_summary, c5_summary, c1_summary, leapfrog_roofline)")
     ap.add_argument("--no-c5", action="store_true", help="skip c5_summary (2^23-particle direct sum: 24 s on one GPU)")
-    ap.add_argument("--c4-mode", default="replicated", choices=["replicated", "sharded"],
+    ap.add_argument("--c4-mode", default="sharded", choices=["replicated", "sharded"],
                     help="c4_summary: every rank builds the whole octree on contiguous index shards (round-1 scheme), "
                          "or octant-sharded build + Hilbert-owned targets")
     ap.add_argument("--sources", default="allgather", choices=["allgather", "peer"],

@@ -327,6 +327,63 @@ int b200_tree_walk_dev(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, 
     return tree_walk(ctx, i0, n_targets, theta, acc3, pick_stream(ctx, stream));
 }
 
+int b200_tree_build_part_dev(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_cap, int max_depth,
+                             int part, int n_parts, void* stream) {
+    if (!ctx) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return tree_build_part(ctx, posm4, n, box, leaf_cap, max_depth, part, n_parts, pick_stream(ctx, stream));
+}
+
+int b200_tree_forest_publish(b200_ctx* ctx, void* stream) {
+    if (!ctx) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return tree_forest_publish(ctx, pick_stream(ctx, stream));
+}
+
+int b200_tree_walk_list_dev(b200_ctx* ctx, const void* list_i32, size_t n_list, float theta, void* acc3,
+                            int use_forest, void* stream) {
+    if (!ctx) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return tree_walk_list(ctx, (const int*)list_i32, n_list, theta, acc3, use_forest, pick_stream(ctx, stream));
+}
+
+int b200_tree_forest_root(b200_ctx* ctx, float out[8]) {
+    if (!ctx || !out) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return tree_forest_root(ctx, out);
+}
+
+int b200_scatter_rows_dev(b200_ctx* ctx, const void* src4, const void* perm_i32, size_t n, void* dst4, void* stream) {
+    if (!ctx || (n && (!src4 || !perm_i32 || !dst4))) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return scatter_rows(ctx, src4, perm_i32, n, dst4, pick_stream(ctx, stream));
+}
+
+int b200_gather_rows_dev(b200_ctx* ctx, const void* src4, const void* src3, const void* list_i32, size_t n,
+                         void* out4, void* out3, void* stream) {
+    if (!ctx || (n && !list_i32) || (src4 && !out4) || (src3 && !out3)) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    return gather_rows(ctx, src4, src3, list_i32, n, out4, out3, pick_stream(ctx, stream));
+}
+
+int b200_host_register(b200_ctx* ctx, void* host_ptr, size_t bytes) {
+    if (!ctx || !host_ptr || bytes == 0) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    const cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return B200_OK; }
+    B200_CUDA(e);
+    return B200_OK;
+}
+
+int b200_host_unregister(b200_ctx* ctx, void* host_ptr) {
+    if (!ctx || !host_ptr) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->device));
+    const cudaError_t e = cudaHostUnregister(host_ptr);
+    if (e == cudaErrorHostMemoryNotRegistered) { cudaGetLastError(); return B200_OK; }
+    B200_CUDA(e);
+    return B200_OK;
+}
+
 // The two phases of compute_forces as the reference class exposes them (tree_force_computer.hpp:78-80:
 // build_tree / compute_tree_forces): the particles stay on the device between the calls.
 int b200_tree_build_host(b200_ctx* ctx, const float* pos3, const float* mass, size_t n, float box,

@@ -158,7 +158,43 @@ __global__ void unpack_pos3_kernel(const float4* __restrict__ posm, long long n,
     pos3[3 * i] = p.x; pos3[3 * i + 1] = p.y; pos3[3 * i + 2] = p.z;
 }
 
+__global__ void scatter_rows_kernel(const float4* __restrict__ src, const int* __restrict__ perm, long long n,
+                                    float4* __restrict__ dst) {
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) dst[perm[k]] = src[k];
+}
+
+__global__ void gather_rows_kernel(const float4* __restrict__ src4, const float* __restrict__ src3,
+                                   const int* __restrict__ list, long long n, float4* __restrict__ out4,
+                                   float* __restrict__ out3) {
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const long long i = list[k];
+    if (src4) out4[k] = src4[i];
+    if (src3) { out3[3 * k] = src3[3 * i]; out3[3 * k + 1] = src3[3 * i + 1]; out3[3 * k + 2] = src3[3 * i + 2]; }
+}
+
 }  // namespace
+
+int scatter_rows(b200_ctx* ctx, const void* src4, const void* perm, size_t n, void* dst4, cudaStream_t st) {
+    if (n == 0) return B200_OK;
+    scatter_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float4*)src4, (const int*)perm, (long long)n,
+                                                                     (float4*)dst4);
+    B200_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return B200_OK;
+}
+
+int gather_rows(b200_ctx* ctx, const void* src4, const void* src3, const void* list, size_t n, void* out4, void* out3,
+                cudaStream_t st) {
+    if (n == 0) return B200_OK;
+    gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float4*)src4, (const float*)src3,
+                                                                    (const int*)list, (long long)n, (float4*)out4,
+                                                                    (float*)out3);
+    B200_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return B200_OK;
+}
 
 int unpack_pos3(b200_ctx* ctx, const void* posm4, size_t n, void* pos3, cudaStream_t st) {
     if (n == 0) return B200_OK;

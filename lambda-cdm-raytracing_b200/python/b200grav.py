@@ -22,6 +22,8 @@ EXPORTS = [
     "b200_morton_keys_dev", "b200_sort_pairs_dev", "b200_tree_build_dev",
     "b200_tree_walk_dev", "b200_tree_forces_host", "b200_tree_stats", "b200_tree_export",
     "b200_tree_set_counting", "b200_tree_counters", "b200_tree_walk_stats", "b200_tree_overflowed",
+    "b200_tree_build_part_dev", "b200_tree_forest_publish", "b200_tree_walk_list_dev", "b200_tree_forest_root",
+    "b200_scatter_rows_dev", "b200_gather_rows_dev", "b200_host_register", "b200_host_unregister",
     "b200_leapfrog_dev", "b200_leapfrog_host", "b200_hubble_a", "b200_scale_factor_step", "b200_pack_posm_dev",
     "b200_device_alloc", "b200_device_free", "b200_memcpy_h2d", "b200_memcpy_d2h", "b200_unpack_pos3_dev", "b200_ipc_export", "b200_ipc_open", "b200_ipc_close",
     "b200_shard_range", "b200_shard_unique_id", "b200_shard_init", "b200_shard_finalize", "b200_shard_info",
@@ -85,6 +87,14 @@ def load_library(path=None):
     L.b200_tree_counters.argtypes = [vp, vp]
     L.b200_tree_walk_stats.argtypes = [vp, vp]
     L.b200_tree_overflowed.argtypes = [vp, C.POINTER(i32)]
+    L.b200_tree_build_part_dev.argtypes = [vp, vp, sz, f32, i32, i32, i32, i32, vp]
+    L.b200_tree_forest_publish.argtypes = [vp, vp]
+    L.b200_tree_walk_list_dev.argtypes = [vp, vp, sz, f32, vp, i32, vp]
+    L.b200_tree_forest_root.argtypes = [vp, vp]
+    L.b200_scatter_rows_dev.argtypes = [vp, vp, vp, sz, vp, vp]
+    L.b200_gather_rows_dev.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
+    L.b200_host_register.argtypes = [vp, vp, sz]
+    L.b200_host_unregister.argtypes = [vp, vp]
     L.b200_leapfrog_dev.argtypes = [vp, vp, vp, vp, sz, i32, f32, f64, f32, f32, vp]
     L.b200_leapfrog_host.argtypes = [vp, vp, vp, vp, vp, sz, i32, f32, f64, f32, f32]
     L.b200_hubble_a.argtypes = [f64] * 5
@@ -291,6 +301,38 @@ class Engine:
         c = np.zeros(3, np.uint64)
         self._check(self.L.b200_tree_counters(self._h, _ptr(c)))
         return c
+
+    # -- octant-sharded build / forest walk ------------------------------------
+    def tree_build_part_dev(self, posm, n, part, n_parts, box=100.0, leaf_cap=8, max_depth=20, stream=None):
+        self._check(self.L.b200_tree_build_part_dev(self._h, _ptr(posm), n, box, leaf_cap, max_depth, part, n_parts,
+                                                    _stream(stream)))
+
+    def tree_forest_publish(self, stream=None):
+        self._check(self.L.b200_tree_forest_publish(self._h, _stream(stream)))
+
+    def tree_walk_list_dev(self, acc, target_list, n_list=None, theta=0.5, forest=False, stream=None):
+        n_list = target_list.shape[0] if n_list is None else n_list
+        self._check(self.L.b200_tree_walk_list_dev(self._h, _ptr(target_list), n_list, theta, _ptr(acc), int(forest),
+                                                   _stream(stream)))
+        return acc
+
+    def tree_forest_root(self):
+        out = np.zeros(8, np.float32)
+        self._check(self.L.b200_tree_forest_root(self._h, _ptr(out)))
+        return out
+
+    def scatter_rows_dev(self, src4, perm, n, dst4, stream=None):
+        self._check(self.L.b200_scatter_rows_dev(self._h, _ptr(src4), _ptr(perm), n, _ptr(dst4), _stream(stream)))
+
+    def gather_rows_dev(self, src4, src3, index_list, n, out4, out3, stream=None):
+        self._check(self.L.b200_gather_rows_dev(self._h, _ptr(src4), _ptr(src3), _ptr(index_list), n, _ptr(out4),
+                                                _ptr(out3), _stream(stream)))
+
+    def host_register(self, array):
+        self._check(self.L.b200_host_register(self._h, _ptr(array), array.nbytes))
+
+    def host_unregister(self, array):
+        self._check(self.L.b200_host_unregister(self._h, _ptr(array)))
 
     def tree_walk_stats(self):
         """Counters of the last counting walk + lane utilisation: nodes visited, cell, pair interactions,

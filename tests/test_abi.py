@@ -24,7 +24,7 @@ def test_every_declared_symbol_is_exported():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/b200grav.h but not exported"
     assert sorted(b200grav.EXPORTS) == names
-    assert lib.b200_abi_version() == 1
+    assert lib.b200_abi_version() == 2
 
 
 def test_host_scalars_match_oracle(oracle):
