@@ -676,14 +676,14 @@ class C4Run:
 
 
 class C4RunSharded:
-    """mode "sharded": (1) OWNERSHIP by space-filling curve -- the particles are ordered once along a Hilbert curve
-    (b200_spatial_order_dev) and rank r owns the r-th N/G run of that order for the whole run (positions, velocities
-    and accelerations packed in that order), so a rank's targets are a compact region whatever the index order; each
-    step the packed float4 shards are all-gathered (NCCL) and scattered back to their original indices
-    (b200_scatter_rows_dev), because the reference's tree depends on index order.  (2) OCTANT-SHARDED BUILD -- rank r
-    builds only the subtrees of its octants of the root (b200_tree_build_part_dev) and the ranks exchange their walk
-    tables (b200_tree_forest_publish: NCCL broadcasts on the context's own communicator).  (3) The walk runs over the
-    forest for the rank's target list (b200_tree_walk_list_dev)."""
+    """mode "sharded": (1) STORAGE along a space-filling curve -- the particles are ordered once along a Hilbert curve
+    (b200_spatial_order_dev) and kept in that order for the whole run; rank r owns the r-th N/G run of slots, a
+    compact region whatever the original index order, and the per-step exchange is the plain in-place NCCL
+    all-gather of the float4 shards.  The octree is still the reference's: the build receives the ARRIVAL order
+    (arrival[k] = slot of original particle k), so particles are inserted in original index order.
+    (2) OCTANT-SHARDED BUILD -- rank r builds only the subtrees of its octants of the root
+    (b200_tree_build_part_dev) and the ranks exchange their walk tables (b200_tree_forest_publish: NCCL broadcasts
+    on the context's own communicator).  (3) The walk of the rank's slots runs over the forest."""
 
     def __init__(self, eng, D, posm, velf, n, mode):
         torch, dist = D.torch, D.dist
@@ -694,99 +694,84 @@ class C4RunSharded:
             box = [eng.shard_unique_id() if D.rank == 0 else None]
             dist.broadcast_object_list(box, src=0)
             eng.shard_init(box[0], D.rank, D.world)
-        self.posm = posm
-        self.perm = torch.empty(n, dtype=torch.int32, device=D.dev)
+        self.perm = torch.empty(n, dtype=torch.int32, device=D.dev)          # perm[slot] = original index
         eng.spatial_order_dev(posm, n, 100.0, self.perm)
-        self.nl = n // D.world
-        self.lo = D.rank * self.nl
-        self.own = self.perm[self.lo:self.lo + self.nl].contiguous()
-        self.posm_own = torch.empty((self.nl, 4), dtype=torch.float32, device=D.dev)
-        self.vel = torch.empty((self.nl, 3), dtype=torch.float32, device=D.dev)
-        eng.gather_rows_dev(posm, velf, self.own, self.nl, self.posm_own, self.vel)
+        stored = torch.empty_like(posm)
+        vel_all = torch.empty_like(velf)
+        eng.gather_rows_dev(posm, velf, self.perm, n, stored, vel_all)
+        self.arrival = torch.empty_like(self.perm)                            # arrival[original index] = slot
+        self.arrival[self.perm.long()] = torch.arange(n, dtype=torch.int32, device=D.dev)
+        self.S = Sharded(D, stored, n)
+        self.lo, self.nl = self.S.lo, self.S.nl
+        self.vel = vel_all[self.lo:self.lo + self.nl].clone()
+        del vel_all
         self.acc = torch.zeros((self.nl, 3), dtype=torch.float32, device=D.dev)
-        self.staging = torch.empty((n, 4), dtype=torch.float32, device=D.dev) if D.world > 1 else None
-        self.phase_names = ["leapfrog", "exchange", "build", "walk"]
-        self.mode_text = ("Hilbert-curve ownership fixed at step 0 (packed shards); per step: NCCL all-gather of the packed "
-                          "float4 shards + scatter to original indices, octant-sharded octree build (each rank its own "
-                          "octants of the root) + NCCL exchange of the walk tables, forest walk of the rank's target list")
+        self.phase_names = ["leapfrog", "allgather", "build", "walk"]
+        self.mode_text = ("particles stored in Hilbert-curve order fixed at step 0 (contiguous slot shards), arrival order "
+                          "= original index order handed to the build; per step: in-place NCCL all-gather of the float4 "
+                          "shards, octant-sharded octree build (each rank its own octants of the root) + NCCL exchange of "
+                          "the walk tables (b200_tree_forest_publish), forest walk of the rank's slots")
 
     def poison(self):
-        if self.D.world > 1:
-            self.posm.fill_(NAN)
-            self.staging.fill_(NAN)
+        self.S.poison()
 
     def forces(self, ev=None):
-        D, eng = self.D, self.eng
-        if D.world > 1:
-            D.dist.all_gather_into_tensor(self.staging.view(-1), self.posm_own.view(-1))
-            eng.scatter_rows_dev(self.staging, self.perm, self.n, self.posm)
-        else:
-            eng.scatter_rows_dev(self.posm_own, self.perm, self.n, self.posm)
+        D, eng, S = self.D, self.eng, self.S
+        S.gather()
         if ev:
             ev[2].record()
+        eng.tree_build_part_dev(S.posm, self.n, D.rank, D.world, 100.0, 8, 20, arrival=self.arrival)
         if D.world > 1:
-            eng.tree_build_part_dev(self.posm, self.n, D.rank, D.world, 100.0, 8, 20)
             eng.tree_forest_publish()
-        else:
-            eng.tree_build_dev(self.posm, self.n, 100.0, 8, 20)
         if ev:
             ev[3].record()
-        eng.tree_walk_list_dev(self.acc, self.own, self.nl, theta=0.5, forest=D.world > 1)
+        eng.tree_walk_dev(self.acc, self.lo, self.nl, theta=0.5)
         if ev:
             ev[4].record()
 
     def step(self, a, dt, ev=None):
         eng = self.eng
-        eng.leapfrog_dev(self.posm_own, self.vel, self.acc, self.nl, 2, np.float32(dt * 0.5), a, np.float32(dt), 0.0)
+        eng.leapfrog_dev(self.S.shard, self.vel, self.acc, self.nl, 2, np.float32(dt * 0.5), a, np.float32(dt), 0.0)
         a = eng.scale_factor_step(a, dt)
         if ev:
             ev[1].record()
         self.forces(ev)
         return a
 
-    def parity(self, per_rank=256):
-        """Untimed.  Rank 0 builds the CPU oracle's tree from the positions it holds after the exchange and walks
-        `per_rank` targets of every rank's list; the exchange itself is checked by comparing rank 0's index-ordered
-        array with every owner's packed shard (gathered again, independently, with torch indexing)."""
+    def parity(self, per_rank=1024):
+        """Untimed.  Rank 0 puts the particles it holds after the all-gather back in original index order, builds the
+        CPU oracle's tree from them and walks a block of every rank's targets."""
         from inputs import rel_l2
         from oracle.pyoracle import Oracle
         D, torch = self.D, self.D.torch
-        sel = torch.linspace(0, self.nl - 1, per_rank, device=D.dev).long()
-        idx = self.own[sel].contiguous()
-        got = self.acc[sel].contiguous()
+        b0, cnt = sample_block(self.lo, self.nl, per_rank)
+        got = self.acc[b0 - self.lo:b0 - self.lo + cnt].contiguous()
+        gots = [torch.empty_like(got) for _ in range(D.world)]
         if D.world > 1:
-            idxs = [torch.empty_like(idx) for _ in range(D.world)]
-            gots = [torch.empty_like(got) for _ in range(D.world)]
-            shards = [torch.empty_like(self.posm_own) for _ in range(D.world)]
-            D.dist.all_gather(idxs, idx)
             D.dist.all_gather(gots, got)
-            D.dist.all_gather(shards, self.posm_own)
         else:
-            idxs, gots, shards = [idx], [got], [self.posm_own]
-        err, exchange_ok = 0.0, True
+            gots = [got]
+        err = 0.0
         if D.rank == 0:
-            check = torch.empty_like(self.posm)
-            check[self.perm.long()] = torch.cat(shards, 0)
-            exchange_ok = bool(torch.equal(check.view(torch.int32), self.posm.view(torch.int32)))
-            del check
-            host = self.posm.cpu().numpy()
+            perm = self.perm.cpu().numpy()
+            host = np.empty((self.n, 4), np.float32)
+            host[perm] = self.S.posm.cpu().numpy()                     # original index order
             if np.isfinite(host).all():
                 pos, mass = np.ascontiguousarray(host[:, :3]), np.ascontiguousarray(host[:, 3])
                 o = Oracle()
                 t = o.tree_build(pos, mass)
                 for r in range(D.world):
-                    ii = idxs[r].cpu().numpy()
-                    ref = np.concatenate([o.tree_forces(t, pos, 0.5, i0=int(i), n_targets=1) for i in ii], 0)
+                    s0 = sample_block(r * self.nl, self.nl, per_rank)[0]
+                    ref = np.concatenate([o.tree_forces(t, pos, 0.5, i0=int(i), n_targets=1) for i in perm[s0:s0 + cnt]], 0)
                     g = gots[r].cpu().numpy()
                     err = max(err, rel_l2(g, ref) if np.isfinite(g).all() else float("inf"))
             else:
                 err = float("inf")
         err = D.max(err)
-        exchange_ok = D.all_ok(exchange_ok)
-        return {"rel_l2": err, "gate": 1e-3, "targets_per_rank": per_rank,
-                "oracle": "orc_tree_build_levels + orc_tree_forces on rank 0 (CPU restatement of TreeForceComputer, "
-                          "all particles as exchanged)",
-                "gather_checksums_ok": exchange_ok, "ok": bool(err <= 1e-3 and exchange_ok)}
+        return {"rel_l2": err, "gate": 1e-3, "targets_per_rank": cnt,
+                "oracle": "orc_tree_build_levels + orc_tree_forces on rank 0 (CPU restatement of TreeForceComputer; all "
+                          "particles as gathered, put back in original index order)",
+                "gather_checksums_ok": self.S.gather_checksums_ok(), "ok": bool(err <= 1e-3)}
 
     def close(self):
         if self.D.world > 1:

@@ -214,22 +214,32 @@ int b200_tree_forces_fixed_host(b200_ctx* ctx, const float* pos3, const float* m
  * The subtrees under the 8 children of the root are independent of each other once the root has routed its
  * arrivals -- the orphan rule is per node -- so the build shards by octant with no change to the tree:
  * part p of n_parts (<= 8) owns octants [8p/n_parts, 8(p+1)/n_parts) of the root; b200_tree_build_part_dev runs
- * the root level over all n particles (index order, sequential reads) and every deeper level over the particles
- * of its own octants only; the other octants stay empty leaves in this part's tree (b200_tree_stats / _export
- * describe the part).  b200_tree_forest_publish makes the part's walk tables visible to all walkers: over NCCL
- * when the context has a communicator of exactly n_parts ranks with rank == part (b200_shard_init; collective:
- * table sizes by an 8-byte all-gather + host read-back, then one grouped broadcast per table and owner),
- * otherwise into this context's own slot (one process building the parts in turn).  When every part is current
- * the root's centre of mass is merged from the parts' level-1 nodes in the reference's order and rounding.
- * b200_tree_walk_list_dev walks explicit target lists: targets = posm4[list[t]] of the array the build saw,
- * acc3[3t..] in LIST order, a warp = 32 consecutive list entries (so the caller chooses the grouping -- e.g. a
- * rank's slice of b200_spatial_order_dev); use_forest != 0 walks the published forest, 0 this context's tree.
+ * the root level over all n particles and every deeper level over the particles of its own octants only; the
+ * other octants stay empty leaves in this part's tree (b200_tree_stats / _export describe the part).
+ *
+ * arrival_i32 (device int32[n], or NULL): the reference's tree depends on the ORDER in which particles are
+ * inserted (:136-140, index order).  arrival[k] = storage slot of the k-th particle to insert decouples that
+ * order from where the particles are stored: a run that keeps its particles in a space-filling order (compact
+ * shards, coherent gathers; b200_spatial_order_dev) passes the inverse of its storage permutation and gets the
+ * reference's tree, node for node.  Particle ids in everything derived from the build (stored lists of
+ * b200_tree_export, walk targets) are STORAGE SLOTS.  NULL = particles are stored in insertion order.
+ * n_parts == 1 builds the whole tree (b200_tree_build_dev with an arrival order).
+ *
+ * b200_tree_forest_publish makes the part's walk tables visible to all walkers: over NCCL when the context has a
+ * communicator of exactly n_parts ranks with rank == part (b200_shard_init; collective: table sizes by an 8-byte
+ * all-gather + host read-back, then one grouped broadcast per table and owner), otherwise into this context's own
+ * slot (one process building the parts in turn -- it must rebuild and publish EVERY part after particles move).
+ * When every part is current the root's centre of mass is merged from the parts' level-1 nodes in the
+ * reference's order and rounding.  After that b200_tree_walk_dev / b200_tree_walk_list_dev on this context walk
+ * the forest (a part alone is not a tree; B200_ERR_STATE while a part is missing or stale).
+ * b200_tree_walk_list_dev walks an explicit target list: targets = posm4[list[t]], acc3[3t..] in LIST order, a
+ * warp = 32 consecutive list entries (the caller chooses the grouping).
  * Forces, counters and per-target interaction sets are those of the unsharded build + walk. */
-int b200_tree_build_part_dev(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_cap,
-                             int max_depth, int part, int n_parts, void* stream);
+int b200_tree_build_part_dev(b200_ctx* ctx, const void* posm4, const void* arrival_i32, size_t n, float box,
+                             int leaf_cap, int max_depth, int part, int n_parts, void* stream);
 int b200_tree_forest_publish(b200_ctx* ctx, void* stream);
 int b200_tree_walk_list_dev(b200_ctx* ctx, const void* list_i32, size_t n_list, float theta, void* acc3,
-                            int use_forest, void* stream);
+                            void* stream);
 /* Merged root record of the published forest (host): {com x, y, z, M, -, -, cell edge, -}.  Synchronises. */
 int b200_tree_forest_root(b200_ctx* ctx, float out[8]);
 /* dst4[perm[k]] = src4[k] for k < n (float4 rows, device): puts particles stored in another order -- e.g. the

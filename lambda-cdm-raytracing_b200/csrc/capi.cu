@@ -327,11 +327,12 @@ int b200_tree_walk_dev(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, 
     return tree_walk(ctx, i0, n_targets, theta, acc3, pick_stream(ctx, stream));
 }
 
-int b200_tree_build_part_dev(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_cap, int max_depth,
-                             int part, int n_parts, void* stream) {
+int b200_tree_build_part_dev(b200_ctx* ctx, const void* posm4, const void* arrival_i32, size_t n, float box,
+                             int leaf_cap, int max_depth, int part, int n_parts, void* stream) {
     if (!ctx) return B200_ERR_INVALID;
     B200_CUDA(cudaSetDevice(ctx->device));
-    return tree_build_part(ctx, posm4, n, box, leaf_cap, max_depth, part, n_parts, pick_stream(ctx, stream));
+    return tree_build_part(ctx, posm4, (const int*)arrival_i32, n, box, leaf_cap, max_depth, part, n_parts,
+                           pick_stream(ctx, stream));
 }
 
 int b200_tree_forest_publish(b200_ctx* ctx, void* stream) {
@@ -341,10 +342,10 @@ int b200_tree_forest_publish(b200_ctx* ctx, void* stream) {
 }
 
 int b200_tree_walk_list_dev(b200_ctx* ctx, const void* list_i32, size_t n_list, float theta, void* acc3,
-                            int use_forest, void* stream) {
+                            void* stream) {
     if (!ctx) return B200_ERR_INVALID;
     B200_CUDA(cudaSetDevice(ctx->device));
-    return tree_walk_list(ctx, (const int*)list_i32, n_list, theta, acc3, use_forest, pick_stream(ctx, stream));
+    return tree_walk_list(ctx, (const int*)list_i32, n_list, theta, acc3, pick_stream(ctx, stream));
 }
 
 int b200_tree_forest_root(b200_ctx* ctx, float out[8]) {

@@ -94,6 +94,11 @@ struct TreeState {
     // octants in oct_mask only; the other octants are empty leaves.  The walk tables of all parts make a FOREST.
     int part = 0, n_parts = 1;
     unsigned oct_mask = 0xffu;
+    // arrival[k] = storage slot of the k-th particle the reference would insert (nullptr: slot k).  Lets a run
+    // STORE its particles in a space-filling order (compact shards, coherent gathers) while the tree stays the
+    // one the reference builds from the original index order.  Particle ids everywhere below are storage slots.
+    const int* arrival = nullptr;
+    size_t forest_key = 0;        // (posm, arrival, n, box, cap, depth, n_parts) of the forest the slots belong to
     struct ForestSlot {
         DevBuf nodes, leaf_off, leaf_pairs;
         size_t nn = 0, npairs = 0;
@@ -106,7 +111,7 @@ struct TreeState {
         size_t h = 1469598103934665603ull;
         auto mix = [&h](size_t v) { h = (h ^ v) * 1099511628211ull; };
         mix((size_t)posm); mix(n); mix((size_t)cap); mix((size_t)max_depth); mix(fixed ? 1 : 0);
-        mix((size_t)oct_mask); mix((size_t)forest_hdr.p);
+        mix((size_t)oct_mask); mix((size_t)forest_hdr.p); mix((size_t)arrival);
         unsigned bb, eb;
         memcpy(&bb, &box, 4); memcpy(&eb, &eps, 4);
         mix(bb); mix(eb);
@@ -196,7 +201,8 @@ __global__ void root_cube_kernel(TreeGlobals* g) {
 }
 
 __global__ void tree_init_kernel(TreeGlobals* g, float4* center, float4* com, int4* meta, int* nstart,
-                                 int* ncount, int* ent_idx, int* ent_node, int n, float box, int fixed) {
+                                 int* ncount, int* ent_idx, int* ent_node, int n, float box, int fixed,
+                                 const int* __restrict__ arrival) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         for (int l = 0; l < MAX_LEVELS + 2; ++l) {
@@ -217,7 +223,7 @@ __global__ void tree_init_kernel(TreeGlobals* g, float4* center, float4* com, in
         ncount[0] = n;
     }
     for (; i < n; i += gridDim.x * blockDim.x) {
-        ent_idx[i] = i;
+        ent_idx[i] = arrival ? arrival[i] : i;          // arrival order = the reference's insertion order (:136-140)
         ent_node[i] = 0;
     }
 }
@@ -1331,12 +1337,12 @@ void tree_destroy(b200_ctx* ctx) {
 
 static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st);
 
-static int tree_build_impl(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_cap, int max_depth,
-                           bool fixed, float eps, int part, int n_parts, cudaStream_t st);
+static int tree_build_impl(b200_ctx* ctx, const void* posm4, const int* arrival, size_t n, float box, int leaf_cap,
+                           int max_depth, bool fixed, float eps, int part, int n_parts, cudaStream_t st);
 
 int tree_build(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_cap, int max_depth,
                bool fixed, float eps, cudaStream_t st) {
-    return tree_build_impl(ctx, posm4, n, box, leaf_cap, max_depth, fixed, eps, 0, 1, st);
+    return tree_build_impl(ctx, posm4, nullptr, n, box, leaf_cap, max_depth, fixed, eps, 0, 1, st);
 }
 
 // Octants [part * 8 / n_parts, (part + 1) * 8 / n_parts) of the root belong to part `part`.
@@ -1346,15 +1352,15 @@ static unsigned part_octants(int part, int n_parts) {
     return m;
 }
 
-int tree_build_part(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_cap, int max_depth, int part,
-                    int n_parts, cudaStream_t st) {
+int tree_build_part(b200_ctx* ctx, const void* posm4, const int* arrival, size_t n, float box, int leaf_cap,
+                    int max_depth, int part, int n_parts, cudaStream_t st) {
     if (n_parts < 1 || n_parts > 8 || part < 0 || part >= n_parts) return B200_ERR_INVALID;
-    if (n <= (size_t)leaf_cap) return B200_ERR_UNSUPPORTED;      // the root does not split: nothing to shard
-    return tree_build_impl(ctx, posm4, n, box, leaf_cap, max_depth, false, 0.01f, part, n_parts, st);
+    if (n_parts > 1 && n <= (size_t)leaf_cap) return B200_ERR_UNSUPPORTED;      // the root does not split: nothing to shard
+    return tree_build_impl(ctx, posm4, arrival, n, box, leaf_cap, max_depth, false, 0.01f, part, n_parts, st);
 }
 
-static int tree_build_impl(b200_ctx* ctx, const void* posm4, size_t n, float box, int leaf_cap, int max_depth,
-                           bool fixed, float eps, int part, int n_parts, cudaStream_t st) {
+static int tree_build_impl(b200_ctx* ctx, const void* posm4, const int* arrival, size_t n, float box, int leaf_cap,
+                           int max_depth, bool fixed, float eps, int part, int n_parts, cudaStream_t st) {
     if (!posm4 || n == 0) return B200_ERR_INVALID;
     if (fixed ? !(eps > 0.f) : !(box > 0.f)) return B200_ERR_INVALID;
     if (leaf_cap < 1 || max_depth < 0 || max_depth > MAX_LEVELS - 2) return B200_ERR_UNSUPPORTED;
@@ -1369,12 +1375,22 @@ static int tree_build_impl(b200_ctx* ctx, const void* posm4, size_t n, float box
     T->eps = fixed ? eps : 0.01f;
     T->posm = (const float4*)posm4;
     T->part = part; T->n_parts = n_parts;
+    T->arrival = arrival;
     T->oct_mask = n_parts > 1 ? part_octants(part, n_parts) : 0xffu;
     if (n_parts > 1) {
         B200_TRY(T->forest_hdr.reserve(8 * 2 * sizeof(int)));
-        // every rank of a communicator rebuilds its part in the same step: all slots go stale together; a
-        // single process playing all parts (tests) replaces them one at a time
-        if (ctx->shard != nullptr) for (auto& f : T->forest) f.valid = false;
+        // The slots belong to one forest: same particle array, arrival order, sizes and parameters.  Every rank of
+        // a communicator rebuilds its part in the same step, so all slots go stale together; a single process
+        // playing all parts (tests) replaces them one at a time -- and must rebuild every part after the
+        // particles have moved.
+        size_t key = 1469598103934665603ull;
+        auto mix = [&key](size_t v) { key = (key ^ v) * 1099511628211ull; };
+        unsigned bb;
+        memcpy(&bb, &box, 4);
+        mix((size_t)posm4); mix((size_t)arrival); mix(n); mix(bb); mix((size_t)leaf_cap); mix((size_t)max_depth);
+        mix((size_t)n_parts);
+        if (ctx->shard != nullptr || key != T->forest_key) for (auto& f : T->forest) f.valid = false;
+        T->forest_key = key;
         T->forest[part].valid = false;
     }
     // reference tree: every internal node keeps exactly leaf_cap particles => at most n/leaf_cap
@@ -1486,7 +1502,7 @@ static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st) {
         ctx->launches += 3;
     }
     tree_init_kernel<<<pgrid, 256, 0, st>>>(g, center, com, meta, nstart, ncount, T->ent_idx[0].as<int>(),
-                                            T->ent_node[0].as<int>(), (int)n, box, fixed ? 1 : 0);
+                                            T->ent_node[0].as<int>(), (int)n, box, fixed ? 1 : 0, T->arrival);
     ctx->launches += 1;
     for (int L = 0; L <= max_depth; ++L) {
         const int cur = L & 1, nxt = cur ^ 1;
@@ -1576,17 +1592,16 @@ static int tree_target_order(b200_ctx* ctx, TreeState* T, size_t i0, size_t n_ta
 // range computed here; acc3 indexed by index - i0) or an explicit list of particle indices (warps = runs of 32
 // list entries, acc3 in list order).  forest: walk the published forest of part builds, else this context's tree.
 static int tree_walk_impl(b200_ctx* ctx, const int* list, size_t i0, size_t n_targets, float theta, void* acc3,
-                          bool forest, cudaStream_t st) {
+                          cudaStream_t st) {
     TreeState* T = ctx->tree;
     if (!T || !T->built) return B200_ERR_STATE;
     if (n_targets == 0) return B200_OK;
     if (!acc3 || (!list && i0 + n_targets > T->n)) return B200_ERR_INVALID;
+    const bool forest = T->n_parts > 1;       // a part build alone is not the whole tree: its walk is the forest's
     if (forest) {
-        if (T->fixed || T->n_parts < 2) return B200_ERR_STATE;
+        if (T->fixed) return B200_ERR_STATE;
         for (int q = 0; q < T->n_parts; ++q)
             if (!T->forest[q].valid) return B200_ERR_STATE;               // a part has not been published since its rebuild
-    } else if (T->n_parts > 1) {
-        return B200_ERR_STATE;                                            // a part build alone is not the whole tree
     }
     const int* order = list;
     if (!list) {
@@ -1635,12 +1650,12 @@ static int tree_walk_impl(b200_ctx* ctx, const int* list, size_t i0, size_t n_ta
 }
 
 int tree_walk(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void* acc3, cudaStream_t st) {
-    return tree_walk_impl(ctx, nullptr, i0, n_targets, theta, acc3, false, st);
+    return tree_walk_impl(ctx, nullptr, i0, n_targets, theta, acc3, st);
 }
 
-int tree_walk_list(b200_ctx* ctx, const int* list, size_t n_list, float theta, void* acc3, int forest, cudaStream_t st) {
+int tree_walk_list(b200_ctx* ctx, const int* list, size_t n_list, float theta, void* acc3, cudaStream_t st) {
     if (n_list && !list) return B200_ERR_INVALID;
-    return tree_walk_impl(ctx, list, 0, n_list, theta, acc3, forest != 0, st);
+    return tree_walk_impl(ctx, list, 0, n_list, theta, acc3, st);
 }
 
 // ---- forest of part builds -------------------------------------------------------------------

@@ -4,6 +4,7 @@
 
 #include <iostream>
 #include <stdexcept>
+#include <unordered_map>
 #include <vector>
 
 #include "b200grav.h"
@@ -190,6 +191,15 @@ void B200LeapfrogIntegrator::step(float* positions, float* velocities, const flo
     if (!ctx_) throw std::runtime_error("LeapfrogIntegrator: not initialized (no B200 context)");
     LeapfrogStepParams p;
     if (const LeapfrogStepParams* q = std::any_cast<LeapfrogStepParams>(&params)) p = *q;
+    // the same parameters as a plain map, for hosts that do not want a plugin type in their translation units
+    // (integration/engine_wiring.patch): "scale_factor", "n_kicks", "drift" (0/1), "box_size"; unit masses
+    else if (const auto* m = std::any_cast<std::unordered_map<std::string, double>>(&params)) {
+        auto get = [m](const char* k, double dflt) { auto it = m->find(k); return it == m->end() ? dflt : it->second; };
+        p.scale_factor = get("scale_factor", 1.0);
+        p.n_kicks = (int)get("n_kicks", 1.0);
+        p.drift = get("drift", 1.0) != 0.0;
+        p.box_size = (float)get("box_size", 0.0);
+    }
     // lambda_cdm_impl.cu:170-189: kick by dt*0.5 (double, narrowed to the kernel's float dt), drift by dt
     const int rc = b200_leapfrog_host(ctx_, positions, velocities, forces, p.masses, num_particles, p.n_kicks,
                                       (float)(dt * 0.5), p.scale_factor, p.drift ? (float)dt : 0.0f, p.box_size);

@@ -87,9 +87,9 @@ def load_library(path=None):
     L.b200_tree_counters.argtypes = [vp, vp]
     L.b200_tree_walk_stats.argtypes = [vp, vp]
     L.b200_tree_overflowed.argtypes = [vp, C.POINTER(i32)]
-    L.b200_tree_build_part_dev.argtypes = [vp, vp, sz, f32, i32, i32, i32, i32, vp]
+    L.b200_tree_build_part_dev.argtypes = [vp, vp, vp, sz, f32, i32, i32, i32, i32, vp]
     L.b200_tree_forest_publish.argtypes = [vp, vp]
-    L.b200_tree_walk_list_dev.argtypes = [vp, vp, sz, f32, vp, i32, vp]
+    L.b200_tree_walk_list_dev.argtypes = [vp, vp, sz, f32, vp, vp]
     L.b200_tree_forest_root.argtypes = [vp, vp]
     L.b200_scatter_rows_dev.argtypes = [vp, vp, vp, sz, vp, vp]
     L.b200_gather_rows_dev.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
@@ -303,16 +303,19 @@ class Engine:
         return c
 
     # -- octant-sharded build / forest walk ------------------------------------
-    def tree_build_part_dev(self, posm, n, part, n_parts, box=100.0, leaf_cap=8, max_depth=20, stream=None):
-        self._check(self.L.b200_tree_build_part_dev(self._h, _ptr(posm), n, box, leaf_cap, max_depth, part, n_parts,
-                                                    _stream(stream)))
+    def tree_build_part_dev(self, posm, n, part=0, n_parts=1, box=100.0, leaf_cap=8, max_depth=20, arrival=None,
+                            stream=None):
+        """Part `part` of an octant-sharded build (n_parts = 1: the whole tree); arrival: device int32[n], slot of
+        the k-th particle in the reference's insertion order (None: stored in insertion order)."""
+        self._check(self.L.b200_tree_build_part_dev(self._h, _ptr(posm), _ptr(arrival), n, box, leaf_cap, max_depth,
+                                                    part, n_parts, _stream(stream)))
 
     def tree_forest_publish(self, stream=None):
         self._check(self.L.b200_tree_forest_publish(self._h, _stream(stream)))
 
-    def tree_walk_list_dev(self, acc, target_list, n_list=None, theta=0.5, forest=False, stream=None):
+    def tree_walk_list_dev(self, acc, target_list, n_list=None, theta=0.5, stream=None):
         n_list = target_list.shape[0] if n_list is None else n_list
-        self._check(self.L.b200_tree_walk_list_dev(self._h, _ptr(target_list), n_list, theta, _ptr(acc), int(forest),
+        self._check(self.L.b200_tree_walk_list_dev(self._h, _ptr(target_list), n_list, theta, _ptr(acc),
                                                    _stream(stream)))
         return acc
 

@@ -19,19 +19,24 @@ def _posm(p, m):
     return torch.from_numpy(np.ascontiguousarray(np.concatenate([p, m[:, None]], 1), np.float32)).cuda()
 
 
-def _build_forest(engine, posm, n, n_parts, **kw):
+def _build_forest(engine, posm, n, n_parts, arrival=None, **kw):
     import torch
     exports = []
     for q in range(n_parts):
-        engine.tree_build_part_dev(posm, n, q, n_parts, **kw)
-        engine.tree_forest_publish()
+        engine.tree_build_part_dev(posm, n, q, n_parts, arrival=arrival, **kw)
+        if n_parts > 1:
+            engine.tree_forest_publish()
         torch.cuda.synchronize()
         exports.append(engine.tree_export())
     return exports
 
 
-@pytest.mark.parametrize("gen,n_parts", [("uniform", 2), ("uniform", 8), ("clustered", 4), ("box", 8), ("uniform", 3)])
-def test_forest_topology_forces_counters(engine, oracle, gen, n_parts):
+@pytest.mark.parametrize("gen,n_parts,stored", [("uniform", 2, "index"), ("uniform", 8, "hilbert"), ("clustered", 4, "hilbert"),
+                                                ("box", 8, "index"), ("uniform", 3, "hilbert"), ("uniform", 1, "hilbert")])
+def test_forest_topology_forces_counters(engine, oracle, gen, n_parts, stored):
+    """stored = "hilbert": the particles are STORED along a Hilbert curve and the build gets the arrival order
+    (inverse permutation) -- the tree, its stored lists (mapped back to original indices) and the forces must still
+    be the reference's, which inserts in original index order."""
     import torch
     n = 60000
     if gen == "uniform":
@@ -43,42 +48,55 @@ def test_forest_topology_forces_counters(engine, oracle, gen, n_parts):
     p[100:130] = p[0:30]                                    # duplicates
     p[200:230, 0] = 0.0                                     # on the root's x boundary (strict > sends them low)
     m = masses_np(n, seed=24)
-    posm = _posm(p, m)
-    # the unsharded build + walk
-    engine.tree_build_dev(posm, n, 100.0, 8, 20)
+    posm0 = _posm(p, m)
+    # the unsharded build + walk on the particles in their original order
+    engine.tree_build_dev(posm0, n, 100.0, 8, 20)
     engine.tree_set_counting(True)
     acc0 = torch.empty((n, 3), dtype=torch.float32, device="cuda")
     engine.tree_walk_dev(acc0, 0, n, theta=0.5)
     torch.cuda.synchronize()
     cnt0 = engine.tree_counters()
     # the same targets as an explicit list on the unsharded tree
-    perm = torch.from_numpy(np.random.default_rng(5).permutation(n).astype(np.int32)).cuda()
+    shuffle = torch.from_numpy(np.random.default_rng(5).permutation(n).astype(np.int32)).cuda()
     acc_l = torch.empty((n, 3), dtype=torch.float32, device="cuda")
-    engine.tree_walk_list_dev(acc_l, perm, theta=0.5, forest=False)
+    engine.tree_walk_list_dev(acc_l, shuffle, theta=0.5)
     torch.cuda.synchronize()
-    assert np.array_equal(acc_l.cpu().numpy(), acc0.cpu().numpy()[perm.cpu().numpy()])
+    assert np.array_equal(acc_l.cpu().numpy(), acc0.cpu().numpy()[shuffle.cpu().numpy()])
     assert np.array_equal(engine.tree_counters(), cnt0)
-    # parts -> forest
-    exports = _build_forest(engine, posm, n, n_parts, box=100.0, leaf_cap=8, max_depth=20)
-    merged = merge_parts(exports, engine.tree_forest_root())
+    # storage order and arrival order
+    if stored == "hilbert":
+        perm = torch.empty(n, dtype=torch.int32, device="cuda")
+        engine.spatial_order_dev(posm0, n, 100.0, perm)           # perm[slot] = original index
+        posm = posm0[perm.long()].contiguous()
+        arrival = torch.empty_like(perm)
+        arrival[perm.long()] = torch.arange(n, dtype=torch.int32, device="cuda")      # arrival[original] = slot
+        slot_to_orig = perm.cpu().numpy()
+    else:
+        posm, arrival, slot_to_orig = posm0, None, np.arange(n)
+    exports = _build_forest(engine, posm, n, n_parts, arrival=arrival, box=100.0, leaf_cap=8, max_depth=20)
     o = oracle.tree_build(p, m)
+    if n_parts > 1:
+        merged = merge_parts(exports, engine.tree_forest_root())
+    else:
+        merged = exports[0]
+    merged["part_idx"] = slot_to_orig[merged["part_idx"]].astype(np.int32)
     for k in TREE_KEYS:
         assert np.array_equal(merged[k], getattr(o, k)), k
     acc1 = torch.empty((n, 3), dtype=torch.float32, device="cuda")
-    engine.tree_walk_list_dev(acc1, perm, theta=0.5, forest=True)
+    engine.tree_walk_dev(acc1, 0, n, theta=0.5)             # on a part-built context this walks the forest
     torch.cuda.synchronize()
     cnt1 = engine.tree_counters()
     engine.tree_set_counting(False)
     want, ocnt = oracle.tree_forces(o, p, 0.5, counters=True)
     assert np.array_equal(cnt1, ocnt) and np.array_equal(cnt0, ocnt), (cnt0, cnt1, ocnt)
-    a0, a1 = acc0.cpu().numpy()[perm.cpu().numpy()], acc1.cpu().numpy()
+    a0, a1 = acc0.cpu().numpy()[slot_to_orig], acc1.cpu().numpy()
     assert rel_l2(a1, a0) < 1e-6, rel_l2(a1, a0)
-    assert rel_l2(a1, want[perm.cpu().numpy()]) < 1e-5
-    # the shipped (non-counting) instance gives the same numbers
+    assert rel_l2(a1, want[slot_to_orig]) < 1e-5
+    # the shipped (non-counting) instance, explicit target list, gives the same numbers
     acc2 = torch.empty((n, 3), dtype=torch.float32, device="cuda")
-    engine.tree_walk_list_dev(acc2, perm, theta=0.5, forest=True)
+    engine.tree_walk_list_dev(acc2, shuffle, theta=0.5)
     torch.cuda.synchronize()
-    assert np.array_equal(acc2.cpu().numpy(), a1)
+    assert np.array_equal(acc2.cpu().numpy(), a1[shuffle.cpu().numpy()])
 
 
 def test_forest_state_errors(engine):
@@ -91,18 +109,18 @@ def test_forest_state_errors(engine):
     lst = torch.arange(n, dtype=torch.int32, device="cuda")
     engine.tree_build_part_dev(posm, n, 0, 2)
     engine.tree_forest_publish()
-    with pytest.raises(b200grav.B200Error):                 # part 1 was never published
-        engine.tree_walk_list_dev(acc, lst, forest=True)
+    with pytest.raises(b200grav.B200Error):                 # part 1 of THIS forest was never published (slots of
+        engine.tree_walk_list_dev(acc, lst)                 # earlier forests do not count)
     with pytest.raises(b200grav.B200Error):                 # a part alone is not the tree
         engine.tree_walk_dev(acc, 0, n)
     engine.tree_build_part_dev(posm, n, 1, 2)
     engine.tree_forest_publish()
-    engine.tree_walk_list_dev(acc, lst, forest=True)
+    engine.tree_walk_list_dev(acc, lst)
     torch.cuda.synchronize()
     assert np.isfinite(acc.cpu().numpy()).all()
     engine.tree_build_part_dev(posm, n, 0, 2)               # part 0 rebuilt: its slot is stale until published again
     with pytest.raises(b200grav.B200Error):
-        engine.tree_walk_list_dev(acc, lst, forest=True)
+        engine.tree_walk_list_dev(acc, lst)
     with pytest.raises(b200grav.B200Error):                 # the root does not split: nothing to shard
         engine.tree_build_part_dev(posm, 8, 0, 2)
     engine.tree_build_dev(posm, n, 100.0, 8, 20)            # back to a whole tree
@@ -126,7 +144,7 @@ def test_forest_full_size_16m_topology(engine, oracle):
         assert np.array_equal(merged[k], getattr(o, k)), k
     lst = torch.arange(3000000, 3000000 + 65536, dtype=torch.int32, device="cuda")
     acc = torch.empty((65536, 3), dtype=torch.float32, device="cuda")
-    engine.tree_walk_list_dev(acc, lst, theta=0.5, forest=True)
+    engine.tree_walk_list_dev(acc, lst, theta=0.5)
     torch.cuda.synchronize()
     want = oracle.tree_forces(o, p, 0.5, i0=3000000, n_targets=65536)
     assert rel_l2(acc.cpu().numpy(), want) < 1e-3

@@ -46,3 +46,17 @@ def test_example_program(args):
     print(r.stdout[-3000:], r.stderr[-1000:])
     assert r.returncode == 0, r.stderr[-1000:]
     assert "particle-updates/second" in r.stdout and "nan" not in r.stdout.lower()
+
+
+def test_engine_wiring_builder_run():
+    """the reference's SimulationBuilder / SimulationEngine with integration/engine_wiring.patch applied
+    (to a temporary copy of its sources, at build time) runs 10 KDK steps through DirectForceComputer /
+    TreeForceComputer on the B200 -- device-resident and through host arrays -- and lands on the CPU reference's
+    positions."""
+    exe = os.path.join(ROOT, "tests", "host", "_bin", "engine_wiring_test")
+    if not os.path.exists(exe):
+        pytest.skip("tests/host/_bin/engine_wiring_test not built (needs the reference sources at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-4000:], r.stderr[-2000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ENGINE WIRING OK" in r.stdout and "FAIL" not in r.stdout

@@ -94,21 +94,27 @@ def _forest_worker(rank, world, port, n, q):
     eng.shard_init(box[0], rank, world)
     pos = uniform_mt(n, seed=31)
     mass = masses_np(n, seed=32)
-    posm = torch.from_numpy(np.concatenate([pos, mass[:, None]], 1).astype(np.float32)).to(dev)
+    posm0 = torch.from_numpy(np.concatenate([pos, mass[:, None]], 1).astype(np.float32)).to(dev)
+    # particles STORED along a Hilbert curve (rank r owns the r-th run of slots), inserted in original index order
     perm = torch.empty(n, dtype=torch.int32, device=dev)
-    eng.spatial_order_dev(posm, n, 100.0, perm)
+    eng.spatial_order_dev(posm0, n, 100.0, perm)
+    posm = posm0[perm.long()].contiguous()
+    arrival = torch.empty_like(perm)
+    arrival[perm.long()] = torch.arange(n, dtype=torch.int32, device=dev)
     nl = n // world
-    own = perm[rank * nl:(rank + 1) * nl].contiguous()
     acc = torch.empty((nl, 3), dtype=torch.float32, device=dev)
     eng.tree_set_counting(True)
     for _ in range(2):                              # twice: slots are refilled, the build graph is replayed
-        eng.tree_build_part_dev(posm, n, rank, world)
+        eng.tree_build_part_dev(posm, n, rank, world, arrival=arrival)
         eng.tree_forest_publish()
-        eng.tree_walk_list_dev(acc, own, theta=0.5, forest=True)
+        eng.tree_walk_dev(acc, rank * nl, nl, theta=0.5)
         torch.cuda.synchronize()
     cnt = eng.tree_counters()
+    own = perm[rank * nl:(rank + 1) * nl]
+    exp = eng.tree_export()
+    exp["part_idx"] = perm.cpu().numpy()[exp["part_idx"]].astype(np.int32)      # slots -> original indices
     out = [None] * world
-    dist.all_gather_object(out, (own.cpu().numpy(), acc.cpu().numpy(), cnt, eng.tree_export(), eng.tree_forest_root()))
+    dist.all_gather_object(out, (own.cpu().numpy(), acc.cpu().numpy(), cnt, exp, eng.tree_forest_root()))
     dist.barrier()
     eng.shard_finalize()
     eng.close()
