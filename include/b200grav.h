@@ -226,7 +226,7 @@ int b200_tree_forces_fixed_host(b200_ctx* ctx, const float* pos3, const float* m
  * n_parts == 1 builds the whole tree (b200_tree_build_dev with an arrival order).
  *
  * b200_tree_forest_publish makes the part's walk tables visible to all walkers: over NCCL when the context has a
- * communicator of exactly n_parts ranks with rank == part (b200_shard_init; collective: table sizes by an 8-byte
+ * communicator of exactly n_parts ranks with rank == part (b200_shard_init; collective: table sizes and level-1 centres of mass by a 160-byte
  * all-gather + host read-back, then one grouped broadcast per table and owner), otherwise into this context's own
  * slot (one process building the parts in turn -- it must rebuild and publish EVERY part after particles move).
  * When every part is current the root's centre of mass is merged from the parts' level-1 nodes in the

@@ -75,7 +75,7 @@ struct TreeState {
     DevBuf ent_idx[2], ent_node[2], digit;
     DevBuf part_idx, part_pos;
     DevBuf nodes;                 // walk records, 32 B per node: {centre of mass, M} {first, skip, edge, leaf count}
-    DevBuf leaf_pos, leaf_off, lscan, pscan, leaf_tile_sum;   // leaf sources grouped by parent, pair-interleaved (walk-only)
+    DevBuf leaf_pos, leaf_off, lscan, pscan, cscan, leaf_tile_sum;   // leaf sources grouped by parent, pair-interleaved (walk-only)
     DevBuf slot_node;             // node that stores slot q of part_idx
     DevBuf globals;
     DevBuf tile_hist, tile_warp_prefix, node_tile_sum;
@@ -117,7 +117,7 @@ struct TreeState {
         mix(bb); mix(eb);
         const DevBuf* all[] = {&center, &com, &meta, &nstart, &ncount, &nsplit_rank, &ent_idx[0], &ent_idx[1],
                                &ent_node[0], &ent_node[1], &digit, &part_idx, &part_pos, &nodes, &leaf_pos,
-                               &leaf_off, &lscan, &pscan, &leaf_tile_sum, &slot_node, &globals, &tile_hist,
+                               &leaf_off, &lscan, &pscan, &cscan, &leaf_tile_sum, &slot_node, &globals, &tile_hist,
                                &tile_warp_prefix, &node_tile_sum, &split_node, &split_where, &split_local,
                                &split_cstart};
         for (const DevBuf* b : all) mix((size_t)b->p);
@@ -137,7 +137,7 @@ struct TreeState {
         if (ev_out) cudaEventDestroy(ev_out);
         ev_in = ev_out = nullptr;
         DevBuf* all[] = {&center, &com, &meta, &nstart, &ncount, &nsplit_rank, &ent_idx[0],
-                         &ent_idx[1], &ent_node[0], &ent_node[1], &digit, &part_idx, &part_pos, &nodes, &leaf_pos, &leaf_off, &lscan, &pscan, &leaf_tile_sum, &slot_node,
+                         &ent_idx[1], &ent_node[0], &ent_node[1], &digit, &part_idx, &part_pos, &nodes, &leaf_pos, &leaf_off, &lscan, &pscan, &cscan, &leaf_tile_sum, &slot_node,
                          &globals, &tile_hist, &tile_warp_prefix, &node_tile_sum, &split_node,
                          &split_where, &split_local, &split_cstart, &keys, &keys_sorted, &perm,
                          &sort_scratch, &order};
@@ -669,6 +669,8 @@ pair_pad_kernel(const TreeGlobals* __restrict__ g, int max_depth, const int* __r
 // summed by the whole warp instead: coalesced gathers, then every lane replays the
 // SAME sequential sum from shuffled values, so the result keeps the reference's
 // summation order bit for bit while the memory latency is paid once per 32 particles.
+constexpr int COM_HUGE = 2048;       // leaves above this size (max-depth overflow leaves only) go to com_huge_kernel
+
 __global__ void __launch_bounds__(256)
 com_kernel(const TreeGlobals* __restrict__ g, int level, int4* __restrict__ meta,
            const float4* __restrict__ center, const int* __restrict__ part_idx,
@@ -681,9 +683,10 @@ com_kernel(const TreeGlobals* __restrict__ g, int level, int4* __restrict__ meta
         const bool have = i < n_nodes;
         const int k = L.node_begin + (have ? i : 0);
         const int4 m = have ? meta[k] : make_int4(0, 0, 0, 0);
-        const bool big = have && m.x < 0 && m.w > 64;
+        const bool huge = have && m.x < 0 && m.w > COM_HUGE;      // summed by a whole CTA afterwards
+        const bool big = have && m.x < 0 && m.w > 64 && !huge;
         float total = 0.f, wx = 0.f, wy = 0.f, wz = 0.f;
-        if (have && !big) {
+        if (have && !big && !huge) {
             if (m.x < 0) {
                 for (int q = m.z; q < m.z + m.w; ++q) {
                     const float4 p = posm[part_idx[q]];
@@ -728,7 +731,7 @@ com_kernel(const TreeGlobals* __restrict__ g, int level, int4* __restrict__ meta
         }
         if (have && m.x >= 0)       // walk-only field: an internal node's cell edge rides in meta.w
             meta[k].w = __float_as_int(center[k].w);
-        if (have) {
+        if (have && !huge) {
             float4 o = make_float4(0.f, 0.f, 0.f, total);
             if (total > 0.f) {
                 o.x = __fdiv_rn(wx, total);
@@ -737,6 +740,73 @@ com_kernel(const TreeGlobals* __restrict__ g, int level, int4* __restrict__ meta
             }
             com[k] = o;
         }
+    }
+}
+
+// Leaves of the deepest level that hold thousands of particles (inputs outside the root cube pile up in the
+// corner cell: the reference generators' [0, box) convention puts N/8 particles into ONE max-depth leaf).  The sum is
+// sequential by definition (:203-215, FP32, insertion order), so one thread adds -- but the whole CTA feeds it:
+// 1024-particle tiles are gathered and multiplied by all threads into shared memory, double-buffered, while
+// thread 0 runs the four dependent add chains of the previous tile (~4 cycles per particle; the per-warp version
+// above pays a dependent global gather every 32 particles: 5 ms for a 131 072-particle leaf, this one 0.4 ms).
+__global__ void __launch_bounds__(256)
+com_huge_kernel(const TreeGlobals* __restrict__ g, int level, const int4* __restrict__ meta,
+                const int* __restrict__ part_idx, const float4* __restrict__ posm, float4* __restrict__ com) {
+    constexpr int TILE = 1024;
+    __shared__ float4 prod[2][TILE];
+    __shared__ float4 acc_s;
+    const LevelInfo L = g->lv[level];
+    const int n_nodes = L.node_end - L.node_begin;
+    for (int i = blockIdx.x; i < n_nodes; i += gridDim.x) {
+        const int k = L.node_begin + i;
+        const int4 m = meta[k];
+        if (!(m.x < 0 && m.w > COM_HUGE)) continue;           // CTA-uniform
+        const int np = m.w, off = m.z;
+        const int n_tiles = (np + TILE - 1) / TILE;
+        float4 r[4];
+        auto fetch = [&](int tile) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int q = tile * TILE + j * 256 + threadIdx.x;
+                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q < np) p = posm[part_idx[off + q]];
+                r[j] = make_float4(__fmul_rn(p.x, p.w), __fmul_rn(p.y, p.w), __fmul_rn(p.z, p.w), p.w);
+            }
+        };
+        auto stash = [&](int buf) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) prod[buf][j * 256 + threadIdx.x] = r[j];
+        };
+        if (threadIdx.x == 0) acc_s = make_float4(0.f, 0.f, 0.f, 0.f);
+        fetch(0);
+        stash(0);
+        __syncthreads();
+        for (int t = 0; t < n_tiles; ++t) {
+            if (t + 1 < n_tiles) fetch(t + 1);                 // loads in flight while thread 0 adds
+            if (threadIdx.x == 0) {
+                float4 a = acc_s;
+                const int cnt = min(TILE, np - t * TILE);
+                const float4* src = prod[t & 1];
+#pragma unroll 8
+                for (int j = 0; j < cnt; ++j) {
+                    const float4 v = src[j];
+                    a.w = __fadd_rn(a.w, v.w);
+                    a.x = __fadd_rn(a.x, v.x);
+                    a.y = __fadd_rn(a.y, v.y);
+                    a.z = __fadd_rn(a.z, v.z);
+                }
+                acc_s = a;
+            }
+            if (t + 1 < n_tiles) stash((t + 1) & 1);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const float4 a = acc_s;
+            float4 o = make_float4(0.f, 0.f, 0.f, a.w);
+            if (a.w > 0.f) { o.x = __fdiv_rn(a.x, a.w); o.y = __fdiv_rn(a.y, a.w); o.z = __fdiv_rn(a.z, a.w); }
+            com[k] = o;
+        }
+        __syncthreads();
     }
 }
 
@@ -749,13 +819,17 @@ com_kernel(const TreeGlobals* __restrict__ g, int level, int4* __restrict__ meta
 // depth-first order inside or after X's children, `skip` = first internal node after X's subtree.
 // The two scans of the build tail share one set of kernels:
 //   MODE 0, item = node k:           particles stored in k if k is a leaf            -> lscan
+//   MODE 2, item = node k:           1 if k is internal -> cscan: COMPACT id of an internal node.  The walk
+//                                    records are stored by compact id (an eighth of the node count), links
+//                                    included: denser in L1/L2 and an eighth of the bytes to exchange.
 //   MODE 1, item = sibling group j   (nodes 1+8j .. 8+8j, the children of one internal node):
 //                                    source PAIRS of the group = ceil(leaf particles / 2) -> pscan
 template <int MODE>
-__device__ __forceinline__ int scan_items(int nn) { return MODE == 0 ? nn : (nn - 1) / 8; }
+__device__ __forceinline__ int scan_items(int nn) { return MODE == 1 ? (nn - 1) / 8 : nn; }
 template <int MODE>
 __device__ __forceinline__ int scan_value(int k, const int4* __restrict__ meta, const int* __restrict__ lscan) {
     if (MODE == 0) { const int4 m = meta[k]; return m.x < 0 ? m.w : 0; }
+    if (MODE == 2) return meta[k].x >= 0 ? 1 : 0;
     return (lscan[9 + 8 * k] - lscan[1 + 8 * k] + 1) >> 1;
 }
 
@@ -866,20 +940,17 @@ leaf_apply_kernel(const TreeGlobals* __restrict__ g, int max_depth, const int4* 
 }
 // walk records of the internal nodes (and of a root that is a leaf: first = ROOT_LEAF)
 constexpr int ROOT_LEAF = -2;
+constexpr int FOREST_HDR_INTS = 40;     // per part: {records, source pairs, 6 pad} + the 8 level-1 {com, M}
 __global__ void __launch_bounds__(256)
 pack_walk_kernel(const TreeGlobals* __restrict__ g, int max_depth, const float4* __restrict__ com,
                  const int4* __restrict__ meta, const int* __restrict__ lscan, const int* __restrict__ pscan,
-                 float4* __restrict__ nodes, int* __restrict__ leaf_off, int* __restrict__ hdr) {
+                 const int* __restrict__ cscan, float4* __restrict__ nodes, int* __restrict__ leaf_off,
+                 int* __restrict__ hdr) {
     const int nn = tree_node_count(g, max_depth);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nn; k += gridDim.x * blockDim.x) {
         const int4 m = meta[k];
-        if (m.x < 0 && k != 0) {
-            if (k <= 8) {                            // the root's children: the forest's root record is merged from these
-                nodes[2 * k] = com[k];
-                nodes[2 * k + 1] = make_float4(__int_as_float(-1), __int_as_float(-1), 0.f, 0.f);
-            }
-            continue;
-        }
+        if (hdr && k >= 1 && k <= 8) reinterpret_cast<float4*>(hdr + 8)[k - 1] = com[k];   // forest: root merge input
+        if (m.x < 0 && k != 0) continue;
         int first, skip = -1, loff, lcnt;
         // the walk visits internal nodes that carry mass; everything else is stepped over here, once
         auto stepped_over = [&](int j) { return meta[j].x < 0 || com[j].w == 0.0f; };     // leaf, or :260
@@ -890,16 +961,19 @@ pack_walk_kernel(const TreeGlobals* __restrict__ g, int max_depth, const float4*
             while (first >= 0 && stepped_over(first)) first = meta[first].y;
             skip = m.y;
             while (skip >= 0 && stepped_over(skip)) skip = meta[skip].y;
+            if (first >= 0) first = cscan[first];           // links are compact ids
+            if (skip >= 0) skip = cscan[skip];
             loff = pscan[(m.x - 1) >> 3];                   // first source pair of the children
             lcnt = lscan[m.x + 8] - lscan[m.x];             // leaf particles among them
         }
-        nodes[2 * k] = com[k];
-        nodes[2 * k + 1] = make_float4(__int_as_float(first), __int_as_float(skip), __int_as_float(m.w),
-                                       __int_as_float(lcnt));      // m.w of an internal node = cell edge bits
-        leaf_off[k] = loff;
+        const int cid = cscan[k];                           // 0 for the root, internal or not
+        nodes[2 * cid] = com[k];
+        nodes[2 * cid + 1] = make_float4(__int_as_float(first), __int_as_float(skip), __int_as_float(m.w),
+                                         __int_as_float(lcnt));      // m.w of an internal node = cell edge bits
+        leaf_off[cid] = loff;
     }
     if (hdr && blockIdx.x == 0 && threadIdx.x == 0) {       // sizes of this part's walk tables
-        hdr[0] = nn;
+        hdr[0] = cscan[nn] > 0 ? cscan[nn] : 1;
         hdr[1] = nn > 1 ? pscan[(nn - 1) / 8] : (lscan[1] + 1) / 2;
     }
 }
@@ -913,10 +987,10 @@ struct ForestTables {
     int owner[8];                 // part that owns octant d
     int n_parts;
 };
-__global__ void forest_root_kernel(ForestTables F, float4* __restrict__ root) {
+__global__ void forest_root_kernel(ForestTables F, const int* __restrict__ hdr, float4* __restrict__ root) {
     float total = 0.f, wx = 0.f, wy = 0.f, wz = 0.f;
     for (int d = 0; d < 8; ++d) {
-        const float4 c = F.nodes[F.owner[d]][2 * (1 + d)];
+        const float4 c = reinterpret_cast<const float4*>(hdr + F.owner[d] * FOREST_HDR_INTS + 8)[d];
         if (c.w > 0.f) {
             total = __fadd_rn(total, c.w);
             wx = __fadd_rn(wx, __fmul_rn(c.x, c.w));
@@ -1378,7 +1452,7 @@ static int tree_build_impl(b200_ctx* ctx, const void* posm4, const int* arrival,
     T->arrival = arrival;
     T->oct_mask = n_parts > 1 ? part_octants(part, n_parts) : 0xffu;
     if (n_parts > 1) {
-        B200_TRY(T->forest_hdr.reserve(8 * 2 * sizeof(int)));
+        B200_TRY(T->forest_hdr.reserve(8 * FOREST_HDR_INTS * sizeof(int)));
         // The slots belong to one forest: same particle array, arrival order, sizes and parameters.  Every rank of
         // a communicator rebuilds its part in the same step, so all slots go stale together; a single process
         // playing all parts (tests) replaces them one at a time -- and must rebuild every part after the
@@ -1414,12 +1488,13 @@ static int tree_build_impl(b200_ctx* ctx, const void* posm4, const int* arrival,
     B200_TRY(T->digit.reserve(n));
     B200_TRY(T->part_idx.reserve(n * sizeof(int)));
     B200_TRY(T->part_pos.reserve(n * sizeof(float4)));
-    B200_TRY(T->nodes.reserve(T->max_nodes * 2 * sizeof(float4)));
+    B200_TRY(T->nodes.reserve((T->max_split + 2) * 2 * sizeof(float4)));     // walk records: internal nodes only
     B200_TRY(T->leaf_pos.reserve((n + T->max_split + 2) * sizeof(float4)));     // pair layout: <= 1 pad slot per parent
     B200_TRY(T->pscan.reserve((T->max_split + 2) * sizeof(int)));
     B200_TRY(T->slot_node.reserve(n * sizeof(int)));
-    B200_TRY(T->leaf_off.reserve(T->max_nodes * sizeof(int)));
+    B200_TRY(T->leaf_off.reserve((T->max_split + 2) * sizeof(int)));
     B200_TRY(T->lscan.reserve((T->max_nodes + 1) * sizeof(int)));
+    B200_TRY(T->cscan.reserve((T->max_nodes + 1) * sizeof(int)));
     B200_TRY(T->leaf_tile_sum.reserve(T->max_node_tiles * sizeof(int)));
     B200_TRY(T->globals.reserve(sizeof(TreeGlobals)));
     B200_TRY(T->tile_hist.reserve(T->max_tiles * 8 * sizeof(unsigned)));
@@ -1539,6 +1614,10 @@ static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st) {
         const int cgrid = (int)((nb + 255) / 256 < (size_t)pgrid ? (nb + 255) / 256 : (size_t)pgrid);
         com_kernel<<<cgrid, 256, 0, st>>>(g, L, meta, center, T->part_idx.as<int>(), T->posm, com);
         ctx->launches += 1;
+        if (L == max_depth || leaf_cap > COM_HUGE) {          // only the deepest level can hold leaves above leaf_cap
+            com_huge_kernel<<<ctx->sm_count, 256, 0, st>>>(g, L, meta, T->part_idx.as<int>(), T->posm, com);
+            ctx->launches += 1;
+        }
     }
     // walk-only structures: leaf particles grouped by parent, records with leaf-skipping links
     int* lscan = T->lscan.as<int>();
@@ -1547,6 +1626,10 @@ static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st) {
     leaf_reduce_kernel<0><<<pgrid, 256, 0, st>>>(g, max_depth, meta, nullptr, tsum);
     leaf_scan_kernel<0><<<1, 1024, 0, st>>>(g, max_depth, tsum);
     leaf_apply_kernel<0><<<pgrid, 256, 0, st>>>(g, max_depth, meta, nullptr, tsum, lscan);
+    int* cscan = T->cscan.as<int>();
+    leaf_reduce_kernel<2><<<pgrid, 256, 0, st>>>(g, max_depth, meta, nullptr, tsum);
+    leaf_scan_kernel<2><<<1, 1024, 0, st>>>(g, max_depth, tsum);
+    leaf_apply_kernel<2><<<pgrid, 256, 0, st>>>(g, max_depth, meta, nullptr, tsum, cscan);
     leaf_reduce_kernel<1><<<pgrid, 256, 0, st>>>(g, max_depth, meta, lscan, tsum);
     leaf_scan_kernel<1><<<1, 1024, 0, st>>>(g, max_depth, tsum);
     leaf_apply_kernel<1><<<pgrid, 256, 0, st>>>(g, max_depth, meta, lscan, tsum, pscan);
@@ -1554,10 +1637,10 @@ static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st) {
         g, T->part_idx.as<int>(), T->slot_node.as<int>(), meta, lscan, pscan, T->posm, (int)n,
         T->part_pos.as<float4>(), T->leaf_pos.as<float>(), fixed ? 1 : 0);
     pair_pad_kernel<<<pgrid, 256, 0, st>>>(g, max_depth, lscan, pscan, T->leaf_pos.as<float>(), fixed ? 1 : 0);
-    pack_walk_kernel<<<pgrid, 256, 0, st>>>(g, max_depth, com, meta, lscan, pscan, T->nodes.as<float4>(),
+    pack_walk_kernel<<<pgrid, 256, 0, st>>>(g, max_depth, com, meta, lscan, pscan, cscan, T->nodes.as<float4>(),
                                             T->leaf_off.as<int>(),
-                                            T->forest_hdr.p ? T->forest_hdr.as<int>() + 2 * T->part : nullptr);
-    ctx->launches += 9;
+                                            T->forest_hdr.p ? T->forest_hdr.as<int>() + FOREST_HDR_INTS * T->part : nullptr);
+    ctx->launches += 12;
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }
@@ -1665,7 +1748,7 @@ __global__ void set_forest_kernel(ForestTables F, ForestTables* dst) { *dst = F;
 
 // Makes this part's walk tables (node records, leaf offsets, leaf source pairs) available to every walker:
 // with a communicator of n_parts ranks (b200_shard_init) the parts exchange their tables over NCCL -- sizes first
-// (one 8-byte all-gather and a host read-back), then one grouped broadcast per table and owner; without one (a
+// (one 160-byte all-gather and a host read-back), then one grouped broadcast per table and owner; without one (a
 // single process building the parts one after another) the tables are copied into this context's slot.
 // When all slots are current the merged root record and the table directory are written.
 int tree_forest_publish(b200_ctx* ctx, cudaStream_t st) {
@@ -1676,10 +1759,11 @@ int tree_forest_publish(b200_ctx* ctx, cudaStream_t st) {
     shard_info(ctx, &rank, &world);
     const bool collective = ctx->shard != nullptr && world > 1;
     if (collective && (world != P || rank != part)) return B200_ERR_STATE;
-    if (!T->forest_hdr_host) B200_CUDA(cudaMallocHost((void**)&T->forest_hdr_host, 16 * sizeof(int)));
+    constexpr size_t HDR_BYTES = FOREST_HDR_INTS * sizeof(int);
+    if (!T->forest_hdr_host) B200_CUDA(cudaMallocHost((void**)&T->forest_hdr_host, 8 * HDR_BYTES));
     int* hdr = T->forest_hdr.as<int>();
-    if (collective) B200_TRY(shard_allgather_bytes(ctx, hdr + 2 * part, hdr, 2 * sizeof(int), st));
-    B200_CUDA(cudaMemcpyAsync(T->forest_hdr_host, hdr, 16 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (collective) B200_TRY(shard_allgather_bytes(ctx, hdr + FOREST_HDR_INTS * part, hdr, HDR_BYTES, st));
+    B200_CUDA(cudaMemcpyAsync(T->forest_hdr_host, hdr, 8 * HDR_BYTES, cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     {
         TreeGlobals* g = T->globals.as<TreeGlobals>();
@@ -1692,9 +1776,9 @@ int tree_forest_publish(b200_ctx* ctx, cudaStream_t st) {
     for (int q = 0; q < P; ++q) {
         if (!collective && q != part) continue;
         TreeState::ForestSlot& f = T->forest[q];
-        f.nn = (size_t)T->forest_hdr_host[2 * q];
-        f.npairs = (size_t)T->forest_hdr_host[2 * q + 1];
-        if (f.nn < 9) return B200_ERR_STATE;
+        f.nn = (size_t)T->forest_hdr_host[FOREST_HDR_INTS * q];            // walk records (internal nodes)
+        f.npairs = (size_t)T->forest_hdr_host[FOREST_HDR_INTS * q + 1];
+        if (f.nn < 1) return B200_ERR_STATE;
         B200_TRY(f.nodes.reserve(f.nn * 2 * sizeof(float4)));
         B200_TRY(f.leaf_off.reserve(f.nn * sizeof(int)));
         B200_TRY(f.leaf_pairs.reserve((f.npairs + 1) * 2 * sizeof(float4)));
@@ -1726,7 +1810,7 @@ int tree_forest_publish(b200_ctx* ctx, cudaStream_t st) {
         }
         // forest_root buffer: [0, 32) the merged root record, [64, 64 + sizeof F) the table directory
         B200_TRY(T->forest_root.reserve(64 + sizeof(ForestTables)));
-        forest_root_kernel<<<1, 1, 0, st>>>(F, T->forest_root.as<float4>());
+        forest_root_kernel<<<1, 1, 0, st>>>(F, hdr, T->forest_root.as<float4>());
         set_forest_kernel<<<1, 1, 0, st>>>(F, (ForestTables*)(T->forest_root.as<char>() + 64));
         ctx->launches += 2;
         B200_CUDA(cudaGetLastError());

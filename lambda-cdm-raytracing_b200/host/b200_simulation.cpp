@@ -35,6 +35,7 @@ B200LambdaCDMSimulation::~B200LambdaCDMSimulation() {
     b200_device_free(ctx_, d_vel_);
     b200_device_free(ctx_, d_acc_);
     b200_device_free(ctx_, d_tmp3_);
+    if (d_arrival_) b200_device_free(ctx_, d_arrival_);
     b200_ctx_destroy(ctx_);
 }
 
@@ -49,6 +50,7 @@ void B200LambdaCDMSimulation::enable_sharding(const unsigned char* nccl_unique_i
 void B200LambdaCDMSimulation::set_particles(const float* pos3, const float* vel3, const float* mass) {
     const size_t n = num_particles_;
     if (n == 0) return;
+    if (d_arrival_) { b200_device_free(ctx_, d_arrival_); d_arrival_ = nullptr; }      // stored in insertion order
     void* d_mass = nullptr;
     check(b200_memcpy_h2d(ctx_, d_tmp3_, pos3, n * 12, stream_), "upload positions");
     if (mass) {   // velocities' buffer doubles as the mass staging area before the velocities land
@@ -83,12 +85,18 @@ void B200LambdaCDMSimulation::set_particles_spatially_ordered(const float* pos3,
     b200_device_free(ctx_, d_perm);
     check(rc, "spatial order");
     std::vector<float> ps(3 * n), vs(3 * n), ms(mass ? n : 0);
+    std::vector<int> arrival(n);
     for (size_t k = 0; k < n; ++k) {
         const size_t i = (size_t)order_[k];
         for (int c = 0; c < 3; ++c) { ps[3 * k + c] = pos3[3 * i + c]; vs[3 * k + c] = vel3[3 * i + c]; }
         if (mass) ms[k] = mass[i];
+        arrival[i] = (int)k;                    // the caller's particle i sits in slot k
     }
     set_particles(ps.data(), vs.data(), mass ? ms.data() : nullptr);
+    // the reference-faithful tree depends on insertion order = the caller's index order: hand it to the build
+    if (!d_arrival_) check(b200_device_alloc(ctx_, n * sizeof(int), &d_arrival_), "alloc arrival order");
+    check(b200_memcpy_h2d(ctx_, d_arrival_, arrival.data(), n * sizeof(int), stream_), "upload arrival order");
+    check(b200_ctx_sync(ctx_, stream_), "sync");
 }
 
 void B200LambdaCDMSimulation::initialize_particles(uint32_t seed) {
@@ -200,9 +208,21 @@ void B200LambdaCDMSimulation::compute_forces() {
     // every rank sees all sources (replicated positions), and evaluates its own targets only
     if (method_ == B200ForceMethod::Tree || method_ == B200ForceMethod::TreeFixed ||
         method_ == B200ForceMethod::TreeFixedPeriodic) {
-        if (method_ == B200ForceMethod::Tree)
-            check(b200_tree_build_dev(ctx_, d_posm_, n, box_size_, leaf_capacity_, max_depth_, stream_), "tree build");
-        else
+        if (method_ == B200ForceMethod::Tree) {
+            // Sharded runs build the octree by octants: rank r only the subtrees of its own octants of the root, then
+            // the ranks exchange their walk tables (same tree, same forces; the replicated build was the part of a step
+            // that did not shrink with the GPU count).  Particles stored in space-filling order keep the reference's
+            // insertion order through the arrival array.
+            const bool by_octant = world_ > 1 && world_ <= 8 && n > (size_t)leaf_capacity_;
+            if (by_octant || d_arrival_) {
+                check(b200_tree_build_part_dev(ctx_, d_posm_, d_arrival_, n, box_size_, leaf_capacity_, max_depth_,
+                                               by_octant ? rank_ : 0, by_octant ? world_ : 1, stream_),
+                      "tree build (octant part)");
+                if (by_octant) check(b200_tree_forest_publish(ctx_, stream_), "tree table exchange");
+            } else {
+                check(b200_tree_build_dev(ctx_, d_posm_, n, box_size_, leaf_capacity_, max_depth_, stream_), "tree build");
+            }
+        } else
             check(b200_tree_build_fixed_dev(ctx_, d_posm_, n, leaf_capacity_, max_depth_, softening_, stream_),
                   "tree build (fixed physics)");
         check(b200_tree_set_periodic(ctx_, method_ == B200ForceMethod::TreeFixedPeriodic ? box_size_ : 0.0f),

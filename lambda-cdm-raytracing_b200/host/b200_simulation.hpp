@@ -62,6 +62,7 @@ class B200LambdaCDMSimulation {
     void* d_vel_ = nullptr;                 // float[3N]
     void* d_acc_ = nullptr;                 // float[3N]
     void* d_tmp3_ = nullptr;                // float[3N] staging
+    void* d_arrival_ = nullptr;             // int32[N]: slot of the caller's particle i (spatially ordered storage)
 
     // closing half-kick of the last step(), folded into the next step's kick-kick-drift pass
     mutable bool pending_kick_ = false;
@@ -93,7 +94,8 @@ public:
     // Same, but the particles are first put in space-filling-curve order (b200_spatial_order_dev; the cube is
     // centred on the origin for the tree methods and on box/2 otherwise): contiguous index ranges -- the shards
     // of a multi-GPU run -- become compact regions.  get_particle_order()[k] is the caller's index of stored
-    // particle k.
+    // particle k.  The Tree method still builds the reference's tree: particles are inserted in the caller's index
+    // order (arrival order handed to b200_tree_build_part_dev), wherever they are stored.
     void set_particles_spatially_ordered(const float* pos3, const float* vel3, const float* mass);
     const std::vector<int>& get_particle_order() const { return order_; }
     // Multi-GPU: call once, before set_particles/initialize_particles, on every rank with the

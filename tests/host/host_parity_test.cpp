@@ -259,6 +259,24 @@ int main() {
         CHECK(perm_ok && dmax < 1e-4 && jump / m_n < 12.0,
               "spatially ordered storage: same trajectories (max |dx| %.2e), neighbours in storage %.1f apart (L1)",
               dmax, jump / m_n);
+
+        // the reference-faithful tree depends on insertion order: stored along the curve, it must still be the tree of
+        // the caller's index order (arrival array) -- same node count, same forces particle for particle
+        physics::B200LambdaCDMSimulation c(m_n, 100.0f), d(m_n, 100.0f);
+        c.set_force_method(physics::B200ForceMethod::Tree);
+        d.set_force_method(physics::B200ForceMethod::Tree);
+        c.set_particles(pos.data(), v0.data(), mass.data());
+        d.set_particles_spatially_ordered(pos.data(), v0.data(), mass.data());
+        c.compute_forces();
+        d.compute_forces();
+        std::vector<float> fc(3 * m_n), fd(3 * m_n), fd_back(3 * m_n);
+        c.copy_forces_to_host(fc.data());
+        d.copy_forces_to_host(fd.data());
+        const std::vector<int>& ord2 = d.get_particle_order();
+        for (size_t k = 0; k < m_n; ++k)
+            for (int q = 0; q < 3; ++q) fd_back[3 * (size_t)ord2[k] + q] = fd[3 * k + q];
+        CHECK(rel_l2(fd_back, fc) < 1e-6, "faithful tree on spatially ordered storage == index-order storage (rel-L2 %.1e)",
+              rel_l2(fd_back, fc));
     }
 
     {   // device-generated initial conditions + the particle / power-spectrum accessors of the simulation class
