@@ -987,6 +987,13 @@ def bench_gpu(args):
     e2e_steps = max(2, min(args.steps, 5))
     e2e_s = e2e_time(False)
     e2e_page_s = e2e_time(True) if world == 1 and not args.kdk else None
+    e2e_reg_s = None
+    if e2e_page_s is not None:      # the same plain arrays, page-locked in place once (b200_host_register: what the
+        for a in (page_pos, page_mass, page_out):       # plugin's set_pin_host_arrays(true) does on first sight)
+            eng.host_register(a)
+        e2e_reg_s = e2e_time(True)
+        for a in (page_pos, page_mass, page_out):
+            eng.host_unregister(a)
 
     tree_counts = None
     if args.workload == "direct":
@@ -1028,6 +1035,11 @@ def bench_gpu(args):
                 "ms_per_step": 1e3 * e2e_page_s / e2e_steps,
                 "api": "the same call on plain (pageable) host arrays -- what IForceComputer::compute_forces receives "
                        "from the engine's unique_ptr<float[]> (simulation_engine.hpp:60-63)"}
+            line["e2e_registered"] = {
+                "value": per_step * e2e_steps / e2e_reg_s, "unit": "interactions/s",
+                "ms_per_step": 1e3 * e2e_reg_s / e2e_steps,
+                "api": "the same plain arrays after one b200_host_register (cudaHostRegister in place; the plugin's opt-in "
+                       "set_pin_host_arrays(true), switched on by integration/engine_wiring.patch for the engine's arrays)"}
     if args.workload == "direct":
         if rank == 0:
             achieved = FLOP_PER_INTERACTION * per_launch / kern_s / 1e12

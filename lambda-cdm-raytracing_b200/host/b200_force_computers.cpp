@@ -27,8 +27,24 @@ const forces::ForceComputeParameters* params_of(const std::any& a) {
 namespace forces {
 
 B200ComputerBase::~B200ComputerBase() {
+    unpin_all();
     if (ctx_) b200_ctx_destroy(ctx_);
     ctx_ = nullptr;
+}
+
+void B200ComputerBase::pin(const void* ptr, size_t bytes) {
+    if (!pin_host_arrays_ || !ctx_ || !ptr || bytes < (1u << 16)) return;        // small arrays: not worth a registration
+    for (const auto& r : pinned_)
+        if (r.first == ptr && r.second >= bytes) return;
+    for (auto it = pinned_.begin(); it != pinned_.end();)                       // same base, grown: register afresh
+        if (it->first == ptr) { b200_host_unregister(ctx_, const_cast<void*>(ptr)); it = pinned_.erase(it); } else ++it;
+    if (pinned_.size() >= 8) { b200_host_unregister(ctx_, const_cast<void*>(pinned_.front().first)); pinned_.erase(pinned_.begin()); }
+    if (b200_host_register(ctx_, const_cast<void*>(ptr), bytes) == B200_OK) pinned_.emplace_back(ptr, bytes);
+}
+
+void B200ComputerBase::unpin_all() {
+    if (ctx_) for (const auto& r : pinned_) b200_host_unregister(ctx_, const_cast<void*>(r.first));
+    pinned_.clear();
 }
 
 bool B200ComputerBase::initialize(const core::SimulationContext& context) {
@@ -48,6 +64,7 @@ bool B200ComputerBase::initialize(const core::SimulationContext& context) {
 }
 
 void B200ComputerBase::finalize() {
+    unpin_all();
     if (ctx_) {
         b200_ctx_destroy(ctx_);
         ctx_ = nullptr;
@@ -64,6 +81,7 @@ void B200ComputerBase::use_device(int device) {
     b200_ctx* fresh = nullptr;
     const int rc = b200_ctx_create(device, 0, &fresh);
     if (rc != B200_OK) fail((get_type() + ": cuda_device_id " + std::to_string(device)).c_str(), rc);
+    unpin_all();
     if (ctx_) b200_ctx_destroy(ctx_);
     ctx_ = fresh;
     device_ = device;
@@ -79,6 +97,7 @@ void DirectForceComputer::compute_forces(const float* positions, const float* ma
     require_ctx();
     float eps = softening_;
     if (const ForceComputeParameters* p = params_of(params)) { eps = p->softening_length; use_device(p->cuda_device_id); }
+    pin(positions, num_particles * 12); pin(masses, num_particles * 4); pin(forces, num_particles * 12);
     const int rc = b200_direct_forces_host(ctx_, positions, masses, forces, num_particles, eps, box_size_);
     if (rc != B200_OK) {
         std::cerr << "DirectForceComputer::compute_forces failed: " << b200_error_string(rc) << std::endl;
@@ -99,6 +118,7 @@ void B200TreeForceComputer::compute_forces(const float* positions, const float* 
         theta = p->theta; cap = p->leaf_capacity; depth = p->tree_max_depth; eps = p->softening_length;
         use_device(p->cuda_device_id);
     }
+    pin(positions, num_particles * 12); pin(masses, num_particles * 4); pin(forces, num_particles * 12);
     const int rc = fixed_physics_
                        ? b200_tree_forces_fixed_host(ctx_, positions, masses, forces, num_particles, theta, (int)cap,
                                                      depth, eps)

@@ -27,6 +27,8 @@
 #include <cstddef>
 #include <memory>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "core/interfaces.hpp"
 #include "forces/force_computer_factory.hpp"
@@ -47,6 +49,13 @@ protected:
     explicit B200ComputerBase(const std::string& name) : name_(name) {}
     void require_ctx() const;
     void use_device(int device);               // ForceComputeParameters::cuda_device_id
+    // Opt-in (set_pin_host_arrays): page-lock the caller's arrays the first time they are seen, so that the host
+    // entry points copy at DMA speed instead of through the driver's pageable staging.  Only for callers whose
+    // arrays outlive this object's finalize() -- the engine's particle arrays do (simulation_engine.hpp:60-63).
+    bool pin_host_arrays_ = false;
+    std::vector<std::pair<const void*, size_t>> pinned_;
+    void pin(const void* ptr, size_t bytes);
+    void unpin_all();
 
 public:
     ~B200ComputerBase() override;
@@ -59,6 +68,7 @@ public:
     size_t get_max_particles() const override { return max_particles_; }
     void set_max_particles(size_t n) { max_particles_ = n; }
     void set_cuda_device(int device) { device_ = device; }
+    void set_pin_host_arrays(bool on) { pin_host_arrays_ = on; if (!on) unpin_all(); }
     size_t get_force_evaluations() const { return force_evaluations_; }
     b200_ctx* native_handle() const { return ctx_; }
 };
