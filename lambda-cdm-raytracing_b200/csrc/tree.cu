@@ -74,8 +74,9 @@ struct TreeState {
     DevBuf center, com, meta, nstart, ncount, nsplit_rank;
     DevBuf ent_idx[2], ent_node[2], digit;
     DevBuf part_idx, part_pos;
-    DevBuf nodes;                 // walk records, 32 B per node: {centre of mass, M} {first, skip, edge, leaf count}
-    DevBuf leaf_pos, leaf_off, lscan, pscan, cscan, leaf_tile_sum;   // leaf sources grouped by parent, pair-interleaved (walk-only)
+    DevBuf nodes;                 // walk records, 32 B each, depth-first order: {centre of mass, M} {skip, first leaf pair, edge, leaf count}
+    DevBuf leaf_pos, lscan, pscan, leaf_tile_sum;   // leaf sources grouped by parent, pair-interleaved (walk-only)
+    DevBuf sub;                   // walk records in the subtree of a node (0: leaf or massless)
     DevBuf slot_node;             // node that stores slot q of part_idx
     DevBuf globals;
     DevBuf tile_hist, tile_warp_prefix, node_tile_sum;
@@ -100,7 +101,7 @@ struct TreeState {
     const int* arrival = nullptr;
     size_t forest_key = 0;        // (posm, arrival, n, box, cap, depth, n_parts) of the forest the slots belong to
     struct ForestSlot {
-        DevBuf nodes, leaf_off, leaf_pairs;
+        DevBuf nodes, leaf_pairs;
         size_t nn = 0, npairs = 0;
         bool valid = false;
     } forest[8];
@@ -117,7 +118,7 @@ struct TreeState {
         mix(bb); mix(eb);
         const DevBuf* all[] = {&center, &com, &meta, &nstart, &ncount, &nsplit_rank, &ent_idx[0], &ent_idx[1],
                                &ent_node[0], &ent_node[1], &digit, &part_idx, &part_pos, &nodes, &leaf_pos,
-                               &leaf_off, &lscan, &pscan, &cscan, &leaf_tile_sum, &slot_node, &globals, &tile_hist,
+                               &lscan, &pscan, &sub, &leaf_tile_sum, &slot_node, &globals, &tile_hist,
                                &tile_warp_prefix, &node_tile_sum, &split_node, &split_where, &split_local,
                                &split_cstart};
         for (const DevBuf* b : all) mix((size_t)b->p);
@@ -129,7 +130,7 @@ struct TreeState {
     }
     void release() {
         drop_graph();
-        for (ForestSlot& f : forest) { f.nodes.release(); f.leaf_off.release(); f.leaf_pairs.release(); f.valid = false; }
+        for (ForestSlot& f : forest) { f.nodes.release(); f.leaf_pairs.release(); f.valid = false; }
         forest_root.release(); forest_hdr.release();
         if (forest_hdr_host) cudaFreeHost(forest_hdr_host);
         forest_hdr_host = nullptr;
@@ -137,7 +138,7 @@ struct TreeState {
         if (ev_out) cudaEventDestroy(ev_out);
         ev_in = ev_out = nullptr;
         DevBuf* all[] = {&center, &com, &meta, &nstart, &ncount, &nsplit_rank, &ent_idx[0],
-                         &ent_idx[1], &ent_node[0], &ent_node[1], &digit, &part_idx, &part_pos, &nodes, &leaf_pos, &leaf_off, &lscan, &pscan, &cscan, &leaf_tile_sum, &slot_node,
+                         &ent_idx[1], &ent_node[0], &ent_node[1], &digit, &part_idx, &part_pos, &nodes, &leaf_pos, &lscan, &pscan, &sub, &leaf_tile_sum, &slot_node,
                          &globals, &tile_hist, &tile_warp_prefix, &node_tile_sum, &split_node,
                          &split_where, &split_local, &split_cstart, &keys, &keys_sorted, &perm,
                          &sort_scratch, &order};
@@ -674,7 +675,7 @@ constexpr int COM_HUGE = 2048;       // leaves above this size (max-depth overfl
 __global__ void __launch_bounds__(256)
 com_kernel(const TreeGlobals* __restrict__ g, int level, int4* __restrict__ meta,
            const float4* __restrict__ center, const int* __restrict__ part_idx,
-           const float4* __restrict__ posm, float4* __restrict__ com) {
+           const float4* __restrict__ posm, float4* __restrict__ com, int* __restrict__ sub) {
     const LevelInfo L = g->lv[level];
     const int n_nodes = L.node_end - L.node_begin;
     const int lane = threadIdx.x & 31;
@@ -686,6 +687,7 @@ com_kernel(const TreeGlobals* __restrict__ g, int level, int4* __restrict__ meta
         const bool huge = have && m.x < 0 && m.w > COM_HUGE;      // summed by a whole CTA afterwards
         const bool big = have && m.x < 0 && m.w > 64 && !huge;
         float total = 0.f, wx = 0.f, wy = 0.f, wz = 0.f;
+        int records = 0;             // walk records in this subtree: internal nodes that carry mass (the walk's visits)
         if (have && !big && !huge) {
             if (m.x < 0) {
                 for (int q = m.z; q < m.z + m.w; ++q) {
@@ -705,9 +707,12 @@ com_kernel(const TreeGlobals* __restrict__ g, int level, int4* __restrict__ meta
                         wy = __fadd_rn(wy, __fmul_rn(c.y, c.w));
                         wz = __fadd_rn(wz, __fmul_rn(c.z, c.w));
                     }
+                    records += sub[m.x + d];
                 }
+                records = (total == 0.0f) ? 0 : records + 1;      // :260 -- a massless cell ends the descent
             }
         }
+        if (have) sub[k] = records;                              // leaves: 0
         unsigned todo = __ballot_sync(FULL, big);
         while (todo) {
             const int src = __ffs(todo) - 1;
@@ -815,13 +820,14 @@ com_huge_kernel(const TreeGlobals* __restrict__ g, int level, const int4* __rest
 // ALL of X's leaf children (:268-270 makes no distance test for leaves), so those particles are
 // laid out contiguously per parent (leaf nodes in node-id order = grouped by parent, children in
 // order; orphans stored at internal nodes are left out -- they are never sources) and X's record
-// carries the range.  The links of the records skip leaf nodes: `first` = first INTERNAL node in
-// depth-first order inside or after X's children, `skip` = first internal node after X's subtree.
+// carries the range.
+// The walk records -- one per internal node that carries mass -- are stored in DEPTH-FIRST (pre-)ORDER, the order
+// the walk visits them in: the record after X's is the first record inside X's subtree if there is one, else the
+// first one after it, so "descend" is always id + 1 (no link, and the load can be issued before X's record has
+// arrived); `skip` = id + records in X's subtree (com_kernel counts them bottom-up, pack_level_kernel hands out the
+// ids top-down); "asleep until the walk leaves this subtree" is one compare, id >= wake.
 // The two scans of the build tail share one set of kernels:
 //   MODE 0, item = node k:           particles stored in k if k is a leaf            -> lscan
-//   MODE 2, item = node k:           1 if k is internal -> cscan: COMPACT id of an internal node.  The walk
-//                                    records are stored by compact id (an eighth of the node count), links
-//                                    included: denser in L1/L2 and an eighth of the bytes to exchange.
 //   MODE 1, item = sibling group j   (nodes 1+8j .. 8+8j, the children of one internal node):
 //                                    source PAIRS of the group = ceil(leaf particles / 2) -> pscan
 template <int MODE>
@@ -829,7 +835,6 @@ __device__ __forceinline__ int scan_items(int nn) { return MODE == 1 ? (nn - 1) 
 template <int MODE>
 __device__ __forceinline__ int scan_value(int k, const int4* __restrict__ meta, const int* __restrict__ lscan) {
     if (MODE == 0) { const int4 m = meta[k]; return m.x < 0 ? m.w : 0; }
-    if (MODE == 2) return meta[k].x >= 0 ? 1 : 0;
     return (lscan[9 + 8 * k] - lscan[1 + 8 * k] + 1) >> 1;
 }
 
@@ -938,43 +943,52 @@ leaf_apply_kernel(const TreeGlobals* __restrict__ g, int max_depth, const int4* 
         }
     }
 }
-// walk records of the internal nodes (and of a root that is a leaf: first = ROOT_LEAF)
+// Walk records of one level, top-down: a node that has an id writes its record and hands ids to its children.
+// record = {centre of mass, M} {skip | first source pair of the leaf children | cell edge | their particle count}.
+// A root that is a leaf: skip = ROOT_LEAF.  Record 0 is always the root's (a part build's root: its own octants).
 constexpr int ROOT_LEAF = -2;
 constexpr int FOREST_HDR_INTS = 40;     // per part: {records, source pairs, 6 pad} + the 8 level-1 {com, M}
 __global__ void __launch_bounds__(256)
-pack_walk_kernel(const TreeGlobals* __restrict__ g, int max_depth, const float4* __restrict__ com,
-                 const int4* __restrict__ meta, const int* __restrict__ lscan, const int* __restrict__ pscan,
-                 const int* __restrict__ cscan, float4* __restrict__ nodes, int* __restrict__ leaf_off,
-                 int* __restrict__ hdr) {
-    const int nn = tree_node_count(g, max_depth);
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nn; k += gridDim.x * blockDim.x) {
+pack_level_kernel(const TreeGlobals* __restrict__ g, int level, int max_depth, const float4* __restrict__ com,
+                  const int4* __restrict__ meta, const int* __restrict__ lscan, const int* __restrict__ pscan,
+                  const int* __restrict__ sub, int* __restrict__ pre, float4* __restrict__ nodes,
+                  int* __restrict__ hdr) {
+    const LevelInfo L = g->lv[level];
+    const int n_nodes = L.node_end - L.node_begin;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += gridDim.x * blockDim.x) {
+        const int k = L.node_begin + i;
         const int4 m = meta[k];
+        const int records = sub[k];
         if (hdr && k >= 1 && k <= 8) reinterpret_cast<float4*>(hdr + 8)[k - 1] = com[k];   // forest: root merge input
-        if (m.x < 0 && k != 0) continue;
-        int first, skip = -1, loff, lcnt;
-        // the walk visits internal nodes that carry mass; everything else is stepped over here, once
-        auto stepped_over = [&](int j) { return meta[j].x < 0 || com[j].w == 0.0f; };     // leaf, or :260
-        if (m.x < 0) {                               // the whole tree is one leaf
-            first = ROOT_LEAF; loff = 0; lcnt = m.w;
-        } else {
-            first = m.x;                             // children, then whatever follows the subtree
-            while (first >= 0 && stepped_over(first)) first = meta[first].y;
-            skip = m.y;
-            while (skip >= 0 && stepped_over(skip)) skip = meta[skip].y;
-            if (first >= 0) first = cscan[first];           // links are compact ids
-            if (skip >= 0) skip = cscan[skip];
-            loff = pscan[(m.x - 1) >> 3];                   // first source pair of the children
-            lcnt = lscan[m.x + 8] - lscan[m.x];             // leaf particles among them
+        if (k == 0) {
+            const int nn = tree_node_count(g, max_depth);
+            if (hdr) {                                              // sizes of this part's walk tables
+                hdr[0] = records > 0 ? records : 1;
+                hdr[1] = nn > 1 ? pscan[(nn - 1) / 8] : (lscan[1] + 1) / 2;
+            }
+            if (m.x < 0) {                                          // the whole tree is one leaf
+                nodes[0] = com[0];
+                nodes[1] = make_float4(__int_as_float(ROOT_LEAF), __int_as_float(0), 0.0f, __int_as_float(m.w));
+                continue;
+            }
+            pre[0] = 0;
+        } else if (records == 0) {
+            continue;                                               // leaf, or massless (:260): never visited
         }
-        const int cid = cscan[k];                           // 0 for the root, internal or not
-        nodes[2 * cid] = com[k];
-        nodes[2 * cid + 1] = make_float4(__int_as_float(first), __int_as_float(skip), __int_as_float(m.w),
-                                         __int_as_float(lcnt));      // m.w of an internal node = cell edge bits
-        leaf_off[cid] = loff;
-    }
-    if (hdr && blockIdx.x == 0 && threadIdx.x == 0) {       // sizes of this part's walk tables
-        hdr[0] = cscan[nn] > 0 ? cscan[nn] : 1;
-        hdr[1] = nn > 1 ? pscan[(nn - 1) / 8] : (lscan[1] + 1) / 2;
+        const int id = pre[k];
+        int next = id + 1;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+            const int s = sub[m.x + d];
+            if (s > 0) { pre[m.x + d] = next; next += s; }
+        }
+        // a massless root still gets record 0 (M = 0: the walk stops there, :260); skip = 1 = end of its table
+        const int skip = records > 0 ? id + records : 1;
+        const int loff = pscan[(m.x - 1) >> 3];                     // first source pair of the children
+        const int lcnt = lscan[m.x + 8] - lscan[m.x];               // leaf particles among them
+        nodes[2 * id] = com[k];
+        nodes[2 * id + 1] = make_float4(__int_as_float(skip), __int_as_float(loff), __int_as_float(m.w),
+                                        __int_as_float(lcnt));      // m.w of an internal node = cell edge bits
     }
 }
 
@@ -982,7 +996,6 @@ pack_walk_kernel(const TreeGlobals* __restrict__ g, int max_depth, const float4*
 // rounding of compute_center_of_mass (:226-241, children 0..7 with M > 0) -- the value the unsharded build gives.
 struct ForestTables {
     const float4* nodes[8];
-    const int* leaf_off[8];
     const ulonglong2* leaf_pairs[8];
     int owner[8];                 // part that owns octant d
     int n_parts;
@@ -1167,10 +1180,17 @@ __device__ __forceinline__ void ld256(const ulonglong2* p, ulonglong2& a, ulongl
 // record.  A target tests the root once, then walks part after part -- octant order, i.e. the depth-first order
 // of the whole tree -- with the same loop; node ids are local to a part's table.
 // by_slot: acc3 is indexed by the target's position in `order` (an explicit target list), not by index - i0.
-template <bool COUNT, bool FIXED, bool PERIODIC = false, bool POT = false, bool FOREST = false>
-__global__ void __launch_bounds__(128, 10)
+// MINB: resident 128-thread CTAs per SM the register budget is cut for (10 -> 48 registers, 9 -> 56, 8 -> 64).
+// EARLY: the record of the next visit is requested as soon as the successor is known (after the vote, before the
+// monopole arithmetic and the leaf range) instead of at the end of the visit.  Measured: no gain in either kernel,
+// and speculative requests (the skip target, or id + 1, before the vote) cost time -- every broadcast 256-bit load
+// writes 1 KB into the register file, and in the one-target kernel that return path (l1tex lsu writeback, 128 B per
+// clock and SM) is 76 % busy, as busy as the issue slots: a wrong guess is not free.
+template <bool COUNT, bool FIXED, bool PERIODIC = false, bool POT = false, bool FOREST = false, int MINB = 9,
+          bool EARLY = false>
+__global__ void __launch_bounds__(128, MINB)
 walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order, int i0, int n_targets,
-                 const float4* __restrict__ nodes, const int* __restrict__ leaf_off,
+                 const float4* __restrict__ nodes,
                  const ulonglong2* __restrict__ leaf_pairs, float theta, float theta2, float eps2, float box,
                  float* __restrict__ acc3, TreeGlobals* __restrict__ g,
                  const ForestTables* __restrict__ forest = nullptr, const float4* __restrict__ forest_root = nullptr,
@@ -1197,8 +1217,9 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
     }
     unsigned long long c_vis = valid ? 1 : 0, c_pc = 0, c_pp = 0;        // the root is visited by everyone
     [[maybe_unused]] unsigned long long c_slots = 0, c_nl = 0, c_na = 0;  // lane-utilisation counters (COUNT only)
-    constexpr int AWAKE = -2, NEVER = -3;
-    int wake = valid ? AWAKE : NEVER;     // node id at which a sleeping lane resumes
+    constexpr int NEVER = 0x7fffffff;
+    int wake = valid ? 0 : NEVER;         // record id at which a sleeping lane resumes: ids grow along the walk, so a
+                                          // lane is awake iff id >= wake
 
     // `cnt` leaf particles stored as pairs from pair `q` on, against this lane's target; on_lane = the
     // lane takes part.  Branch-free packed rows: a lane that is out, or is the particle itself (:321), or a
@@ -1264,16 +1285,19 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
         }
         return;
     }
-    // One table: every node the links lead to is internal and carries mass (pack_walk_kernel).
-    auto walk_table = [&](const float4* __restrict__ nd, const int* __restrict__ loff,
-                          const ulonglong2* __restrict__ pairs, int k) {
-        while (k >= 0) {
-            if (wake == k) wake = AWAKE;
-            const bool active = (wake == AWAKE);
+    // One table, records [k, kend) in depth-first order; every record is an internal node that carries mass
+    // (pack_level_kernel).  The table has one readable record of padding after kend.
+    auto walk_table = [&](const float4* __restrict__ nd, const ulonglong2* __restrict__ pairs, int k, const int kend) {
+        auto record = [&](int id) {
+            return reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nd) + (size_t)(unsigned)id * 32);
+        };
+        // One visit.  (c, mf) = {centre of mass, M} {skip | first leaf pair | cell edge | leaf-child particles} of
+        // record k; the record of the next visit goes into (cn, mn).  The caller alternates two register sets, so
+        // no record is ever moved.
+        auto visit = [&](const float4& c, const float4& mf, float4& cn, float4& mn) {
+            const int skip = __float_as_int(mf.x), lcnt = __float_as_int(mf.w);
+            const bool active = k >= wake;
             if (COUNT) { c_nl += 1; c_na += active; }
-            float4 c, mf;            // {centre of mass, M} {first | skip | cell edge | leaf-child particles}
-            ld256(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nd) + (size_t)(unsigned)k * 32), c, mf);
-            const int first = __float_as_int(mf.x), skip = __float_as_int(mf.y), lcnt = __float_as_int(mf.w);
             // Branch-free: every lane runs the test and the monopole; a lane that sleeps or opens the cell takes
             // 1/r = 0, so its term is exactly 0.
             float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
@@ -1282,45 +1306,70 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
                 dy = __fsub_rn(dy, __fmul_rn(box, roundf(__fdiv_rn(dy, box))));
                 dz = __fsub_rn(dz, __fmul_rn(box, roundf(__fdiv_rn(dz, box))));
             }
+            // size/|d| < theta (:309) screened as size^2 < theta^2 |d|^2 on a contracted |d|^2: decided unless the two
+            // sides are within 3e-5 of each other (the roundings of either form are < 3e-7)
             const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            bool wraps = false;          // periodic: a cell reaching across the half-box distance is never a monopole
-            if constexpr (PERIODIC) {
+            const float t2 = theta2 * d2;
+            const float diff = fmaf(mf.z, mf.z, -t2);
+            bool sure = fabsf(diff) > 3.0e-5f * t2;
+            bool accept = diff < 0.0f;
+            if constexpr (PERIODIC) {    // a cell reaching across the half-box distance is never a monopole
                 const float hb = __fmul_rn(box, 0.5f);
-                wraps = __fadd_rn(fabsf(dx), mf.z) > hb || __fadd_rn(fabsf(dy), mf.z) > hb || __fadd_rn(fabsf(dz), mf.z) > hb;
+                if (__fadd_rn(fabsf(dx), mf.z) > hb || __fadd_rn(fabsf(dy), mf.z) > hb || __fadd_rn(fabsf(dz), mf.z) > hb) {
+                    sure = true; accept = false;
+                }
             }
-            const bool accept = !wraps && accept_cell_d(mf.z, dx, dy, dz, d2, theta, theta2);      // :309
-            const bool take = active && accept;
-            const bool open = active && !accept;
-            {
+            auto monopole = [&](bool take) {                                 // :280-290; 1/r = 0 for a lane that is out
                 const float rinv = take ? rsqrt_fast(d2 + eps2) : 0.0f;
                 if constexpr (POT) {
                     ax = fmaf(c.w, rinv, ax);
                 } else {
-                    const float f = c.w * rinv * rinv * rinv;                // :280-290
+                    const float f = c.w * rinv * rinv * rinv;
                     ax = fmaf(f, dx, ax); ay = fmaf(f, dy, ay); az = fmaf(f, dz, az);
                 }
                 if (COUNT) c_pc += take;
                 if (take) wake = skip;                                       // sleep through this subtree
-            }
-            if (__any_sync(FULL, open)) {                                    // :293-297
-                if (COUNT && open) c_vis += 8;                               // its 8 children, leaves included
-                if (lcnt > 0) leaf_range(pairs, loff[k], lcnt, open);
-                k = first;
+            };
+            int nk = skip;
+            if (!__any_sync(FULL, active & !(sure & accept))) {
+                if constexpr (EARLY) { if (nk < kend) ld256(record(nk), cn, mn); }
+                monopole(active);        // the common visit: every awake lane accepts the cell outright
             } else {
-                k = skip;
+                if (!sure) {             // the reference's own sequence, one rounding per operation
+                    const float d2r = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                    accept = __fdiv_rn(mf.z, __fsqrt_rn(d2r)) < theta;
+                }
+                const bool open = active && !accept;
+                const bool descend = __any_sync(FULL, open);                 // :293-297
+                if (descend) nk = k + 1;
+                if constexpr (EARLY) { if (nk < kend) ld256(record(nk), cn, mn); }
+                monopole(active && accept);
+                if (descend) {
+                    if (COUNT && open) c_vis += 8;                           // its 8 children, leaves included
+                    if (lcnt > 0) leaf_range(pairs, __float_as_int(mf.y), lcnt, open);
+                }
             }
+            if (!EARLY && nk < kend) ld256(record(nk), cn, mn);
+            k = nk;
+        };
+        float4 c0, m0, c1, m1;
+        if (k < kend) ld256(record(k), c0, m0);
+        while (k < kend) {
+            visit(c0, m0, c1, m1);
+            if (k >= kend) break;
+            visit(c1, m1, c0, m0);
         }
     };
     if constexpr (!FOREST) {
         // the root: massless -> nothing to do (:260); a leaf -> one pair loop (:268-270)
-        int k = 0;
-        {
-            const float4 c = nodes[0];
-            const float4 mf = nodes[1];
-            if (c.w == 0.0f) k = -1;
-            else if (__float_as_int(mf.x) == ROOT_LEAF) { leaf_range(leaf_pairs, 0, __float_as_int(mf.w), valid); k = -1; }
+        const float4* nd = nodes;
+        const ulonglong2* pairs = leaf_pairs;
+        const float4 c = nd[0];
+        const float4 mf = nd[1];
+        if (c.w != 0.0f) {
+            if (__float_as_int(mf.x) == ROOT_LEAF) leaf_range(pairs, 0, __float_as_int(mf.w), valid);
+            else walk_table(nd, pairs, 0, __float_as_int(mf.x));             // the root's skip = the record count
         }
-        walk_table(nodes, leaf_off, leaf_pairs, k);
     } else {
         // the merged root: one accept test per target (:257-300 at depth 0), then part after part
         const float4 c = forest_root[0], mf = forest_root[1];
@@ -1340,13 +1389,12 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
                 const int n_parts = forest->n_parts;
                 for (int q = 0; q < n_parts; ++q) {
                     const float4* nd = forest->nodes[q];
-                    const int* loff = forest->leaf_off[q];
                     const ulonglong2* pairs = forest->leaf_pairs[q];
                     const float4 r1 = nd[1];                                 // this part's root record: its own octants
-                    if (wake != NEVER) wake = AWAKE;                         // a lane sleeping to the end of a part wakes here
+                    if (wake != NEVER) wake = 0;                             // a lane sleeping to the end of a part wakes here
                     const int lcnt = __float_as_int(r1.w);
-                    if (lcnt > 0) leaf_range(pairs, loff[0], lcnt, open);    // root children that are leaves
-                    walk_table(nd, loff, pairs, __float_as_int(r1.x));
+                    if (lcnt > 0) leaf_range(pairs, __float_as_int(r1.y), lcnt, open);    // root children that are leaves
+                    walk_table(nd, pairs, 1, __float_as_int(r1.x));
                 }
             }
         }
@@ -1374,6 +1422,251 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
             c_na += __shfl_down_sync(FULL, c_na, s);
         }
         if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&g->counters[0], c_vis);
+            atomicAdd(&g->counters[1], c_pc);
+            atomicAdd(&g->counters[2], c_pp);
+            atomicAdd(&g->counters[3], c_slots);
+            atomicAdd(&g->counters[4], c_nl);
+            atomicAdd(&g->counters[5], c_na);
+        }
+    }
+}
+
+// Two targets per lane: a warp owns 64 Hilbert-adjacent targets -- lane l holds targets l (A) and 32 + l (B) of the
+// group -- and walks the union of their 64 traversals.  One record load (1 KB written into the register file, the
+// unit the L1 return path counts) and one visit now serve 64 accept tests, and the whole visit runs in packed FP32:
+// a lane's A and B separations, |d|^2, screening test and monopole are the two halves of FADD2 / FFMA2 / FMUL2
+// operands.  A leaf range is summed for group A and for group B separately, each only if one of its own 32 targets
+// opened the cell, so the pair rows serve the same compact 32-target groups as in the one-target kernel and the
+// row loads are shared.  Decisions, interaction sets and counters are those of the one-target walk.
+// The reference's faithful tree only (unit-mass leaf pairs, eps = 0.01 literal from the host).
+template <bool COUNT, bool FOREST, int MINB, bool EARLY, int THREADS>
+__global__ void __launch_bounds__(THREADS, MINB * 64 / THREADS)
+walk_warp2_kernel(const float4* __restrict__ posm, const int* __restrict__ order, int i0, int n_targets,
+                  const float4* __restrict__ nodes, const ulonglong2* __restrict__ leaf_pairs, float theta,
+                  float theta2, float eps2, float* __restrict__ acc3, TreeGlobals* __restrict__ g,
+                  const ForestTables* __restrict__ forest, const float4* __restrict__ forest_root, int by_slot) {
+    typedef unsigned long long u64;
+    const int lane = threadIdx.x & 31;
+    const int tA = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 64 + lane, tB = tA + 32;
+    const bool vA = tA < n_targets, vB = tB < n_targets;
+    const int iA = vA ? (order ? order[tA] : (i0 + tA)) : -1, iB = vB ? (order ? order[tB] : (i0 + tB)) : -1;
+    float4 pA = make_float4(0.f, 0.f, 0.f, 0.f), pB = pA;
+    if (vA) pA = posm[iA];
+    if (vB) pB = posm[iB];
+    if (g->error) {                                                      // incomplete tree: fail loudly
+        const float nan = __int_as_float(0x7fc00000);
+        if (vA) { const size_t o = (size_t)(by_slot ? tA : iA - i0) * 3; acc3[o] = acc3[o + 1] = acc3[o + 2] = nan; }
+        if (vB) { const size_t o = (size_t)(by_slot ? tB : iB - i0) * 3; acc3[o] = acc3[o + 1] = acc3[o + 2] = nan; }
+        return;
+    }
+    const u64 npx = w_pk(-pA.x, -pB.x), npy = w_pk(-pA.y, -pB.y), npz = w_pk(-pA.z, -pB.z);   // {A | B}
+    u64 cx = 0ull, cy = 0ull, cz = 0ull;                                 // cells {A | B}
+    u64 ax2 = 0ull, ay2 = 0ull, az2 = 0ull, bx2 = 0ull, by2 = 0ull, bz2 = 0ull;   // leaf pairs, two sources per lane-op
+    unsigned long long c_vis = (vA ? 1 : 0) + (vB ? 1 : 0), c_pc = 0, c_pp = 0;
+    [[maybe_unused]] unsigned long long c_slots = 0, c_nl = 0, c_na = 0;
+    constexpr int NEVER = 0x7fffffff;
+    int wakeA = vA ? 0 : NEVER, wakeB = vB ? 0 : NEVER;
+
+    // one packed row (two sources) against one target; e2 = eps^2, or +inf for a lane that is out
+    auto row = [&](const ulonglong2& a, const ulonglong2& b, float px, float py, float pz, float e2, int self,
+                   bool on_lane, u64& sx, u64& sy, u64& sz) {
+        const u64 dx = w_add2(a.x, w_pk(-px, -px)), dy = w_add2(a.y, w_pk(-py, -py)), dz = w_add2(b.x, w_pk(-pz, -pz));
+        u64 r2 = w_fma2(dx, dx, w_pk(e2, e2));
+        r2 = w_fma2(dy, dy, r2);
+        r2 = w_fma2(dz, dz, r2);
+        float r2a, r2b;
+        w_unpk(r2, r2a, r2b);
+        const u64 rinv = w_pk(rsqrt_fast(r2a), rsqrt_fast(r2b));
+        const u64 f = w_mul2(w_mul2(rinv, rinv), rinv);                  // unit mass (:253, :340)
+        sx = w_fma2(f, dx, sx); sy = w_fma2(f, dy, sy); sz = w_fma2(f, dz, sz);
+        if (COUNT) {
+            c_slots += 2;
+            float w0, w1;
+            w_unpk(b.y, w0, w1);
+            c_pp += (on_lane && __float_as_int(w0) != self && __float_as_int(w0) >= 0) +
+                    (on_lane && __float_as_int(w1) != self && __float_as_int(w1) >= 0);
+        }
+    };
+    // `cnt` leaf particles from pair `q` on; group A / B takes part iff anyA / anyB (warp-uniform)
+    auto leaf_range = [&](const ulonglong2* __restrict__ pairs, int q, int cnt, bool onA, bool onB, bool anyA, bool anyB) {
+        const float inf = __int_as_float(0x7f800000);
+        const float eA = onA ? eps2 : inf, eB = onB ? eps2 : inf;
+        const ulonglong2* src = pairs + 2 * (size_t)q;
+        const int np = (cnt + 1) >> 1;
+        if (anyA && anyB) {
+            for (int r = 0; r < np; ++r) {
+                ulonglong2 a, b;
+                ld256(src + 2 * r, a, b);
+                row(a, b, pA.x, pA.y, pA.z, eA, iA, onA, ax2, ay2, az2);
+                row(a, b, pB.x, pB.y, pB.z, eB, iB, onB, bx2, by2, bz2);
+            }
+        } else if (anyA) {
+            int r = 0;
+            for (; r + 2 <= np; r += 2) {
+                ulonglong2 a0, b0, a1, b1;
+                ld256(src + 2 * r, a0, b0);
+                ld256(src + 2 * r + 2, a1, b1);
+                row(a0, b0, pA.x, pA.y, pA.z, eA, iA, onA, ax2, ay2, az2);
+                row(a1, b1, pA.x, pA.y, pA.z, eA, iA, onA, ax2, ay2, az2);
+            }
+            if (r < np) { ulonglong2 a, b; ld256(src + 2 * r, a, b); row(a, b, pA.x, pA.y, pA.z, eA, iA, onA, ax2, ay2, az2); }
+        } else {
+            int r = 0;
+            for (; r + 2 <= np; r += 2) {
+                ulonglong2 a0, b0, a1, b1;
+                ld256(src + 2 * r, a0, b0);
+                ld256(src + 2 * r + 2, a1, b1);
+                row(a0, b0, pB.x, pB.y, pB.z, eB, iB, onB, bx2, by2, bz2);
+                row(a1, b1, pB.x, pB.y, pB.z, eB, iB, onB, bx2, by2, bz2);
+            }
+            if (r < np) { ulonglong2 a, b; ld256(src + 2 * r, a, b); row(a, b, pB.x, pB.y, pB.z, eB, iB, onB, bx2, by2, bz2); }
+        }
+    };
+
+    const u64 nth2 = w_pk(-theta2, -theta2), eps2_2 = w_pk(eps2, eps2), nband = w_pk(-3.0e-5f, -3.0e-5f);
+    auto walk_table = [&](const float4* __restrict__ nd, const ulonglong2* __restrict__ pairs, int k, const int kend) {
+        auto record = [&](int id) {
+            return reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nd) + (size_t)(unsigned)id * 32);
+        };
+        auto visit = [&](const float4& c, const float4& mf, float4& cn, float4& mn) {
+            const int skip = __float_as_int(mf.x), lcnt = __float_as_int(mf.w);
+            const bool actA = k >= wakeA, actB = k >= wakeB;
+            if (COUNT) { c_nl += 2; c_na += (actA ? 1 : 0) + (actB ? 1 : 0); }
+            // separations of A and B in the two halves; add.rn(c, -p) is fsub_rn(c, p)
+            const u64 dx = w_add2(w_pk(c.x, c.x), npx), dy = w_add2(w_pk(c.y, c.y), npy), dz = w_add2(w_pk(c.z, c.z), npz);
+            const u64 d2 = w_fma2(dz, dz, w_fma2(dy, dy, w_mul2(dx, dx)));
+            // size^2 - theta^2 |d|^2 and the 3e-5 band around 0, as in the one-target kernel: -t2 = (-theta^2) |d|^2
+            const u64 nt2 = w_mul2(nth2, d2);
+            const u64 diff = w_fma2(w_pk(mf.z, mf.z), w_pk(mf.z, mf.z), nt2);
+            const u64 band = w_mul2(nband, nt2);
+            float diffA, diffB, bandA, bandB;
+            w_unpk(diff, diffA, diffB);
+            w_unpk(band, bandA, bandB);
+            const bool sureA = fabsf(diffA) > bandA, sureB = fabsf(diffB) > bandB;
+            bool accA = diffA < 0.0f, accB = diffB < 0.0f;
+            auto monopole = [&](bool takeA, bool takeB) {                    // :280-290; 1/r = 0 for a target that is out
+                float r2A, r2B;
+                w_unpk(w_add2(d2, eps2_2), r2A, r2B);
+                const float riA = takeA ? rsqrt_fast(r2A) : 0.0f, riB = takeB ? rsqrt_fast(r2B) : 0.0f;
+                const u64 ri = w_pk(riA, riB);
+                const u64 f = w_mul2(w_mul2(w_mul2(w_pk(c.w, c.w), ri), ri), ri);
+                cx = w_fma2(f, dx, cx); cy = w_fma2(f, dy, cy); cz = w_fma2(f, dz, cz);
+                if (COUNT) c_pc += (takeA ? 1 : 0) + (takeB ? 1 : 0);
+                if (takeA) wakeA = skip;                                     // sleep through this subtree
+                if (takeB) wakeB = skip;
+            };
+            int nk = skip;
+            // (bitwise on purpose: four independent compares and one combine, not a chain of dependent predicates)
+            if (!__any_sync(FULL, (actA & !(sureA & accA)) | (actB & !(sureB & accB)))) {
+                if constexpr (EARLY) { if (nk < kend) ld256(record(nk), cn, mn); }
+                monopole(actA, actB);    // the common visit: every awake target accepts the cell outright
+            } else {
+                auto exact = [&](float ddx, float ddy, float ddz) {          // :302-310, one rounding per operation
+                    const float d2r = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
+                    return __fdiv_rn(mf.z, __fsqrt_rn(d2r)) < theta;
+                };
+                if (!sureA || !sureB) {
+                    float dxA, dxB, dyA, dyB, dzA, dzB;
+                    w_unpk(dx, dxA, dxB); w_unpk(dy, dyA, dyB); w_unpk(dz, dzA, dzB);
+                    if (!sureA) accA = exact(dxA, dyA, dzA);
+                    if (!sureB) accB = exact(dxB, dyB, dzB);
+                }
+                const bool openA = actA && !accA, openB = actB && !accB;
+                const bool anyA = __any_sync(FULL, openA), anyB = __any_sync(FULL, openB);
+                if (anyA || anyB) nk = k + 1;                                // :293-297
+                if constexpr (EARLY) { if (nk < kend) ld256(record(nk), cn, mn); }
+                monopole(actA && accA, actB && accB);
+                if (anyA || anyB) {
+                    if (COUNT) c_vis += (openA ? 8 : 0) + (openB ? 8 : 0);   // its 8 children, leaves included
+                    if (lcnt > 0) leaf_range(pairs, __float_as_int(mf.y), lcnt, openA, openB, anyA, anyB);
+                }
+            }
+            if (!EARLY && nk < kend) ld256(record(nk), cn, mn);
+            k = nk;
+        };
+        float4 c0, m0, c1, m1;
+        if (k < kend) ld256(record(k), c0, m0);
+        while (k < kend) {
+            visit(c0, m0, c1, m1);
+            if (k >= kend) break;
+            visit(c1, m1, c0, m0);
+        }
+    };
+    if constexpr (!FOREST) {
+        const float4* nd = nodes;
+        const ulonglong2* pairs = leaf_pairs;
+        const float4 c = nd[0];
+        const float4 mf = nd[1];
+        if (c.w != 0.0f) {                                                   // :260
+            if (__float_as_int(mf.x) == ROOT_LEAF) leaf_range(pairs, 0, __float_as_int(mf.w), vA, vB, true, true);
+            else walk_table(nd, pairs, 0, __float_as_int(mf.x));
+        }
+    } else {
+        // the merged root: one accept test per target (:257-300 at depth 0), then part after part
+        const float4 c = forest_root[0], mf = forest_root[1];
+        if (c.w != 0.0f) {
+            if (COUNT) { c_nl += 2; c_na += (vA ? 1 : 0) + (vB ? 1 : 0); }
+            float fx[2], fy[2], fz[2];
+            bool open[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float4& p = h ? pB : pA;
+                const bool valid = h ? vB : vA;
+                const float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
+                const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                const bool accept = accept_cell_d(mf.z, dx, dy, dz, d2, theta, theta2);
+                const bool take = valid && accept;
+                open[h] = valid && !accept;
+                const float rinv = take ? rsqrt_fast(d2 + eps2) : 0.0f;
+                const float f = c.w * rinv * rinv * rinv;
+                fx[h] = f * dx; fy[h] = f * dy; fz[h] = f * dz;
+                if (COUNT) c_pc += take;
+                if (take) { if (h) wakeB = NEVER; else wakeA = NEVER; }    // the whole tree is one monopole for this target
+            }
+            cx = w_pk(fx[0], fx[1]); cy = w_pk(fy[0], fy[1]); cz = w_pk(fz[0], fz[1]);
+            const bool anyA = __any_sync(FULL, open[0]), anyB = __any_sync(FULL, open[1]);
+            if (anyA || anyB) {
+                if (COUNT) c_vis += (open[0] ? 8 : 0) + (open[1] ? 8 : 0);
+                const int n_parts = forest->n_parts;
+                for (int q = 0; q < n_parts; ++q) {
+                    const float4* nd = forest->nodes[q];
+                    const ulonglong2* pairs = forest->leaf_pairs[q];
+                    const float4 r1 = nd[1];                                 // this part's root record: its own octants
+                    if (wakeA != NEVER) wakeA = 0;                           // a target sleeping to the end of a part wakes here
+                    if (wakeB != NEVER) wakeB = 0;
+                    const int lcnt = __float_as_int(r1.w);
+                    if (lcnt > 0) leaf_range(pairs, __float_as_int(r1.y), lcnt, open[0], open[1], anyA, anyB);
+                    walk_table(nd, pairs, 1, __float_as_int(r1.x));
+                }
+            }
+        }
+    }
+    float cxA, cxB, cyA, cyB, czA, czB, lo, hi;
+    w_unpk(cx, cxA, cxB); w_unpk(cy, cyA, cyB); w_unpk(cz, czA, czB);
+    if (vA) {
+        const size_t o = (size_t)(by_slot ? tA : iA - i0) * 3;
+        w_unpk(ax2, lo, hi); acc3[o + 0] = cxA + (lo + hi);
+        w_unpk(ay2, lo, hi); acc3[o + 1] = cyA + (lo + hi);
+        w_unpk(az2, lo, hi); acc3[o + 2] = czA + (lo + hi);
+    }
+    if (vB) {
+        const size_t o = (size_t)(by_slot ? tB : iB - i0) * 3;
+        w_unpk(bx2, lo, hi); acc3[o + 0] = cxB + (lo + hi);
+        w_unpk(by2, lo, hi); acc3[o + 1] = cyB + (lo + hi);
+        w_unpk(bz2, lo, hi); acc3[o + 2] = czB + (lo + hi);
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            c_vis += __shfl_down_sync(FULL, c_vis, s);
+            c_pc += __shfl_down_sync(FULL, c_pc, s);
+            c_pp += __shfl_down_sync(FULL, c_pp, s);
+            c_slots += __shfl_down_sync(FULL, c_slots, s);
+            c_nl += __shfl_down_sync(FULL, c_nl, s);
+            c_na += __shfl_down_sync(FULL, c_na, s);
+        }
+        if (lane == 0) {
             atomicAdd(&g->counters[0], c_vis);
             atomicAdd(&g->counters[1], c_pc);
             atomicAdd(&g->counters[2], c_pp);
@@ -1492,9 +1785,8 @@ static int tree_build_impl(b200_ctx* ctx, const void* posm4, const int* arrival,
     B200_TRY(T->leaf_pos.reserve((n + T->max_split + 2) * sizeof(float4)));     // pair layout: <= 1 pad slot per parent
     B200_TRY(T->pscan.reserve((T->max_split + 2) * sizeof(int)));
     B200_TRY(T->slot_node.reserve(n * sizeof(int)));
-    B200_TRY(T->leaf_off.reserve((T->max_split + 2) * sizeof(int)));
     B200_TRY(T->lscan.reserve((T->max_nodes + 1) * sizeof(int)));
-    B200_TRY(T->cscan.reserve((T->max_nodes + 1) * sizeof(int)));
+    B200_TRY(T->sub.reserve((T->max_nodes + 1) * sizeof(int)));
     B200_TRY(T->leaf_tile_sum.reserve(T->max_node_tiles * sizeof(int)));
     B200_TRY(T->globals.reserve(sizeof(TreeGlobals)));
     B200_TRY(T->tile_hist.reserve(T->max_tiles * 8 * sizeof(unsigned)));
@@ -1612,7 +1904,7 @@ static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st) {
         const double lvl_nodes = (L < 10) ? (double)(1ull << (3 * L)) : 1e30;
         const size_t nb = (size_t)((lvl_nodes < (double)T->max_nodes) ? lvl_nodes : (double)T->max_nodes);
         const int cgrid = (int)((nb + 255) / 256 < (size_t)pgrid ? (nb + 255) / 256 : (size_t)pgrid);
-        com_kernel<<<cgrid, 256, 0, st>>>(g, L, meta, center, T->part_idx.as<int>(), T->posm, com);
+        com_kernel<<<cgrid, 256, 0, st>>>(g, L, meta, center, T->part_idx.as<int>(), T->posm, com, T->sub.as<int>());
         ctx->launches += 1;
         if (L == max_depth || leaf_cap > COM_HUGE) {          // only the deepest level can hold leaves above leaf_cap
             com_huge_kernel<<<ctx->sm_count, 256, 0, st>>>(g, L, meta, T->part_idx.as<int>(), T->posm, com);
@@ -1626,10 +1918,6 @@ static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st) {
     leaf_reduce_kernel<0><<<pgrid, 256, 0, st>>>(g, max_depth, meta, nullptr, tsum);
     leaf_scan_kernel<0><<<1, 1024, 0, st>>>(g, max_depth, tsum);
     leaf_apply_kernel<0><<<pgrid, 256, 0, st>>>(g, max_depth, meta, nullptr, tsum, lscan);
-    int* cscan = T->cscan.as<int>();
-    leaf_reduce_kernel<2><<<pgrid, 256, 0, st>>>(g, max_depth, meta, nullptr, tsum);
-    leaf_scan_kernel<2><<<1, 1024, 0, st>>>(g, max_depth, tsum);
-    leaf_apply_kernel<2><<<pgrid, 256, 0, st>>>(g, max_depth, meta, nullptr, tsum, cscan);
     leaf_reduce_kernel<1><<<pgrid, 256, 0, st>>>(g, max_depth, meta, lscan, tsum);
     leaf_scan_kernel<1><<<1, 1024, 0, st>>>(g, max_depth, tsum);
     leaf_apply_kernel<1><<<pgrid, 256, 0, st>>>(g, max_depth, meta, lscan, tsum, pscan);
@@ -1637,10 +1925,18 @@ static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st) {
         g, T->part_idx.as<int>(), T->slot_node.as<int>(), meta, lscan, pscan, T->posm, (int)n,
         T->part_pos.as<float4>(), T->leaf_pos.as<float>(), fixed ? 1 : 0);
     pair_pad_kernel<<<pgrid, 256, 0, st>>>(g, max_depth, lscan, pscan, T->leaf_pos.as<float>(), fixed ? 1 : 0);
-    pack_walk_kernel<<<pgrid, 256, 0, st>>>(g, max_depth, com, meta, lscan, pscan, cscan, T->nodes.as<float4>(),
-                                            T->leaf_off.as<int>(),
-                                            T->forest_hdr.p ? T->forest_hdr.as<int>() + FOREST_HDR_INTS * T->part : nullptr);
-    ctx->launches += 12;
+    ctx->launches += 8;
+    // walk records in depth-first order: ids handed down level by level (nsplit_rank is free after the level loop
+    // and holds them)
+    for (int L = 0; L <= max_depth; ++L) {
+        const double lvl_nodes = (L < 10) ? (double)(1ull << (3 * L)) : 1e30;
+        const size_t nb = (size_t)((lvl_nodes < (double)T->max_nodes) ? lvl_nodes : (double)T->max_nodes);
+        const int grid = (int)((nb + 255) / 256 < (size_t)pgrid ? (nb + 255) / 256 : (size_t)pgrid);
+        pack_level_kernel<<<grid, 256, 0, st>>>(
+            g, L, max_depth, com, meta, lscan, pscan, T->sub.as<int>(), nsr, T->nodes.as<float4>(),
+            T->forest_hdr.p ? T->forest_hdr.as<int>() + FOREST_HDR_INTS * T->part : nullptr);
+        ctx->launches += 1;
+    }
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }
@@ -1702,22 +1998,54 @@ static int tree_walk_impl(b200_ctx* ctx, const int* list, size_t i0, size_t n_ta
     const bool per_thread = !T->fixed && !forest && !list && getenv("B200_WALK_PER_THREAD") != nullptr;     // tuning hook
     const float theta2 = theta > 0.f ? theta * theta : 0.f;
     const float eps2 = T->fixed ? T->eps * T->eps : 0.01f * 0.01f;
-    // one launch macro for the warp walk's instances: <COUNT, FIXED, PERIODIC, POT, FOREST>
-#define B200_WALK(COUNT_, FIXED_, PERIODIC_, FOREST_)                                                            \
-    walk_warp_kernel<COUNT_, FIXED_, PERIODIC_, false, FOREST_><<<grid, 128, 0, st>>>(                           \
-        T->posm, order, (int)i0, (int)n_targets, T->nodes.as<float4>(), T->leaf_off.as<int>(),                   \
+    // launch macros for the walk's instances.  One-target kernel <COUNT, FIXED, PERIODIC, POT, FOREST, MINB, EARLY>:
+    // the fixed-physics modes, 128-thread CTAs, 9 resident per SM (56 registers).  Two-target kernel
+    // <COUNT, FOREST, MINB, EARLY, THREADS>: the reference-faithful tree (the hot path), MINB = resident CTAs per SM
+    // in units of 64 threads (16 -> 64 registers).
+#define B200_WALK_V(COUNT_, FIXED_, PERIODIC_, FOREST_, MINB_, EARLY_)                                           \
+    walk_warp_kernel<COUNT_, FIXED_, PERIODIC_, false, FOREST_, MINB_, EARLY_><<<grid, 128, 0, st>>>(            \
+        T->posm, order, (int)i0, (int)n_targets, T->nodes.as<float4>(),                                          \
         T->leaf_pos.as<ulonglong2>(), theta, theta2, eps2, T->periodic_box, (float*)acc3, g,                     \
         T->forest_root.as<ForestTables>() ? (const ForestTables*)(T->forest_root.as<char>() + 64) : nullptr,     \
         T->forest_root.as<float4>(), by_slot)
+#define B200_WALK(COUNT_, FIXED_, PERIODIC_, FOREST_) B200_WALK_V(COUNT_, FIXED_, PERIODIC_, FOREST_, 9, false)
+    const unsigned groups = (unsigned)((n_targets + 63) / 64);           // 64 targets per warp
+#define B200_WALK2(COUNT_, FOREST_, MINB_, EARLY_, THREADS_)                                                     \
+    walk_warp2_kernel<COUNT_, FOREST_, MINB_, EARLY_, THREADS_>                                                  \
+        <<<(groups * 32 + THREADS_ - 1) / THREADS_, THREADS_, 0, st>>>(                                          \
+        T->posm, order, (int)i0, (int)n_targets, T->nodes.as<float4>(), T->leaf_pos.as<ulonglong2>(), theta,     \
+        theta2, eps2, (float*)acc3, g,                                                                           \
+        T->forest_root.as<ForestTables>() ? (const ForestTables*)(T->forest_root.as<char>() + 64) : nullptr,     \
+        T->forest_root.as<float4>(), by_slot)
+    // Tuning hook (B200_WALK_VARIANT): 0 = two targets per lane, 256-thread CTAs (default: adjacent groups share the
+    // L1; 1.79 ms per 2^20 uniform targets), 1 = the same with 64-thread CTAs (1.83 ms), 2 = EARLY (1.88 ms),
+    // 3 = the one-target kernel (2.00 ms), 4 = two targets, 128-thread CTAs, 72 registers.
+    static const int variant = getenv("B200_WALK_VARIANT") ? atoi(getenv("B200_WALK_VARIANT")) : 0;
+#define B200_WALK_HOT(FOREST_)                                                                                   \
+    switch (variant) {                                                                                           \
+        case 1:  B200_WALK2(false, FOREST_, 16, false, 64); break;                                               \
+        case 2:  B200_WALK2(false, FOREST_, 16, true, 256); break;                                               \
+        case 3:  B200_WALK_V(false, false, false, FOREST_, 9, false); break;                                     \
+        case 4:  B200_WALK2(false, FOREST_, 14, false, 128); break;                                              \
+        default: B200_WALK2(false, FOREST_, 16, false, 256); break;                                              \
+    }
+#define B200_WALK_HOT_COUNT(FOREST_)                                                                             \
+    if (variant == 3) B200_WALK(true, false, false, FOREST_); else B200_WALK2(true, FOREST_, 12, false, 256);
     if (forest) {
-        if (T->counting) B200_WALK(true, false, false, true); else B200_WALK(false, false, false, true);
+        if (T->counting) { B200_WALK_HOT_COUNT(true) }
+        else B200_WALK_HOT(true)
     } else if (T->fixed) {
         const bool periodic = T->periodic_box > 0.f;
         if (T->counting) { if (periodic) B200_WALK(true, true, true, false); else B200_WALK(true, true, false, false); }
         else             { if (periodic) B200_WALK(false, true, true, false); else B200_WALK(false, true, false, false); }
     } else if (!per_thread) {
-        if (T->counting) B200_WALK(true, false, false, false); else B200_WALK(false, false, false, false);
+        if (T->counting) { B200_WALK_HOT_COUNT(false) }
+        else B200_WALK_HOT(false)
 #undef B200_WALK
+#undef B200_WALK_V
+#undef B200_WALK2
+#undef B200_WALK_HOT
+#undef B200_WALK_HOT_COUNT
     } else if (T->counting)
         walk_kernel<true><<<grid, 128, 0, st>>>(T->posm, order, (int)i0, (int)n_targets,
                                                 T->com.as<float4>(), T->center.as<float4>(), T->meta.as<int4>(),
@@ -1779,13 +2107,12 @@ int tree_forest_publish(b200_ctx* ctx, cudaStream_t st) {
         f.nn = (size_t)T->forest_hdr_host[FOREST_HDR_INTS * q];            // walk records (internal nodes)
         f.npairs = (size_t)T->forest_hdr_host[FOREST_HDR_INTS * q + 1];
         if (f.nn < 1) return B200_ERR_STATE;
-        B200_TRY(f.nodes.reserve(f.nn * 2 * sizeof(float4)));
-        B200_TRY(f.leaf_off.reserve(f.nn * sizeof(int)));
+        B200_TRY(f.nodes.reserve((f.nn + 1) * 2 * sizeof(float4)));       // + the record of padding the walk may read
         B200_TRY(f.leaf_pairs.reserve((f.npairs + 1) * 2 * sizeof(float4)));
-        const void* src[3] = {T->nodes.p, T->leaf_off.p, T->leaf_pos.p};
-        void* dst[3] = {f.nodes.p, f.leaf_off.p, f.leaf_pairs.p};
-        const size_t sz[3] = {f.nn * 2 * sizeof(float4), f.nn * sizeof(int), f.npairs * 2 * sizeof(float4)};
-        for (int k = 0; k < 3; ++k) { send[items] = src[k]; recv[items] = dst[k]; bytes[items] = sz[k]; root[items] = q; ++items; }
+        const void* src[2] = {T->nodes.p, T->leaf_pos.p};
+        void* dst[2] = {f.nodes.p, f.leaf_pairs.p};
+        const size_t sz[2] = {f.nn * 2 * sizeof(float4), f.npairs * 2 * sizeof(float4)};
+        for (int k = 0; k < 2; ++k) { send[items] = src[k]; recv[items] = dst[k]; bytes[items] = sz[k]; root[items] = q; ++items; }
     }
     if (collective) {
         B200_TRY(shard_bcast_group(ctx, items, send, recv, bytes, root, st));
@@ -1804,7 +2131,6 @@ int tree_forest_publish(b200_ctx* ctx, cudaStream_t st) {
         F.n_parts = P;
         for (int q = 0; q < P; ++q) {
             F.nodes[q] = T->forest[q].nodes.as<float4>();
-            F.leaf_off[q] = T->forest[q].leaf_off.as<int>();
             F.leaf_pairs[q] = T->forest[q].leaf_pairs.as<ulonglong2>();
             for (int d = q * 8 / P; d < (q + 1) * 8 / P; ++d) F.owner[d] = q;
         }
@@ -1842,11 +2168,11 @@ int tree_potential(b200_ctx* ctx, size_t i0, size_t n_targets, float theta, void
     const float eps2 = T->eps * T->eps;
     if (T->periodic_box > 0.f)
         walk_warp_kernel<false, true, true, true><<<grid, 128, 0, st>>>(
-            T->posm, T->order.as<int>(), (int)i0, (int)n_targets, T->nodes.as<float4>(), T->leaf_off.as<int>(),
+            T->posm, T->order.as<int>(), (int)i0, (int)n_targets, T->nodes.as<float4>(),
             T->leaf_pos.as<ulonglong2>(), theta, theta2, eps2, T->periodic_box, (float*)phi, g);
     else
         walk_warp_kernel<false, true, false, true><<<grid, 128, 0, st>>>(
-            T->posm, T->order.as<int>(), (int)i0, (int)n_targets, T->nodes.as<float4>(), T->leaf_off.as<int>(),
+            T->posm, T->order.as<int>(), (int)i0, (int)n_targets, T->nodes.as<float4>(),
             T->leaf_pos.as<ulonglong2>(), theta, theta2, eps2, T->periodic_box, (float*)phi, g);
     B200_CUDA(cudaGetLastError());
     ctx->launches += 1;
