@@ -443,34 +443,42 @@ def parity_tree(D, S, acc, box=100.0, theta=0.5, on_rank0_only=False):
 
 
 def walk_roofline(eng, D, n_total, nl, cnt6, walk_s, clocks, static_ok):
-    """What bounds walk_warp_kernel: instruction issue on L1/L2-resident data.  No HBM fraction is quoted --
-    the algorithmic byte count of SURVEY 8d (32 B per node visit, 16 B per pair source, per LANE) is served by
-    broadcast loads and exceeds what any memory level moves by 10-1000x."""
+    """What bounds the walk (walk_warp2_kernel): instruction issue on L1/L2-resident data, with the L1 -> register
+    write-back of its warp-wide broadcast loads (128 B per clock and SM) as the second ceiling -- the one-target
+    kernel it replaced ran that path at 0.76.  No HBM fraction is quoted -- the algorithmic byte count of SURVEY 8d
+    (32 B per node visit, 16 B per pair source, per LANE) is served by broadcast loads and exceeds what any memory
+    level moves by 10-1000x."""
     vis, pc, pp, slots, nlanes, nawake = [float(x) for x in cnt6]
-    # instruction-weighted lane utilisation: a node visit costs ~38 instructions per warp, a packed pair row ~18
-    # (2 source slots per lane); SASS of the shipped kernel, profiles/r2_walk_sass_excerpt.txt
-    issued = 38.0 * nlanes + 9.0 * slots
-    useful = 38.0 * nawake + 9.0 * pp
+    # instruction-weighted lane utilisation: one node visit of a warp costs ~47 instructions for its 64 target slots
+    # (23.5 per 32), a packed pair row ~18 for 32 lanes x 2 source slots (9 per slot); SASS of the shipped kernel,
+    # profiles/r2_sass_excerpts.md
+    issued = 23.5 * nlanes + 9.0 * slots
+    useful = 23.5 * nawake + 9.0 * pp
     inst = ncu_static("tree_walk_inst_executed", n_total) if static_ok else None
+    wb = ncu_static("tree_walk_lsu_writeback_cycles", n_total) if static_ok else None
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     issue_peak = eng.sm_count * 4 * sm_mhz * 1e6            # warp instructions per second, 4 schedulers per SM
     out = {
         "bound": "issue",
-        "kernel": "walk_warp_kernel (a warp walks the union of the traversals of 32 Hilbert-adjacent targets; per-lane "
-                  "accept test; leaf particles grouped per parent, packed-FP32 pair rows)",
+        "kernel": "walk_warp2_kernel (a warp walks the union of the traversals of 64 Hilbert-adjacent targets, two per "
+                  "lane in the halves of packed-FP32 operands; per-target accept test; depth-first walk records; leaf "
+                  "particles grouped per parent, packed-FP32 pair rows)",
         "kernel_ms": 1e3 * walk_s,
         "interactions_per_s_walk_only": (pc + pp) / walk_s,
         "fp32_tflops_at_20_flop": 20.0 * (pc + pp) / walk_s / 1e12,
         "pair_row_lane_frac": pp / slots if slots else None,
         "node_visit_lane_frac": nawake / nlanes if nlanes else None,
         "useful_lane_frac": useful / issued if issued else None,
-        "lane_frac_weights": "38 instructions per node visit, 9 per pair-row source slot (SASS counts)",
+        "lane_frac_weights": "47 instructions per node visit of 64 target slots, 9 per pair-row source slot (SASS counts)",
         "walk_counters_nodes_cells_pairs": [int(vis), int(pc), int(pp)],
         "warp_instructions": inst,
         "issue_frac": (inst / walk_s / issue_peak) if inst else None,
         "issue_peak": f"{eng.sm_count} SMs x 4 schedulers x {sm_mhz:.0f} MHz (median SM clock sampled in this run)",
         "warp_instructions_source": "ncu smsp__inst_executed.sum of this launch (profiles/ncu_traffic.json; same inputs, "
                                     "same kernel => same count); time and clock are live",
+        # second ceiling: cycles the L1's LSU write-back port was busy (ncu l1tex__lsu_writeback_active.sum over the
+        # SMs; a warp-wide 256-bit broadcast load takes 8) against the cycles of this run's launch
+        "lsu_writeback_frac": (wb / (eng.sm_count * walk_s * sm_mhz * 1e6)) if wb else None,
         "traffic": ncu_static("tree", n_total) if static_ok else None,
         "ncu_l2_bytes": ncu_static("tree_l2_bytes", n_total) if static_ok else None,
         "ncu_l1_bytes": ncu_static("tree_l1_bytes", n_total) if static_ok else None,

@@ -91,6 +91,7 @@ struct TreeState {
     size_t graph_key = 0;
     int graph_launches = 0;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    cudaStream_t body_stream = nullptr;   // capture stream for the bodies of the graph's conditional nodes
     // Part build (octant-sharded octree): this tree holds the root, its 8 children and the subtrees of the
     // octants in oct_mask only; the other octants are empty leaves.  The walk tables of all parts make a FOREST.
     int part = 0, n_parts = 1;
@@ -130,6 +131,8 @@ struct TreeState {
     }
     void release() {
         drop_graph();
+        if (body_stream) cudaStreamDestroy(body_stream);
+        body_stream = nullptr;
         for (ForestSlot& f : forest) { f.nodes.release(); f.leaf_pairs.release(); f.valid = false; }
         forest_root.release(); forest_hdr.release();
         if (forest_hdr_host) cudaFreeHost(forest_hdr_host);
@@ -227,6 +230,16 @@ __global__ void tree_init_kernel(TreeGlobals* g, float4* center, float4* com, in
         ent_idx[i] = arrival ? arrival[i] : i;          // arrival order = the reference's insertion order (:136-140)
         ent_node[i] = 0;
     }
+}
+
+// The graph of a build runs the levels below `shallow` only when the tree gets there: three IF nodes (build levels,
+// centre-of-mass levels, walk-record levels) armed here, after the last unconditional level has been split.
+__global__ void arm_deep_levels_kernel(const TreeGlobals* __restrict__ g, int shallow, cudaGraphConditionalHandle h0,
+                                       cudaGraphConditionalHandle h1, cudaGraphConditionalHandle h2) {
+    const unsigned deep = g->lv[shallow].node_end > g->lv[shallow].node_begin ? 1u : 0u;
+    cudaGraphSetConditional(h0, deep);
+    cudaGraphSetConditional(h1, deep);
+    cudaGraphSetConditional(h2, deep);
 }
 
 // ----------------------------------------------------- K1: classify nodes ---
@@ -1702,7 +1715,7 @@ void tree_destroy(b200_ctx* ctx) {
     }
 }
 
-static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st);
+static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st, bool conditional);
 
 static int tree_build_impl(b200_ctx* ctx, const void* posm4, const int* arrival, size_t n, float box, int leaf_cap,
                            int max_depth, bool fixed, float eps, int part, int n_parts, cudaStream_t st);
@@ -1809,7 +1822,7 @@ static int tree_build_impl(b200_ctx* ctx, const void* posm4, const int* arrival,
             cudaGraph_t graph = nullptr;
             if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
                 const uint64_t before = ctx->launches;
-                const int rc = tree_enqueue(ctx, T, ctx->stream);
+                const int rc = tree_enqueue(ctx, T, ctx->stream, getenv("B200_NO_COND") == nullptr);
                 const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
                 T->graph_launches = (int)(ctx->launches - before);
                 ctx->launches = before;
@@ -1841,13 +1854,17 @@ static int tree_build_impl(b200_ctx* ctx, const void* posm4, const int* arrival,
             return B200_OK;
         }
     }
-    B200_TRY(tree_enqueue(ctx, T, st));
+    B200_TRY(tree_enqueue(ctx, T, st, false));
     T->built = true;
     return B200_OK;
 }
 
 // The launch sequence of one build (kernels only: no allocation, no host synchronisation).
-static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st) {
+// conditional (only while `st` is being captured into the build's own graph): levels from `shallow` on -- deeper
+// than a uniform distribution of n particles reaches -- go into the bodies of three IF nodes (split levels,
+// centre-of-mass levels, walk-record levels) that a one-thread kernel arms when level `shallow` exists.  A tree of
+// 2^20 uniform particles ends at level 7 of 20: the unconditional sequence spends 0.2 ms in ~110 empty launches.
+static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st, bool conditional) {
     const size_t n = T->n;
     const float box = T->box;
     const int leaf_cap = T->cap, max_depth = T->max_depth;
@@ -1861,6 +1878,112 @@ static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st) {
     int* nsr = T->nsplit_rank.as<int>();
     const int pgrid = ctx->sm_count * 8;      // persistent grids: 8 x 256-thread CTAs per SM
     const int keep = fixed ? 0 : leaf_cap;
+    int* lscan = T->lscan.as<int>();
+    int* pscan = T->pscan.as<int>();
+    int* tsum = T->leaf_tile_sum.as<int>();
+
+    // a level cannot hold more nodes than this: trims the grids
+    auto level_nodes = [&](int L) {
+        const double lvl_nodes = (L < 10) ? (double)(1ull << (3 * L)) : 1e30;
+        return (size_t)((lvl_nodes < (double)T->max_nodes) ? lvl_nodes : (double)T->max_nodes);
+    };
+    auto split_levels = [&](int L0, int L1, cudaStream_t s) {               // levels L0..L1: one stable 8-way partition each
+        for (int L = L0; L <= L1; ++L) {
+            const int cur = L & 1, nxt = cur ^ 1;
+            const size_t nb = level_nodes(L);
+            const int ngrid = (int)((nb + NODE_TILE - 1) / NODE_TILE < (size_t)pgrid ? (nb + NODE_TILE - 1) / NODE_TILE : (size_t)pgrid);
+            const int egrid = (int)(T->max_tiles < (size_t)pgrid ? T->max_tiles : (size_t)pgrid);
+            const int sgrid = (int)((nb + 255) / 256 < (size_t)pgrid ? (nb + 255) / 256 : (size_t)pgrid);
+            node_reduce_kernel<<<ngrid, 256, 0, s>>>(g, L, leaf_cap, keep, max_depth, ncount, T->node_tile_sum.as<u64>());
+            node_scan_kernel<<<1, 1024, 0, s>>>(g, L, T->node_tile_sum.as<u64>(), (int)T->max_nodes);
+            node_apply_kernel<<<ngrid, 256, 0, s>>>(g, L, leaf_cap, keep, max_depth, ncount, T->node_tile_sum.as<u64>(),
+                                                    meta, nsr, T->split_node.as<int>());
+            entry_digit_kernel<<<egrid, ET_THREADS, 0, s>>>(
+                g, L, keep, T->oct_mask, T->posm, center, meta, nstart, nsr, T->ent_idx[cur].as<int>(),
+                T->ent_node[cur].as<int>(), T->digit.as<unsigned char>(), T->part_idx.as<int>(),
+                T->slot_node.as<int>(), T->tile_hist.as<unsigned>(), T->tile_warp_prefix.as<unsigned>(), T->split_where.as<int>(),
+                T->split_local.as<unsigned>());
+            tile_scan_kernel<<<8, 1024, 0, s>>>(g, L, T->tile_hist.as<unsigned>());
+            make_children_kernel<<<sgrid, 256, 0, s>>>(g, L, T->split_node.as<int>(), T->split_where.as<int>(),
+                                                       T->split_local.as<unsigned>(), T->tile_hist.as<unsigned>(),
+                                                       T->tile_warp_prefix.as<unsigned>(),
+                                                       T->split_cstart.as<unsigned>(), center, com, meta, nstart, ncount);
+            entry_scatter_kernel<<<egrid, ET_THREADS, 0, s>>>(
+                g, L, meta, nstart, nsr, T->ent_idx[cur].as<int>(), T->ent_node[cur].as<int>(),
+                T->digit.as<unsigned char>(), T->tile_hist.as<unsigned>(), T->tile_warp_prefix.as<unsigned>(),
+                T->split_cstart.as<unsigned>(), T->ent_idx[nxt].as<int>(), T->ent_node[nxt].as<int>());
+        }
+        return 7 * (L1 - L0 + 1);
+    };
+    auto com_levels = [&](int Lhi, int Llo, cudaStream_t s) {                // bottom-up: levels Lhi..Llo
+        int launched = 0;
+        for (int L = Lhi; L >= Llo; --L) {
+            const size_t nb = level_nodes(L);
+            const int cgrid = (int)((nb + 255) / 256 < (size_t)pgrid ? (nb + 255) / 256 : (size_t)pgrid);
+            com_kernel<<<cgrid, 256, 0, s>>>(g, L, meta, center, T->part_idx.as<int>(), T->posm, com, T->sub.as<int>());
+            ++launched;
+            if (L == max_depth || leaf_cap > COM_HUGE) {      // only the deepest level can hold leaves above leaf_cap
+                com_huge_kernel<<<ctx->sm_count, 256, 0, s>>>(g, L, meta, T->part_idx.as<int>(), T->posm, com);
+                ++launched;
+            }
+        }
+        return launched;
+    };
+    // walk records in depth-first order: ids handed down level by level (nsplit_rank is free after the split levels
+    // and holds them)
+    auto pack_levels = [&](int L0, int L1, cudaStream_t s) {
+        for (int L = L0; L <= L1; ++L) {
+            const size_t nb = level_nodes(L);
+            const int grid = (int)((nb + 255) / 256 < (size_t)pgrid ? (nb + 255) / 256 : (size_t)pgrid);
+            pack_level_kernel<<<grid, 256, 0, s>>>(
+                g, L, max_depth, com, meta, lscan, pscan, T->sub.as<int>(), nsr, T->nodes.as<float4>(),
+                T->forest_hdr.p ? T->forest_hdr.as<int>() + FOREST_HDR_INTS * T->part : nullptr);
+        }
+        return L1 - L0 + 1;
+    };
+
+    // first level that goes behind the IF nodes: two levels more than n / leaf_cap leaves fill when spread evenly
+    int shallow = max_depth + 1;
+    cudaGraphConditionalHandle cond[3] = {0, 0, 0};
+    cudaGraph_t capture_graph = nullptr;
+    if (conditional) {
+        int lv = 0;
+        for (size_t cells = 1; cells * (size_t)leaf_cap < n && lv < MAX_LEVELS; cells *= 8) ++lv;
+        shallow = lv + 3;
+        cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+        if (shallow > max_depth ||
+            cudaStreamGetCaptureInfo(st, &status, nullptr, &capture_graph, nullptr, nullptr) != cudaSuccess ||
+            status != cudaStreamCaptureStatusActive || capture_graph == nullptr) {
+            cudaGetLastError();
+            shallow = max_depth + 1;
+        } else {
+            for (int k = 0; k < 3; ++k)
+                B200_CUDA(cudaGraphConditionalHandleCreate(&cond[k], capture_graph, 0, cudaGraphCondAssignDefault));
+            if (!T->body_stream) B200_CUDA(cudaStreamCreateWithFlags(&T->body_stream, cudaStreamNonBlocking));
+        }
+    }
+    const bool deep = shallow <= max_depth;
+    // An IF node after everything captured so far on st; its body = whatever `body` launches on the body stream.
+    auto if_deep = [&](cudaGraphConditionalHandle h, auto&& body) -> int {
+        cudaStreamCaptureStatus status;
+        const cudaGraphNode_t* deps = nullptr;
+        size_t n_deps = 0;
+        B200_CUDA(cudaStreamGetCaptureInfo(st, &status, nullptr, nullptr, &deps, &n_deps));
+        cudaGraphNodeParams p = {};
+        p.type = cudaGraphNodeTypeConditional;
+        p.conditional.handle = h;
+        p.conditional.type = cudaGraphCondTypeIf;
+        p.conditional.size = 1;
+        cudaGraphNode_t node = nullptr;
+        B200_CUDA(cudaGraphAddNode(&node, capture_graph, deps, n_deps, &p));
+        B200_CUDA(cudaStreamUpdateCaptureDependencies(st, &node, 1, cudaStreamSetCaptureDependencies));
+        cudaGraph_t body_graph = p.conditional.phGraph_out[0];
+        B200_CUDA(cudaStreamBeginCaptureToGraph(T->body_stream, body_graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        body(T->body_stream);
+        cudaGraph_t same = nullptr;
+        B200_CUDA(cudaStreamEndCapture(T->body_stream, &same));
+        return B200_OK;
+    };
 
     if (fixed) {
         bbox_init_kernel<<<1, 32, 0, st>>>(g);
@@ -1871,50 +1994,19 @@ static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st) {
     tree_init_kernel<<<pgrid, 256, 0, st>>>(g, center, com, meta, nstart, ncount, T->ent_idx[0].as<int>(),
                                             T->ent_node[0].as<int>(), (int)n, box, fixed ? 1 : 0, T->arrival);
     ctx->launches += 1;
-    for (int L = 0; L <= max_depth; ++L) {
-        const int cur = L & 1, nxt = cur ^ 1;
-        // a level cannot hold more nodes / entries than these bounds: trim the grids
-        const double lvl_nodes = (L < 10) ? (double)(1ull << (3 * L)) : 1e30;
-        const size_t nb = (size_t)((lvl_nodes < (double)T->max_nodes) ? lvl_nodes : (double)T->max_nodes);
-        const int ngrid = (int)((nb + NODE_TILE - 1) / NODE_TILE < (size_t)pgrid ? (nb + NODE_TILE - 1) / NODE_TILE : (size_t)pgrid);
-        const int egrid = (int)(T->max_tiles < (size_t)pgrid ? T->max_tiles : (size_t)pgrid);
-        const int sgrid = (int)((nb + 255) / 256 < (size_t)pgrid ? (nb + 255) / 256 : (size_t)pgrid);
-        node_reduce_kernel<<<ngrid, 256, 0, st>>>(g, L, leaf_cap, keep, max_depth, ncount, T->node_tile_sum.as<u64>());
-        node_scan_kernel<<<1, 1024, 0, st>>>(g, L, T->node_tile_sum.as<u64>(), (int)T->max_nodes);
-        node_apply_kernel<<<ngrid, 256, 0, st>>>(g, L, leaf_cap, keep, max_depth, ncount, T->node_tile_sum.as<u64>(),
-                                                 meta, nsr, T->split_node.as<int>());
-        entry_digit_kernel<<<egrid, ET_THREADS, 0, st>>>(
-            g, L, keep, T->oct_mask, T->posm, center, meta, nstart, nsr, T->ent_idx[cur].as<int>(),
-            T->ent_node[cur].as<int>(), T->digit.as<unsigned char>(), T->part_idx.as<int>(),
-            T->slot_node.as<int>(), T->tile_hist.as<unsigned>(), T->tile_warp_prefix.as<unsigned>(), T->split_where.as<int>(),
-            T->split_local.as<unsigned>());
-        tile_scan_kernel<<<8, 1024, 0, st>>>(g, L, T->tile_hist.as<unsigned>());
-        make_children_kernel<<<sgrid, 256, 0, st>>>(g, L, T->split_node.as<int>(), T->split_where.as<int>(),
-                                                    T->split_local.as<unsigned>(), T->tile_hist.as<unsigned>(),
-                                                    T->tile_warp_prefix.as<unsigned>(),
-                                                    T->split_cstart.as<unsigned>(), center, com, meta, nstart, ncount);
-        entry_scatter_kernel<<<egrid, ET_THREADS, 0, st>>>(
-            g, L, meta, nstart, nsr, T->ent_idx[cur].as<int>(), T->ent_node[cur].as<int>(),
-            T->digit.as<unsigned char>(), T->tile_hist.as<unsigned>(), T->tile_warp_prefix.as<unsigned>(),
-            T->split_cstart.as<unsigned>(), T->ent_idx[nxt].as<int>(), T->ent_node[nxt].as<int>());
-        B200_CUDA(cudaGetLastError());
-        ctx->launches += 7;
-    }
-    for (int L = max_depth; L >= 0; --L) {
-        const double lvl_nodes = (L < 10) ? (double)(1ull << (3 * L)) : 1e30;
-        const size_t nb = (size_t)((lvl_nodes < (double)T->max_nodes) ? lvl_nodes : (double)T->max_nodes);
-        const int cgrid = (int)((nb + 255) / 256 < (size_t)pgrid ? (nb + 255) / 256 : (size_t)pgrid);
-        com_kernel<<<cgrid, 256, 0, st>>>(g, L, meta, center, T->part_idx.as<int>(), T->posm, com, T->sub.as<int>());
+    ctx->launches += split_levels(0, deep ? shallow - 1 : max_depth, st);
+    B200_CUDA(cudaGetLastError());
+    if (deep) {
+        // launches inside the bodies are not counted: they run only for trees deeper than `shallow` levels
+        arm_deep_levels_kernel<<<1, 1, 0, st>>>(g, shallow, cond[0], cond[1], cond[2]);
         ctx->launches += 1;
-        if (L == max_depth || leaf_cap > COM_HUGE) {          // only the deepest level can hold leaves above leaf_cap
-            com_huge_kernel<<<ctx->sm_count, 256, 0, st>>>(g, L, meta, T->part_idx.as<int>(), T->posm, com);
-            ctx->launches += 1;
-        }
+        B200_TRY(if_deep(cond[0], [&](cudaStream_t s) { split_levels(shallow, max_depth, s); }));
+        B200_TRY(if_deep(cond[1], [&](cudaStream_t s) { com_levels(max_depth, shallow, s); }));
+        ctx->launches += com_levels(shallow - 1, 0, st);
+    } else {
+        ctx->launches += com_levels(max_depth, 0, st);
     }
-    // walk-only structures: leaf particles grouped by parent, records with leaf-skipping links
-    int* lscan = T->lscan.as<int>();
-    int* pscan = T->pscan.as<int>();
-    int* tsum = T->leaf_tile_sum.as<int>();
+    // walk-only structures: leaf particles grouped by parent, then the records
     leaf_reduce_kernel<0><<<pgrid, 256, 0, st>>>(g, max_depth, meta, nullptr, tsum);
     leaf_scan_kernel<0><<<1, 1024, 0, st>>>(g, max_depth, tsum);
     leaf_apply_kernel<0><<<pgrid, 256, 0, st>>>(g, max_depth, meta, nullptr, tsum, lscan);
@@ -1926,17 +2018,8 @@ static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st) {
         T->part_pos.as<float4>(), T->leaf_pos.as<float>(), fixed ? 1 : 0);
     pair_pad_kernel<<<pgrid, 256, 0, st>>>(g, max_depth, lscan, pscan, T->leaf_pos.as<float>(), fixed ? 1 : 0);
     ctx->launches += 8;
-    // walk records in depth-first order: ids handed down level by level (nsplit_rank is free after the level loop
-    // and holds them)
-    for (int L = 0; L <= max_depth; ++L) {
-        const double lvl_nodes = (L < 10) ? (double)(1ull << (3 * L)) : 1e30;
-        const size_t nb = (size_t)((lvl_nodes < (double)T->max_nodes) ? lvl_nodes : (double)T->max_nodes);
-        const int grid = (int)((nb + 255) / 256 < (size_t)pgrid ? (nb + 255) / 256 : (size_t)pgrid);
-        pack_level_kernel<<<grid, 256, 0, st>>>(
-            g, L, max_depth, com, meta, lscan, pscan, T->sub.as<int>(), nsr, T->nodes.as<float4>(),
-            T->forest_hdr.p ? T->forest_hdr.as<int>() + FOREST_HDR_INTS * T->part : nullptr);
-        ctx->launches += 1;
-    }
+    ctx->launches += pack_levels(0, deep ? shallow - 1 : max_depth, st);
+    if (deep) B200_TRY(if_deep(cond[2], [&](cudaStream_t s) { pack_levels(shallow, max_depth, s); }));
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }
@@ -2017,9 +2100,11 @@ static int tree_walk_impl(b200_ctx* ctx, const int* list, size_t i0, size_t n_ta
         theta2, eps2, (float*)acc3, g,                                                                           \
         T->forest_root.as<ForestTables>() ? (const ForestTables*)(T->forest_root.as<char>() + 64) : nullptr,     \
         T->forest_root.as<float4>(), by_slot)
-    // Tuning hook (B200_WALK_VARIANT): 0 = two targets per lane, 256-thread CTAs (default: adjacent groups share the
-    // L1; 1.79 ms per 2^20 uniform targets), 1 = the same with 64-thread CTAs (1.83 ms), 2 = EARLY (1.88 ms),
-    // 3 = the one-target kernel (2.00 ms), 4 = two targets, 128-thread CTAs, 72 registers.
+    // Tuning hook (B200_WALK_VARIANT): 0 = two targets per lane, 256-thread CTAs (adjacent groups share the L1;
+    // 1.79 ms per 2^20 uniform targets), 1 = the same with 64-thread CTAs (1.83 ms), 2 = EARLY (1.88 ms),
+    // 3 = the one-target kernel (2.00 ms), 4 = two targets, 128-thread CTAs, 72 registers (1.83 ms).
+    // Tried and removed: persistent warps fed by an SM-local scheduler (a contiguous range of groups per SM, common
+    // pool for the tail) -- L1 hit rate 63 % against 69 %, 1.90 ms; a 48-register build (40 warps per SM) -- 2.11 ms.
     static const int variant = getenv("B200_WALK_VARIANT") ? atoi(getenv("B200_WALK_VARIANT")) : 0;
 #define B200_WALK_HOT(FOREST_)                                                                                   \
     switch (variant) {                                                                                           \
