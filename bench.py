@@ -606,7 +606,8 @@ def c4_summary(eng, D, flush, n, steps, mode):
     sampler.start()
     names = run.phase_names
     acc_ms = {k: [] for k in names}
-    tot = []
+    tot, kern = [], []
+    eng.set_timing(True)                 # the walk kernel's own events (inside b200_tree_walk_dev)
     for _ in range(steps):
         flush.zero_()
         run.poison()
@@ -616,8 +617,18 @@ def c4_summary(eng, D, flush, n, steps, mode):
         a = run.step(a, dt, ev)
         torch.cuda.synchronize()
         tot.append(ev[0].elapsed_time(ev[-1]))
+        kern.append(eng.last_kernel_ms())
         for i, k in enumerate(names):
             acc_ms[k].append(ev[i].elapsed_time(ev[i + 1]))
+    # the same walk once more on its own (tables and target order as the last step left them, L2 flushed, no
+    # collective in front of it): what the kernel costs when nothing else has just used the GPU's memory system
+    alone = []
+    for _ in range(3):
+        flush.zero_()
+        D.sync()
+        run.walk_only()
+        torch.cuda.synchronize()
+        alone.append(eng.last_kernel_ms())
     D.sync()
     sampler.stop()
     step_s = D.max(float(np.sum(tot))) * 1e-3 / steps
@@ -628,6 +639,28 @@ def c4_summary(eng, D, flush, n, steps, mode):
            "scale_factor_after": a}
     for k in names:
         out[k + "_ms"] = D.max(float(np.mean(acc_ms[k])))
+    out["walk_kernel_ms"] = D.max(float(np.mean(kern)))          # the rest of walk_ms: target order (every 8th step), launch
+    out["walk_kernel_ms_min_rank"] = -D.max(-float(np.mean(kern)))
+    out["walk_kernel_alone_ms"] = D.max(float(np.min(alone)))
+    if D.world > 1:                      # per-rank view: which GPU is the slow one, and at what clock
+        mine = {"rank": D.rank, "gpu": D.dev.index, "walk_kernel_ms": float(np.mean(kern)),
+                "walk_kernel_alone_ms": float(np.min(alone)), "sm_mhz": sampler.summary().get("sm_mhz")}
+        if os.environ.get("B200_BENCH_WALK_MATRIX"):       # diagnosis: every rank walks every rank's range on its own
+            row = []
+            for rr in range(D.world):
+                best = 1e30
+                for _ in range(2):
+                    flush.zero_()
+                    D.sync()
+                    eng.tree_walk_dev(run.acc, rr * run.nl, run.nl, theta=0.5)
+                    torch.cuda.synchronize()
+                    best = min(best, eng.last_kernel_ms())
+                row.append(round(best, 3))
+            mine["walk_of_range_ms"] = row
+        per_rank = [None] * D.world
+        dist.all_gather_object(per_rank, mine)
+        out["per_rank"] = per_rank
+    eng.set_timing(False)
     out["clocks"] = sampler.summary()
     peak, _ = hbm_peak()
     out["leapfrog_hbm_frac"] = 68.0 * run.nl / (out["leapfrog_ms"] * 1e-3) / 1e9 / peak if out.get("leapfrog_ms") else None
@@ -665,6 +698,9 @@ class C4Run:
         eng.tree_walk_dev(self.acc, self.lo, self.nl, theta=0.5)
         if ev:
             ev[4].record()
+
+    def walk_only(self):
+        self.eng.tree_walk_dev(self.acc, self.lo, self.nl, theta=0.5)
 
     def step(self, a, dt, ev=None):
         eng = self.eng
@@ -714,7 +750,7 @@ class C4RunSharded:
         self.vel = vel_all[self.lo:self.lo + self.nl].clone()
         del vel_all
         self.acc = torch.zeros((self.nl, 3), dtype=torch.float32, device=D.dev)
-        self.phase_names = ["leapfrog", "allgather", "build", "walk"]
+        self.phase_names = ["leapfrog", "allgather", "build", "publish", "walk"]
         self.mode_text = ("particles stored in Hilbert-curve order fixed at step 0 (contiguous slot shards), arrival order "
                           "= original index order handed to the build; per step: in-place NCCL all-gather of the float4 "
                           "shards, octant-sharded octree build (each rank its own octants of the root) + NCCL exchange of "
@@ -729,13 +765,18 @@ class C4RunSharded:
         if ev:
             ev[2].record()
         eng.tree_build_part_dev(S.posm, self.n, D.rank, D.world, 100.0, 8, 20, arrival=self.arrival)
+        if ev:
+            ev[3].record()
         if D.world > 1:
             eng.tree_forest_publish()
         if ev:
-            ev[3].record()
+            ev[4].record()
         eng.tree_walk_dev(self.acc, self.lo, self.nl, theta=0.5)
         if ev:
-            ev[4].record()
+            ev[5].record()
+
+    def walk_only(self):
+        self.eng.tree_walk_dev(self.acc, self.lo, self.nl, theta=0.5)
 
     def step(self, a, dt, ev=None):
         eng = self.eng

@@ -10,7 +10,9 @@ run() { # name, nproc, args...
 }
 : > $O/scale8.log
 run r2_bench_8gpu 8 --steps 5 --warmup 3
+B200_WALK_VARIANT=4 run r2_bench_8gpu_walk72 8 --steps 3 --warmup 3 --no-c5
 run r2_bench_4gpu 4 --steps 5 --warmup 3 --no-c5
 run r2_bench_2gpu 2 --steps 5 --warmup 3 --no-c5
 tests/host/_bin/shard_test > $O/r2_shard_test_8gpu_box.log 2>&1; echo "shard_test rc=$?" >> $O/scale8.log
-cat $O/scale8.log; tail -12 $O/r2_shard_test_8gpu_box.log
+timeout 600 python -m pytest tests/test_gpu_peer.py -m gpu -x -q > $O/pytest_peer8.log 2>&1; echo "pytest peer rc=$?" >> $O/scale8.log
+cat $O/scale8.log; tail -3 $O/r2_shard_test_8gpu_box.log; tail -3 $O/pytest_peer8.log
