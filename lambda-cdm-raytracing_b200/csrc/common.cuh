@@ -1,6 +1,14 @@
 // common.cuh -- context, error plumbing and small device helpers shared by the
 // sm_100a kernels of libb200grav.so.
 #pragma once
+// -DB200_BOUNDS_CHECK (make check-build): device-side asserts on the indices the tree kernels compute -- the
+// in-tree stand-in for compute-sanitizer, which is not available on the pool (tools/bounds_check.sh).
+#ifdef B200_BOUNDS_CHECK
+#include <assert.h>
+#define B200_DEV_ASSERT(c) assert(c)
+#else
+#define B200_DEV_ASSERT(c) ((void)0)
+#endif
 
 #include <cuda_runtime.h>
 #include <stddef.h>

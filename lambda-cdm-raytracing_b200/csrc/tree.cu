@@ -618,6 +618,7 @@ entry_scatter_kernel(const TreeGlobals* __restrict__ g, int level, const int4* _
                 const int k = ent_node[p];
                 const int child = meta[k].x + d;
                 const int dst = nstart[child] + (int)(cpos - split_cstart[(size_t)nsplit_rank[k] * 8 + d]);
+                B200_DEV_ASSERT(dst >= 0 && dst < g->lv[0].n_entries && child > k);
                 out_idx[dst] = ent_idx[p];
                 out_node[dst] = child;
             }
@@ -703,6 +704,7 @@ com_kernel(const TreeGlobals* __restrict__ g, int level, int4* __restrict__ meta
         int records = 0;             // walk records in this subtree: internal nodes that carry mass (the walk's visits)
         if (have && !big && !huge) {
             if (m.x < 0) {
+                B200_DEV_ASSERT(m.z >= 0 && m.w >= 0 && m.z + m.w <= g->stored_total);
                 for (int q = m.z; q < m.z + m.w; ++q) {
                     const float4 p = posm[part_idx[q]];
                     total = __fadd_rn(total, p.w);
@@ -989,6 +991,7 @@ pack_level_kernel(const TreeGlobals* __restrict__ g, int level, int max_depth, c
             continue;                                               // leaf, or massless (:260): never visited
         }
         const int id = pre[k];
+        B200_DEV_ASSERT(id >= 0 && id + (records > 0 ? records : 1) <= (sub[0] > 0 ? sub[0] : 1));
         int next = id + 1;
 #pragma unroll
         for (int d = 0; d < 8; ++d) {
@@ -1375,6 +1378,7 @@ walk_warp_kernel(const float4* __restrict__ posm, const int* __restrict__ order,
                     if (lcnt > 0) leaf_range(pairs, __float_as_int(mf.y), lcnt, open);
                 }
             }
+            B200_DEV_ASSERT(nk > k && nk <= kend);
             if (!EARLY && nk < kend) ld256(record(nk), cn, mn);
             k = nk;
         };
@@ -1608,6 +1612,7 @@ walk_warp2_kernel(const float4* __restrict__ posm, const int* __restrict__ order
                     if (lcnt > 0) leaf_range(pairs, __float_as_int(mf.y), lcnt, openA, openB, anyA, anyB);
                 }
             }
+            B200_DEV_ASSERT(nk > k && nk <= kend);
             if (!EARLY && nk < kend) ld256(record(nk), cn, mn);
             k = nk;
         };
