@@ -78,6 +78,7 @@ struct TreeState {
     DevBuf leaf_pos, lscan, pscan, leaf_tile_sum;   // leaf sources grouped by parent, pair-interleaved (walk-only)
     DevBuf sub;                   // walk records in the subtree of a node (0: leaf or massless)
     DevBuf slot_node;             // node that stores slot q of part_idx
+    DevBuf slot_digit;            // arrival-order builds: root octant of every storage slot (level 0 reads this, not posm)
     DevBuf globals;
     DevBuf tile_hist, tile_warp_prefix, node_tile_sum;
     DevBuf split_node, split_where, split_local, split_cstart;
@@ -103,9 +104,11 @@ struct TreeState {
     size_t forest_key = 0;        // (posm, arrival, n, box, cap, depth, n_parts) of the forest the slots belong to
     struct ForestSlot {
         DevBuf nodes, leaf_pairs;
+        DevBuf leaf_slot;             // received: storage slot of every leaf source (2 per pair, -1 = padding)
         size_t nn = 0, npairs = 0;
         bool valid = false;
     } forest[8];
+    DevBuf leaf_slot_send;        // this part's leaf sources as storage slots: what the parts exchange (4 B, not 16 B)
     DevBuf forest_root;           // {global centre of mass, M} {-, -, root edge, -}
     DevBuf forest_hdr;            // device: int2 {nodes, source pairs} per part
     int* forest_hdr_host = nullptr;   // pinned mirror
@@ -119,7 +122,7 @@ struct TreeState {
         mix(bb); mix(eb);
         const DevBuf* all[] = {&center, &com, &meta, &nstart, &ncount, &nsplit_rank, &ent_idx[0], &ent_idx[1],
                                &ent_node[0], &ent_node[1], &digit, &part_idx, &part_pos, &nodes, &leaf_pos,
-                               &lscan, &pscan, &sub, &leaf_tile_sum, &slot_node, &globals, &tile_hist,
+                               &lscan, &pscan, &sub, &leaf_tile_sum, &slot_node, &slot_digit, &globals, &tile_hist,
                                &tile_warp_prefix, &node_tile_sum, &split_node, &split_where, &split_local,
                                &split_cstart};
         for (const DevBuf* b : all) mix((size_t)b->p);
@@ -133,15 +136,15 @@ struct TreeState {
         drop_graph();
         if (body_stream) cudaStreamDestroy(body_stream);
         body_stream = nullptr;
-        for (ForestSlot& f : forest) { f.nodes.release(); f.leaf_pairs.release(); f.valid = false; }
-        forest_root.release(); forest_hdr.release();
+        for (ForestSlot& f : forest) { f.nodes.release(); f.leaf_pairs.release(); f.leaf_slot.release(); f.valid = false; }
+        forest_root.release(); forest_hdr.release(); leaf_slot_send.release();
         if (forest_hdr_host) cudaFreeHost(forest_hdr_host);
         forest_hdr_host = nullptr;
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_out) cudaEventDestroy(ev_out);
         ev_in = ev_out = nullptr;
         DevBuf* all[] = {&center, &com, &meta, &nstart, &ncount, &nsplit_rank, &ent_idx[0],
-                         &ent_idx[1], &ent_node[0], &ent_node[1], &digit, &part_idx, &part_pos, &nodes, &leaf_pos, &lscan, &pscan, &sub, &leaf_tile_sum, &slot_node,
+                         &ent_idx[1], &ent_node[0], &ent_node[1], &digit, &part_idx, &part_pos, &nodes, &leaf_pos, &lscan, &pscan, &sub, &leaf_tile_sum, &slot_node, &slot_digit,
                          &globals, &tile_hist, &tile_warp_prefix, &node_tile_sum, &split_node,
                          &split_where, &split_local, &split_cstart, &keys, &keys_sorted, &perm,
                          &sort_scratch, &order};
@@ -394,6 +397,20 @@ __device__ __forceinline__ int entry_index(int tile, int warp, int row, int lane
     return tile * ENT_TILE + warp * (32 * ET_ITEMS) + row * 32 + lane;
 }
 
+// Arrival-order builds (particles stored along a space-filling curve, inserted in their original index order): at
+// level 0 every entry is a random slot, and gathering its float4 from a 2^24-particle array costs a DRAM sector per
+// entry (0.32 ms of a 1.1 ms part build).  One coalesced pass writes the root octant of every SLOT as a byte; the
+// 16 MB table stays in L2 and level 0 gathers from there.
+__global__ void __launch_bounds__(256)
+slot_digit_kernel(const float4* __restrict__ posm, int n, const float4* __restrict__ center,
+                  unsigned char* __restrict__ slot_digit) {
+    const float4 c = center[0];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 x = posm[i];
+        slot_digit[i] = (unsigned char)((x.x > c.x ? 1 : 0) | (x.y > c.y ? 2 : 0) | (x.z > c.z ? 4 : 0));   // :188-194
+    }
+}
+
 __device__ __forceinline__ unsigned digit_mask(unsigned bv, unsigned b0, unsigned b1, unsigned b2, int d) {
     return bv & ((d & 1) ? b0 : ~b0) & ((d & 2) ? b1 : ~b1) & ((d & 4) ? b2 : ~b2);
 }
@@ -407,7 +424,7 @@ entry_digit_kernel(const TreeGlobals* __restrict__ g, int level, int keep, unsig
                    int* __restrict__ part_idx, int* __restrict__ slot_node,
                    unsigned* __restrict__ tile_hist,
                    unsigned* __restrict__ tile_warp_prefix, int* __restrict__ split_where,
-                   unsigned* __restrict__ split_local) {
+                   unsigned* __restrict__ split_local, const unsigned char* __restrict__ slot_digit) {
     __shared__ unsigned wtot[ET_WARPS][8];
     const LevelInfo L = g->lv[level];
     const int n_ent = L.n_entries;
@@ -430,9 +447,13 @@ entry_digit_kernel(const TreeGlobals* __restrict__ g, int level, int keep, unsig
                     part_idx[m.z + rel] = idx;          // leaf member, or orphan of a split node
                     slot_node[m.z + rel] = k;
                 } else {
-                    const float4 c = center[k];
-                    const float4 x = posm[idx];
-                    d = (x.x > c.x ? 1 : 0) | (x.y > c.y ? 2 : 0) | (x.z > c.z ? 4 : 0);   // :188-194
+                    if (slot_digit != nullptr) {           // level 0 of an arrival-order build
+                        d = slot_digit[idx];
+                    } else {
+                        const float4 c = center[k];
+                        const float4 x = posm[idx];
+                        d = (x.x > c.x ? 1 : 0) | (x.y > c.y ? 2 : 0) | (x.z > c.z ? 4 : 0);   // :188-194
+                    }
                     if (rel == keep) { first_live = true; sr = nsplit_rank[k]; }
                     // part build: a particle bound for an octant another part owns leaves the build here (the
                     // root's child of that octant stays an empty leaf in this part's tree)
@@ -1005,6 +1026,31 @@ pack_level_kernel(const TreeGlobals* __restrict__ g, int level, int max_depth, c
         nodes[2 * id] = com[k];
         nodes[2 * id + 1] = make_float4(__int_as_float(skip), __int_as_float(loff), __int_as_float(m.w),
                                         __int_as_float(lcnt));      // m.w of an internal node = cell edge bits
+    }
+}
+
+// The parts of a forest exchange their leaf sources as STORAGE SLOTS, not as positions: every rank holds all
+// positions already (the all-gather that precedes the build), so 4 bytes per source cross NVLink instead of 16, and
+// each rank rebuilds the pair rows of the other parts with one gather pass.  A leaf range's particles are spatial
+// neighbours and the particles are stored along a Hilbert curve, so that gather is coherent.
+// leaf_pairs: pair p = {x0 x1 y0 y1} {z0 z1 w0 w1}; w = slot bits (the faithful tree), -1 = padding.
+__global__ void __launch_bounds__(256)
+leaf_slots_kernel(const float* __restrict__ leaf_pairs, int n_pairs, int2* __restrict__ slots) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += gridDim.x * blockDim.x) {
+        const float2 w = *reinterpret_cast<const float2*>(leaf_pairs + (size_t)p * 8 + 6);
+        slots[p] = make_int2(__float_as_int(w.x), __float_as_int(w.y));
+    }
+}
+__global__ void __launch_bounds__(256)
+leaf_expand_kernel(const int2* __restrict__ slots, int n_pairs, const float4* __restrict__ posm,
+                   float4* __restrict__ leaf_pairs) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += gridDim.x * blockDim.x) {
+        const int2 s = slots[p];
+        const float far = 1.0e18f;                            // pair_pad_kernel's padding source
+        const float4 a = s.x >= 0 ? posm[s.x] : make_float4(far, far, far, 0.f);
+        const float4 b = s.y >= 0 ? posm[s.y] : make_float4(far, far, far, 0.f);
+        leaf_pairs[2 * (size_t)p] = make_float4(a.x, b.x, a.y, b.y);
+        leaf_pairs[2 * (size_t)p + 1] = make_float4(a.z, b.z, __int_as_float(s.x), __int_as_float(s.y));
     }
 }
 
@@ -1816,6 +1862,7 @@ static int tree_build_impl(b200_ctx* ctx, const void* posm4, const int* arrival,
     B200_TRY(T->leaf_pos.reserve((n + T->max_split + 2) * sizeof(float4)));     // pair layout: <= 1 pad slot per parent
     B200_TRY(T->pscan.reserve((T->max_split + 2) * sizeof(int)));
     B200_TRY(T->slot_node.reserve(n * sizeof(int)));
+    if (arrival != nullptr) B200_TRY(T->slot_digit.reserve(n));
     B200_TRY(T->lscan.reserve((T->max_nodes + 1) * sizeof(int)));
     B200_TRY(T->sub.reserve((T->max_nodes + 1) * sizeof(int)));
     B200_TRY(T->leaf_tile_sum.reserve(T->max_node_tiles * sizeof(int)));
@@ -1920,7 +1967,8 @@ static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st, bool condi
                 g, L, keep, T->oct_mask, T->posm, center, meta, nstart, nsr, T->ent_idx[cur].as<int>(),
                 T->ent_node[cur].as<int>(), T->digit.as<unsigned char>(), T->part_idx.as<int>(),
                 T->slot_node.as<int>(), T->tile_hist.as<unsigned>(), T->tile_warp_prefix.as<unsigned>(), T->split_where.as<int>(),
-                T->split_local.as<unsigned>());
+                T->split_local.as<unsigned>(),
+                (L == 0 && T->arrival != nullptr) ? T->slot_digit.as<unsigned char>() : nullptr);
             tile_scan_kernel<<<8, 1024, 0, s>>>(g, L, T->tile_hist.as<unsigned>());
             make_children_kernel<<<sgrid, 256, 0, s>>>(g, L, T->split_node.as<int>(), T->split_where.as<int>(),
                                                        T->split_local.as<unsigned>(), T->tile_hist.as<unsigned>(),
@@ -2012,6 +2060,10 @@ static int tree_enqueue(b200_ctx* ctx, TreeState* T, cudaStream_t st, bool condi
     tree_init_kernel<<<pgrid, 256, 0, st>>>(g, center, com, meta, nstart, ncount, T->ent_idx[0].as<int>(),
                                             T->ent_node[0].as<int>(), (int)n, box, fixed ? 1 : 0, T->arrival);
     ctx->launches += 1;
+    if (T->arrival != nullptr) {
+        slot_digit_kernel<<<pgrid, 256, 0, st>>>(T->posm, (int)n, center, T->slot_digit.as<unsigned char>());
+        ctx->launches += 1;
+    }
     ctx->launches += split_levels(0, deep ? shallow - 1 : max_depth, st);
     B200_CUDA(cudaGetLastError());
     if (deep) {
@@ -2184,7 +2236,8 @@ __global__ void set_forest_kernel(ForestTables F, ForestTables* dst) { *dst = F;
 
 // Makes this part's walk tables (node records, leaf offsets, leaf source pairs) available to every walker:
 // with a communicator of n_parts ranks (b200_shard_init) the parts exchange their tables over NCCL -- sizes first
-// (one 160-byte all-gather and a host read-back), then one grouped broadcast per table and owner; without one (a
+// (one 160-byte all-gather and a host read-back), then one grouped broadcast per table and owner -- node records
+// and the leaf sources as storage slots, from which every rank rebuilds the pair rows locally; without one (a
 // single process building the parts one after another) the tables are copied into this context's slot.
 // When all slots are current the merged root record and the table directory are written.
 int tree_forest_publish(b200_ctx* ctx, cudaStream_t st) {
@@ -2207,6 +2260,12 @@ int tree_forest_publish(b200_ctx* ctx, cudaStream_t st) {
         B200_CUDA(cudaMemcpy(&err, &g->error, sizeof(int), cudaMemcpyDeviceToHost));
         if (err) return B200_ERR_NOMEM;
     }
+    // this part's leaf sources as slots
+    const size_t own_pairs = (size_t)T->forest_hdr_host[FOREST_HDR_INTS * part + 1];
+    B200_TRY(T->leaf_slot_send.reserve((own_pairs + 1) * sizeof(int2)));
+    const int xgrid = ctx->sm_count * 8;
+    leaf_slots_kernel<<<xgrid, 256, 0, st>>>(T->leaf_pos.as<float>(), (int)own_pairs, T->leaf_slot_send.as<int2>());
+    ctx->launches += 1;
     const void* send[24]; void* recv[24]; size_t bytes[24]; int root[24];
     int items = 0;
     for (int q = 0; q < P; ++q) {
@@ -2217,9 +2276,10 @@ int tree_forest_publish(b200_ctx* ctx, cudaStream_t st) {
         if (f.nn < 1) return B200_ERR_STATE;
         B200_TRY(f.nodes.reserve((f.nn + 1) * 2 * sizeof(float4)));       // + the record of padding the walk may read
         B200_TRY(f.leaf_pairs.reserve((f.npairs + 1) * 2 * sizeof(float4)));
-        const void* src[2] = {T->nodes.p, T->leaf_pos.p};
-        void* dst[2] = {f.nodes.p, f.leaf_pairs.p};
-        const size_t sz[2] = {f.nn * 2 * sizeof(float4), f.npairs * 2 * sizeof(float4)};
+        B200_TRY(f.leaf_slot.reserve((f.npairs + 1) * sizeof(int2)));
+        const void* src[2] = {T->nodes.p, T->leaf_slot_send.p};
+        void* dst[2] = {f.nodes.p, f.leaf_slot.p};
+        const size_t sz[2] = {f.nn * 2 * sizeof(float4), f.npairs * sizeof(int2)};
         for (int k = 0; k < 2; ++k) { send[items] = src[k]; recv[items] = dst[k]; bytes[items] = sz[k]; root[items] = q; ++items; }
     }
     if (collective) {
@@ -2230,6 +2290,20 @@ int tree_forest_publish(b200_ctx* ctx, cudaStream_t st) {
             if (bytes[k]) B200_CUDA(cudaMemcpyAsync(recv[k], send[k], bytes[k], cudaMemcpyDeviceToDevice, st));
         T->forest[part].valid = true;
     }
+    // pair rows of the received parts from the positions this rank holds (its own part, in a collective publish:
+    // a copy of the rows it built)
+    for (int q = 0; q < P; ++q) {
+        if (!collective && q != part) continue;
+        TreeState::ForestSlot& f = T->forest[q];
+        if (f.npairs == 0) continue;
+        if (collective && q == part) {
+            B200_CUDA(cudaMemcpyAsync(f.leaf_pairs.p, T->leaf_pos.p, f.npairs * 2 * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+        } else {
+            leaf_expand_kernel<<<xgrid, 256, 0, st>>>(f.leaf_slot.as<int2>(), (int)f.npairs, T->posm, f.leaf_pairs.as<float4>());
+            ctx->launches += 1;
+        }
+    }
+    B200_CUDA(cudaGetLastError());
     ctx->launches += 0;
     bool all = true;
     for (int q = 0; q < P; ++q) all = all && T->forest[q].valid;
