@@ -92,6 +92,36 @@ def test_tree_edge_cases_bit_exact(engine, oracle, cap, depth):
         assert np.array_equal(t[k], getattr(o, k)), k
 
 
+def test_tree_graph_replay_shallow_deep_shallow(engine, oracle):
+    """The build graph runs the levels a uniform tree never reaches only through IF nodes armed on the device
+    (tree.cu: arm_deep_levels_kernel).  One cached graph (same buffers, sizes, parameters) is replayed on a shallow
+    tree, on a 21-level one (the [0, box) convention: an eighth of the particles pile up in one corner chain) and on a
+    shallow one again: every build must be the reference's tree, and the forces of the last must not see leftovers
+    of the deep build."""
+    import torch
+    n = 40000
+    shallow = uniform_np(n, seed=77)
+    deep = uniform_np(n, seed=78, lo=0.0, hi=100.0)
+    m = np.ones(n, np.float32)
+    posm = _posm(shallow, m)
+    acc = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    depths = []
+    for pos in (shallow, deep, shallow):
+        posm[:, :3] = torch.from_numpy(pos).cuda()
+        engine.tree_build_dev(posm, n, 100.0, 8, 20)           # same pointer, n, parameters: the cached graph
+        torch.cuda.synchronize()
+        t = engine.tree_export()
+        o = oracle.tree_build(pos, m)
+        for k in TREE_KEYS:
+            assert np.array_equal(t[k], getattr(o, k)), k
+        depths.append(engine.tree_stats()["depth"])
+        engine.tree_walk_dev(acc, 0, n, theta=0.5)
+        torch.cuda.synchronize()
+        ref = oracle.tree_forces(o, pos, 0.5, i0=0, n_targets=2048)
+        assert rel_l2(acc[:2048].cpu().numpy(), ref) < TOL_TREE
+    assert depths[0] < 12 and depths[1] == 21 and depths[2] == depths[0]
+
+
 @pytest.mark.parametrize("gen", ["uniform", "box", "clustered"])
 def test_tree_forces_and_counters_vs_oracle(engine, oracle, gen):
     import torch
