@@ -10,7 +10,6 @@ run() { # name, nproc, args...
 }
 : > $O/scale8.log
 run r2_bench_8gpu 8 --steps 5 --warmup 3
-B200_WALK_VARIANT=4 run r2_bench_8gpu_walk72 8 --steps 3 --warmup 3 --no-c5
 run r2_bench_4gpu 4 --steps 5 --warmup 3 --no-c5
 run r2_bench_2gpu 2 --steps 5 --warmup 3 --no-c5
 tests/host/_bin/shard_test > $O/r2_shard_test_8gpu_box.log 2>&1; echo "shard_test rc=$?" >> $O/scale8.log
