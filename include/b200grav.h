@@ -227,7 +227,9 @@ int b200_tree_forces_fixed_host(b200_ctx* ctx, const float* pos3, const float* m
  *
  * b200_tree_forest_publish makes the part's walk tables visible to all walkers: over NCCL when the context has a
  * communicator of exactly n_parts ranks with rank == part (b200_shard_init; collective: table sizes and level-1 centres of mass by a 160-byte
- * all-gather + host read-back, then one grouped broadcast per table and owner), otherwise into this context's own
+ * all-gather + host read-back, then two all-gathers of equal-sized slices: the node records and the leaf sources as
+ * 4-byte storage slots, from which every rank rebuilds the other parts' pair rows out of the positions it holds --
+ * posm4 must be the same complete array on every rank), otherwise into this context's own
  * slot (one process building the parts in turn -- it must rebuild and publish EVERY part after particles move).
  * When every part is current the root's centre of mass is merged from the parts' level-1 nodes in the
  * reference's order and rounding.  After that b200_tree_walk_dev / b200_tree_walk_list_dev on this context walk

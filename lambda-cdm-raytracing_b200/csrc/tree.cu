@@ -105,10 +105,13 @@ struct TreeState {
     struct ForestSlot {
         DevBuf nodes, leaf_pairs;
         DevBuf leaf_slot;             // received: storage slot of every leaf source (2 per pair, -1 = padding)
+        const float4* nodes_at = nullptr;      // where this part's records are: `nodes`, or its slice of the all-gather slab
+        const int2* slots_at = nullptr;
         size_t nn = 0, npairs = 0;
         bool valid = false;
     } forest[8];
     DevBuf leaf_slot_send;        // this part's leaf sources as storage slots: what the parts exchange (4 B, not 16 B)
+    DevBuf nodes_slab, slots_slab;    // collective publish: all parts' records / slots, one equal-sized slice per part
     DevBuf forest_root;           // {global centre of mass, M} {-, -, root edge, -}
     DevBuf forest_hdr;            // device: int2 {nodes, source pairs} per part
     int* forest_hdr_host = nullptr;   // pinned mirror
@@ -137,7 +140,7 @@ struct TreeState {
         if (body_stream) cudaStreamDestroy(body_stream);
         body_stream = nullptr;
         for (ForestSlot& f : forest) { f.nodes.release(); f.leaf_pairs.release(); f.leaf_slot.release(); f.valid = false; }
-        forest_root.release(); forest_hdr.release(); leaf_slot_send.release();
+        forest_root.release(); forest_hdr.release(); leaf_slot_send.release(); nodes_slab.release(); slots_slab.release();
         if (forest_hdr_host) cudaFreeHost(forest_hdr_host);
         forest_hdr_host = nullptr;
         if (ev_in) cudaEventDestroy(ev_in);
@@ -998,9 +1001,10 @@ pack_level_kernel(const TreeGlobals* __restrict__ g, int level, int max_depth, c
         if (hdr && k >= 1 && k <= 8) reinterpret_cast<float4*>(hdr + 8)[k - 1] = com[k];   // forest: root merge input
         if (k == 0) {
             const int nn = tree_node_count(g, max_depth);
-            if (hdr) {                                              // sizes of this part's walk tables
+            if (hdr) {                                              // sizes of this part's walk tables, overflow flag
                 hdr[0] = records > 0 ? records : 1;
                 hdr[1] = nn > 1 ? pscan[(nn - 1) / 8] : (lscan[1] + 1) / 2;
+                hdr[2] = g->error;
             }
             if (m.x < 0) {                                          // the whole tree is one leaf
                 nodes[0] = com[0];
@@ -2236,8 +2240,8 @@ __global__ void set_forest_kernel(ForestTables F, ForestTables* dst) { *dst = F;
 
 // Makes this part's walk tables (node records, leaf offsets, leaf source pairs) available to every walker:
 // with a communicator of n_parts ranks (b200_shard_init) the parts exchange their tables over NCCL -- sizes first
-// (one 160-byte all-gather and a host read-back), then one grouped broadcast per table and owner -- node records
-// and the leaf sources as storage slots, from which every rank rebuilds the pair rows locally; without one (a
+// (one 160-byte all-gather and a host read-back), then two all-gathers of equal-sized slices -- node records and the
+// leaf sources as storage slots, from which every rank rebuilds the pair rows locally; without one (a
 // single process building the parts one after another) the tables are copied into this context's slot.
 // When all slots are current the merged root record and the table directory are written.
 int tree_forest_publish(b200_ctx* ctx, cudaStream_t st) {
@@ -2254,41 +2258,53 @@ int tree_forest_publish(b200_ctx* ctx, cudaStream_t st) {
     if (collective) B200_TRY(shard_allgather_bytes(ctx, hdr + FOREST_HDR_INTS * part, hdr, HDR_BYTES, st));
     B200_CUDA(cudaMemcpyAsync(T->forest_hdr_host, hdr, 8 * HDR_BYTES, cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
-    {
-        TreeGlobals* g = T->globals.as<TreeGlobals>();
-        int err = 0;
-        B200_CUDA(cudaMemcpy(&err, &g->error, sizeof(int), cudaMemcpyDeviceToHost));
-        if (err) return B200_ERR_NOMEM;
+    size_t max_nn = 1, max_pairs = 1;
+    for (int q = 0; q < P; ++q) {
+        if (!collective && q != part) continue;
+        const int* h = T->forest_hdr_host + FOREST_HDR_INTS * q;
+        if (h[2]) return B200_ERR_NOMEM;                                  // a part ran out of node slots
+        if (h[0] < 1) return B200_ERR_STATE;
+        max_nn = (size_t)h[0] > max_nn ? (size_t)h[0] : max_nn;
+        max_pairs = (size_t)h[1] > max_pairs ? (size_t)h[1] : max_pairs;
     }
     // this part's leaf sources as slots
     const size_t own_pairs = (size_t)T->forest_hdr_host[FOREST_HDR_INTS * part + 1];
-    B200_TRY(T->leaf_slot_send.reserve((own_pairs + 1) * sizeof(int2)));
+    B200_TRY(T->leaf_slot_send.reserve((max_pairs + 1) * sizeof(int2)));
     const int xgrid = ctx->sm_count * 8;
     leaf_slots_kernel<<<xgrid, 256, 0, st>>>(T->leaf_pos.as<float>(), (int)own_pairs, T->leaf_slot_send.as<int2>());
     ctx->launches += 1;
-    const void* send[24]; void* recv[24]; size_t bytes[24]; int root[24];
-    int items = 0;
-    for (int q = 0; q < P; ++q) {
-        if (!collective && q != part) continue;
-        TreeState::ForestSlot& f = T->forest[q];
-        f.nn = (size_t)T->forest_hdr_host[FOREST_HDR_INTS * q];            // walk records (internal nodes)
-        f.npairs = (size_t)T->forest_hdr_host[FOREST_HDR_INTS * q + 1];
-        if (f.nn < 1) return B200_ERR_STATE;
+    if (collective) {
+        // two all-gathers of equal-sized slices (the largest part's sizes; what lies behind a part's own size is
+        // never read) instead of one broadcast per table and owner: NCCL's best-performing collective, one launch each
+        const size_t node_stride = (max_nn + 1) * 2 * sizeof(float4);     // + the record of padding the walk may read
+        const size_t slot_stride = max_pairs * sizeof(int2);
+        if (node_stride > T->nodes.bytes) return B200_ERR_STATE;           // cannot happen: records <= n / leaf_cap + 1
+        B200_TRY(T->nodes_slab.reserve(P * node_stride));
+        B200_TRY(T->slots_slab.reserve(P * slot_stride));
+        B200_TRY(shard_allgather_bytes(ctx, T->nodes.p, T->nodes_slab.p, node_stride, st));
+        B200_TRY(shard_allgather_bytes(ctx, T->leaf_slot_send.p, T->slots_slab.p, slot_stride, st));
+        for (int q = 0; q < P; ++q) {
+            TreeState::ForestSlot& f = T->forest[q];
+            f.nn = (size_t)T->forest_hdr_host[FOREST_HDR_INTS * q];
+            f.npairs = (size_t)T->forest_hdr_host[FOREST_HDR_INTS * q + 1];
+            f.nodes_at = reinterpret_cast<const float4*>(T->nodes_slab.as<char>() + q * node_stride);
+            f.slots_at = reinterpret_cast<const int2*>(T->slots_slab.as<char>() + q * slot_stride);
+            B200_TRY(f.leaf_pairs.reserve((f.npairs + 1) * 2 * sizeof(float4)));
+            f.valid = true;
+        }
+    } else {
+        TreeState::ForestSlot& f = T->forest[part];
+        f.nn = (size_t)T->forest_hdr_host[FOREST_HDR_INTS * part];        // walk records (internal nodes)
+        f.npairs = own_pairs;
         B200_TRY(f.nodes.reserve((f.nn + 1) * 2 * sizeof(float4)));       // + the record of padding the walk may read
         B200_TRY(f.leaf_pairs.reserve((f.npairs + 1) * 2 * sizeof(float4)));
         B200_TRY(f.leaf_slot.reserve((f.npairs + 1) * sizeof(int2)));
-        const void* src[2] = {T->nodes.p, T->leaf_slot_send.p};
-        void* dst[2] = {f.nodes.p, f.leaf_slot.p};
-        const size_t sz[2] = {f.nn * 2 * sizeof(float4), f.npairs * sizeof(int2)};
-        for (int k = 0; k < 2; ++k) { send[items] = src[k]; recv[items] = dst[k]; bytes[items] = sz[k]; root[items] = q; ++items; }
-    }
-    if (collective) {
-        B200_TRY(shard_bcast_group(ctx, items, send, recv, bytes, root, st));
-        for (int q = 0; q < P; ++q) T->forest[q].valid = true;
-    } else {
-        for (int k = 0; k < items; ++k)
-            if (bytes[k]) B200_CUDA(cudaMemcpyAsync(recv[k], send[k], bytes[k], cudaMemcpyDeviceToDevice, st));
-        T->forest[part].valid = true;
+        B200_CUDA(cudaMemcpyAsync(f.nodes.p, T->nodes.p, f.nn * 2 * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+        if (f.npairs)
+            B200_CUDA(cudaMemcpyAsync(f.leaf_slot.p, T->leaf_slot_send.p, f.npairs * sizeof(int2), cudaMemcpyDeviceToDevice, st));
+        f.nodes_at = f.nodes.as<float4>();
+        f.slots_at = f.leaf_slot.as<int2>();
+        f.valid = true;
     }
     // pair rows of the received parts from the positions this rank holds (its own part, in a collective publish:
     // a copy of the rows it built)
@@ -2299,7 +2315,7 @@ int tree_forest_publish(b200_ctx* ctx, cudaStream_t st) {
         if (collective && q == part) {
             B200_CUDA(cudaMemcpyAsync(f.leaf_pairs.p, T->leaf_pos.p, f.npairs * 2 * sizeof(float4), cudaMemcpyDeviceToDevice, st));
         } else {
-            leaf_expand_kernel<<<xgrid, 256, 0, st>>>(f.leaf_slot.as<int2>(), (int)f.npairs, T->posm, f.leaf_pairs.as<float4>());
+            leaf_expand_kernel<<<xgrid, 256, 0, st>>>(f.slots_at, (int)f.npairs, T->posm, f.leaf_pairs.as<float4>());
             ctx->launches += 1;
         }
     }
@@ -2312,7 +2328,7 @@ int tree_forest_publish(b200_ctx* ctx, cudaStream_t st) {
         memset(&F, 0, sizeof F);
         F.n_parts = P;
         for (int q = 0; q < P; ++q) {
-            F.nodes[q] = T->forest[q].nodes.as<float4>();
+            F.nodes[q] = T->forest[q].nodes_at;
             F.leaf_pairs[q] = T->forest[q].leaf_pairs.as<ulonglong2>();
             for (int d = q * 8 / P; d < (q + 1) * 8 / P; ++d) F.owner[d] = q;
         }
