@@ -17,10 +17,19 @@ positions with NCCL and every rank evaluates its N/G targets against all sources
            timed region).  This is the number to hold against --impl reference.
 `roofline`: dominant kernel (direct_kernel) against the FP32 FMA peak measured
            in this run by an FFMA probe (MEASURED_PEAKS.json has no FP32 figure).
-`tree_summary`: (default direct run on 1 GPU) a short Barnes-Hut measurement on the same particles --
-           ms per build + walk step, interactions/s, particle-steps/s; `--workload tree` gives the full
-           line (roofline with ncu traffic, e2e, CPU reference tree), `--ic zeldovich` / `--order morton`
-           other inputs, `--kdk` full leapfrog steps.
+Sub-lines of the default run, at every N, each ending in its own `parity_check` (a 1 024-target sample per rank
+against the CPU oracle; non-local rows are NaN-poisoned before every gather, so a broken exchange cannot pass):
+`tree_summary`  BASELINE configs[2]: TreeForceComputer theta = 0.5, leaf 8, the same 2^20 particles -- ms per build +
+           walk, interactions/s, roofline = issue fraction + LSU write-back fraction + lane utilisation of the walk.
+`tree_box_convention_summary`  the same with positions in [0, 100)^3 (what the reference's generators emit).
+`c4_summary`    configs[3]: 2^24-particle Lambda-CDM KDK steps (random index order): Hilbert-stored particles, octant-
+           sharded build, table exchange, forest walk; phases leapfrog / allgather / build / publish / walk as the max
+           over ranks, the walk kernel's own time, per-rank list.  `c4_summary_replicated_build`: the round-1 scheme.
+`c5_summary`    configs[4]: 2^23-particle direct sum (--no-c5 skips it: 24 s on one GPU).
+`c1_summary`    configs[0]: 16 384 particles x 10 KDK steps, device-resident.
+`leapfrog_roofline`  the fused kick-kick-drift pass at 2^24 / N particles against the measured HBM peak.
+`--workload tree` makes the Barnes-Hut step the main line (e2e, CPU reference tree); `--ic zeldovich`,
+`--order morton`, `--kdk`, `--c4-mode replicated`, `--sources peer` select other inputs / schemes.
 `cpu_baseline` / --impl reference: the reference's own CPU direct sum
            (oracle/_ref = /root/reference sources compiled in place; falls back
            to the restated port) on all host cores, bounded sample.
