@@ -52,7 +52,12 @@ int b200_abi_version(void);
  * (src/forces/barnes_hut_tree.cu:343-381), LambdaCDMSimulationImpl ctor/dtor
  * (src/physics/lambda_cdm_impl.cu:80-145).  device = ForceComputeParameters::
  * cuda_device_id (include/forces/force_computer_factory.hpp:39).  Scratch
- * grows on demand; max_particles is a sizing hint (0 = grow lazily). */
+ * grows on demand; max_particles is a sizing hint (0 = grow lazily).
+ *
+ * Concurrency: ONE call in flight per context.  The "_dev" entry points accept any stream, but they share the
+ * context's scratch (source tiles, partial sums, the equal-mass flag, tree tables, the target order), so a second
+ * call must be ordered after the first -- same stream, or an event between the two; a tree walk goes on the stream
+ * its build was given.  Independent work runs on independent contexts (one per GPU, or several per GPU). */
 int b200_ctx_create(int device, size_t max_particles, b200_ctx** out);
 int b200_ctx_destroy(b200_ctx* ctx);
 int b200_ctx_device(const b200_ctx* ctx);
