@@ -187,9 +187,12 @@ def cpu_kind():
 def _cpu_sample(workload):
     if workload == "direct":
         return DIRECT_SAMPLE, None, ("the reference CPU direct sum (TreeForceComputer, leaf_capacity>N => leaf "
-                                     "pair loop)")
+                                     "pair loop; its own sources built -O2 -ffp-contract=off by oracle/Makefile, "
+                                     "the bit-reproducible flags of the parity oracle, not the reference's -O3 "
+                                     "-march=native)")
     return TREE_SAMPLE, _tree_sample_interactions(TREE_SAMPLE), ("the reference CPU TreeForceComputer "
-                                                                 "(theta 0.5, leaf 8: build + walk)")
+                                                                 "(theta 0.5, leaf 8: build + walk; its own sources "
+                                                                 "built -O2 -ffp-contract=off by oracle/Makefile)")
 
 
 def run_cpu_baseline(workload="direct", target_seconds=12.0):
