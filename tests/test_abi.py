@@ -104,3 +104,16 @@ def test_ic_params_layout_matches_header(tmp_path):
     lib.b200_ic_params_default(C.byref(p))
     assert (p.box, p.z_initial, p.seed, p.use_2lpt) == (100.0, 49.0, 12345, 0)
     assert (p.omega_m, p.omega_lambda, p.omega_k, p.h, p.sigma_8, p.n_s) == (0.31, 0.69, 0.0, 0.67, 0.81, 0.965)
+
+
+def test_cpp_example_fails_loudly_without_gpu():
+    """The C++ product path (B200LambdaCDMSimulation behind examples/nbody_b200) has no CPU fallback either: on a box
+    without a GPU it must exit non-zero with a clear message, not produce numbers."""
+    import subprocess
+    import torch
+    exe = os.path.join(ROOT, "lambda-cdm-raytracing_b200", "examples", "_bin", "nbody_b200")
+    if torch.cuda.is_available() or not os.path.exists(exe):
+        pytest.skip("needs a GPU-less box and the built example")
+    r = subprocess.run([exe, "1000", "2", "tree"], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0
+    assert "no CPU fallback" in (r.stdout + r.stderr)
